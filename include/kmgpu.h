@@ -1,0 +1,204 @@
+/*
+ * kmgpu.h — C ABI of the B200-native k-mer ingestion backend for khmer's sketches.
+ *
+ * This is the drop-in boundary: a storage backend that sits behind liboxli's
+ * oxli::Storage / oxli::Hashtable interface (reference: include/oxli/storage.hh:56-78,
+ * include/oxli/hashtable.hh:127-433).  Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point names the reference interface it replaces.  A handle is one sketch
+ * (N tables + counters) resident in the HBM of one GPU.
+ *
+ * Conventions
+ *   - All functions return 0 on success or a KMGPU_E* code; kmgpu_last_error() gives the
+ *     thread-local message (the C++ host layer rethrows it as oxli_exception /
+ *     oxli_file_exception, khmer/_oxli/oxli_exception_convert.cc:9-31).
+ *   - Handles are internally locked: several host threads may call into the same handle
+ *     (the reference's scripts run T threads in consume_seqfile on one table,
+ *     scripts/load-into-counting.py:145-158); calls are applied in arrival order and each
+ *     call is applied as if its k-mers were consumed one after another in stream order —
+ *     results equal the reference at ONE thread, bit for bit.
+ *   - "reads" are passed as one concatenated ASCII buffer plus offsets[n_reads + 1]
+ *     (read r = seqs[offsets[r] .. offsets[r+1])), all HOST pointers unless a function
+ *     says otherwise.
+ *   - There is no CPU fallback: without a CUDA device every call fails with KMGPU_ENODEV.
+ */
+#ifndef KMGPU_H
+#define KMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMGPU_ABI_VERSION 1
+
+/* storage kinds — include/oxli/storage.hh: ByteStorage :480, NibbleStorage :241, BitStorage :92 */
+enum { KMGPU_BYTE = 0, KMGPU_NIBBLE = 1, KMGPU_BIT = 2 };
+/* hash kinds — TwoBitKmerHashIterator (_hash, src/oxli/kmer_hash.cc:65-95, k <= 32) and
+ * MurmurKmerHashIterator (_hash_murmur, src/oxli/kmer_hash.cc:177-198) */
+enum { KMGPU_TWOBIT = 0, KMGPU_MURMUR = 1 };
+
+/* flags for sequence inputs */
+#define KMGPU_CLEAN 1u /* bulk-loader cleaning: ACGT kept, acgt upper-cased, anything else 'A'
+                          (Read::set_clean_seq, include/oxli/read_parsers.hh:128-133).  Without it
+                          sequences are taken as consume_string takes them (no cleaning,
+                          src/oxli/hashtable.cc:280-294): 2-bit code A=0 T=1 C=2 else 3. */
+
+enum {
+    KMGPU_OK = 0,
+    KMGPU_EINVAL = 1,   /* bad argument                         -> oxli_value_exception */
+    KMGPU_ENODEV = 2,   /* no CUDA device / driver              -> oxli_exception       */
+    KMGPU_ECUDA = 3,    /* CUDA runtime error                   -> oxli_exception       */
+    KMGPU_ENOMEM = 4,   /* device or host allocation failed     -> oxli_exception       */
+    KMGPU_ENONACGT = 5, /* Murmur hashing of an uncleaned sequence holding non-ACGT bytes */
+    KMGPU_ESHAPE = 6,   /* sketches of different shape          -> oxli_exception       */
+    KMGPU_EUNSUPPORTED = 7
+};
+
+typedef struct kmgpu_sketch kmgpu_t;
+typedef struct kmgpu_batch kmgpu_batch_t;
+
+/* optional hash-band predicate: consume only k-mers with lo <= hash < hi
+ * (Hashtable::consume_seqfile_banding, src/oxli/hashtable.cc:192-232; compute_band_interval
+ * src/oxli/kmer_hash.cc:262-276) */
+typedef struct {
+    uint64_t lo, hi;
+} kmgpu_band_t;
+
+/* optional mask predicate: consume only k-mers whose count in `mask` is <= threshold
+ * (or >= threshold when consume_masked != 0) — Hashtable::consume_seqfile_with_mask,
+ * src/oxli/hashtable.cc:152-190 */
+typedef struct {
+    kmgpu_t* mask;
+    uint32_t threshold;
+    int consume_masked;
+} kmgpu_mask_t;
+
+const char* kmgpu_last_error(void);
+int kmgpu_abi_version(void);
+int kmgpu_device_count(int* n);
+
+/* ---- lifetime -------------------------------------------------------------------------
+ * Replaces: ByteStorage/NibbleStorage/BitStorage constructors + _allocate_counters
+ * (include/oxli/storage.hh:118-130, :283-297, :501-523) and the Hashtable/MurmurHashtable choice of
+ * hash function (include/oxli/hashtable.hh:143-172, :494-520).  `sizes` are the table sizes in BINS
+ * (bytes / nibbles / bits), normally get_n_primes_near_x (hashtable.hh:99-123). */
+int kmgpu_create(int storage, int hash, int ksize, int n_tables, const uint64_t* sizes, int device,
+                 kmgpu_t** out);
+int kmgpu_destroy(kmgpu_t* h);
+
+/* Storage::set_use_bigcount / get_use_bigcount (src/oxli/storage.cc:50-61): only ByteStorage. */
+int kmgpu_set_use_bigcount(kmgpu_t* h, int on);
+int kmgpu_get_use_bigcount(kmgpu_t* h, int* on);
+
+/* ---- bulk ingestion --------------------------------------------------------------------
+ * Replaces the per-read loop of Hashtable::consume_seqfile (src/oxli/hashtable.cc:126-150) minus the
+ * file parsing: clean (flag), iterate k-mers (KmerIterator, src/oxli/kmer_hash.cc:278-343), store->add
+ * (storage.hh:571-624 / :320-359 / :172-199).  n_kmers_out receives the number of k-mers consumed
+ * (= sum over reads of max(0, len - k + 1), or the number passing band/mask). */
+int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                        uint32_t flags, const kmgpu_band_t* band, const kmgpu_mask_t* mask,
+                        uint64_t* n_kmers_out);
+
+/* Same, from 2-bit packed host buffers as produced by the host read feed: 64-bit words, 32 bases per
+ * word, first base in the two most significant bits, code A=0 T=1 C=2 G=3
+ * (include/oxli/kmer_hash.hh:70-72); reads are concatenated without padding, offsets in bases. */
+int kmgpu_consume_packed(kmgpu_t* h, const uint64_t* words, uint64_t n_words, const uint64_t* offsets,
+                         uint64_t n_reads, const kmgpu_band_t* band, const kmgpu_mask_t* mask,
+                         uint64_t* n_kmers_out);
+
+/* Device-resident read batches (inputs already in HBM): upload once, consume many times. */
+int kmgpu_batch_create(int device, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                       uint32_t flags, int ksize, kmgpu_batch_t** out);
+int kmgpu_batch_destroy(kmgpu_batch_t* b);
+int kmgpu_batch_info(const kmgpu_batch_t* b, uint64_t* n_reads, uint64_t* n_bases, uint64_t* device_bytes);
+int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmgpu_band_t* band,
+                        const kmgpu_mask_t* mask, uint64_t* n_kmers_out);
+
+/* Hashtable::add(HashIntoType) / count (hashtable.hh:222-237): add already-hashed k-mers in order;
+ * is_new_out[i] (nullable) = the bool Storage::add returns for the i-th hash. */
+int kmgpu_add_hashes(kmgpu_t* h, const uint64_t* hashes, uint64_t n, uint8_t* is_new_out);
+
+/* ---- queries ---------------------------------------------------------------------------
+ * Storage::get_count (storage.hh:627-649 / :362-379 / :207-219) for n hashed k-mers. */
+int kmgpu_get_counts(kmgpu_t* h, const uint64_t* hashes, uint64_t n, uint16_t* counts_out);
+
+/* Hashtable::get_kmer_counts (src/oxli/hashtable.cc:403-413) for a set of reads: counts of all k-mers
+ * of read 0, then read 1, ... ; counts_out must hold sum(max(0, len_r - k + 1)) entries. */
+int kmgpu_kmer_counts(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                      uint32_t flags, uint16_t* counts_out, uint64_t* n_kmers_out);
+
+/* Hashtable::get_kmer_hashes (src/oxli/hashtable.cc:377-386). */
+int kmgpu_kmer_hashes(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                      uint32_t flags, uint64_t* hashes_out, uint64_t* n_kmers_out);
+
+/* Hashtable::get_median_count (src/oxli/hashtable.cc:299-328) per read: median = sorted[n/2], float mean,
+ * float population stddev.  n_kmers_out[r] == 0 marks reads with no k-mer (the reference throws). */
+int kmgpu_read_medians(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                       uint32_t flags, uint16_t* median_out, float* average_out, float* stddev_out,
+                       uint32_t* n_kmers_out);
+
+/* Hashtable::median_at_least (src/oxli/hashtable.cc:333-364) per read; out[r] in {0,1}, 2 = no k-mers. */
+int kmgpu_median_at_least(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
+                          uint32_t flags, uint32_t cutoff, uint8_t* out);
+
+/* Hashtable::abundance_distribution (src/oxli/hashtable.cc:451-493): for every k-mer in stream order,
+ * if `tracking` does not hold it, add it there and bump hist[count in `counts`].  hist (65536 entries)
+ * is ACCUMULATED into, so a file can be fed in several calls. */
+int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, const char* seqs,
+                                 const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                 uint64_t* hist);
+
+/* ---- state -----------------------------------------------------------------------------
+ * Storage::n_occupied / n_unique_kmers / n_tables / get_tablesizes (storage.hh:65-74). */
+int kmgpu_stats(kmgpu_t* h, uint64_t* n_occupied, uint64_t* n_unique_kmers);
+int kmgpu_set_stats(kmgpu_t* h, uint64_t n_occupied, uint64_t n_unique_kmers);
+int kmgpu_shape(kmgpu_t* h, int* storage, int* hash, int* ksize, int* n_tables, uint64_t* sizes /*>=n_tables or NULL*/);
+int kmgpu_set_ksize(kmgpu_t* h, int ksize);
+
+/* Storage::get_raw_tables (storage.hh:74) and the table payload of save/load
+ * (src/oxli/storage.cc:99-136, :582-638, :772-803): byte-exact table images. */
+int kmgpu_table_nbytes(kmgpu_t* h, int table, uint64_t* nbytes);
+int kmgpu_download_table(kmgpu_t* h, int table, uint8_t* dst, uint64_t offset, uint64_t nbytes);
+int kmgpu_upload_table(kmgpu_t* h, int table, const uint8_t* src, uint64_t offset, uint64_t nbytes);
+
+/* ByteStorage::_bigcounts (storage.hh:513): entries in the iteration order of the
+ * std::unordered_map the reference writes to .ct files (src/oxli/storage.cc:623-632). */
+int kmgpu_bigcount_size(kmgpu_t* h, uint64_t* n);
+int kmgpu_bigcount_export(kmgpu_t* h, uint64_t* hashes, uint16_t* counts, uint64_t cap);
+int kmgpu_bigcount_import(kmgpu_t* h, const uint64_t* hashes, const uint16_t* counts, uint64_t n);
+
+/* BitStorage::update_from (src/oxli/storage.cc:63-96) generalised: dst |= src (bits),
+ * dst = min(cap, dst + src) per counter (bytes: 255, nibbles: 15); n_occupied is recomputed from
+ * table 0.  Shapes must match (KMGPU_ESHAPE otherwise). */
+int kmgpu_merge(kmgpu_t* dst, kmgpu_t* src);
+int kmgpu_recount_occupied(kmgpu_t* h);
+
+/* ---- multi-GPU (no reference counterpart) -----------------------------------
+ * Replicated sketches, one per GPU / process, merged over NVLink peer memory.  Each rank exports the
+ * IPC handles of its tables, the caller exchanges them (any transport), every rank attaches its
+ * peers, then:  reduce_scatter (rank r folds slice r of every peer into its own tables with the
+ * saturating add / OR above, reading peers over NVLink)  ->  caller barrier  ->  all_gather (rank r
+ * pulls every other slice from its owner)  ->  caller barrier. */
+#define KMGPU_IPC_HANDLE_BYTES 64
+int kmgpu_ipc_export(kmgpu_t* h, uint8_t* handles /* n_tables * 64 bytes */);
+int kmgpu_ipc_attach(kmgpu_t* h, int rank, int world, const uint8_t* all_handles /* world * n_tables * 64 */);
+int kmgpu_ipc_detach(kmgpu_t* h);
+int kmgpu_reduce_scatter_peers(kmgpu_t* h);
+int kmgpu_all_gather_peers(kmgpu_t* h);
+/* single-process variant: fold sketches living on different GPUs of this process into replicas[0..n)
+ * (peer access enabled internally). */
+int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
+
+/* ---- measurement -----------------------------------------------------------------------
+ * Device time (ms) and launch count of the ingest kernel accumulated since the last reset, measured
+ * with CUDA events on the handle's own stream. */
+int kmgpu_profile_reset(kmgpu_t* h);
+int kmgpu_profile_get(kmgpu_t* h, double* ingest_kernel_ms, uint64_t* ingest_launches, uint64_t* all_launches);
+int kmgpu_sync(kmgpu_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMGPU_H */

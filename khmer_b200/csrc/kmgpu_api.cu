@@ -1,0 +1,1512 @@
+// C ABI (include/kmgpu.h) + host orchestration of the kernels in kmgpu_kernels.cuh.
+//
+// One handle = one sketch resident in HBM.  Reads are processed in chunks of at most CHUNK_BASES stream
+// positions; per chunk: H2D (ASCII or packed) -> k_pack -> k_ingest -> [only when the chunk occupied new
+// bins] exact first-toucher resolution -> [only when bytes saturated] bigcount events to the host map.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kmgpu.h"
+#include "kmgpu_kernels.cuh"
+
+using namespace kmgpu;
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            int _c = (_e == cudaErrorMemoryAllocation) ? KMGPU_ENOMEM                                      \
+                     : (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? KMGPU_ENODEV      \
+                                                                                      : KMGPU_ECUDA;      \
+            return fail(_c, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,       \
+                        cudaGetErrorString(_e));                                                          \
+        }                                                                                                 \
+    } while (0)
+
+#define CKR(call)                  \
+    do {                           \
+        int _r = (call);           \
+        if (_r != KMGPU_OK) return _r; \
+    } while (0)
+
+static uint64_t env_u64(const char* name, uint64_t dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return strtoull(v, nullptr, 10);
+}
+
+// stream positions per chunk (multiple of TILE).  Bounded so positions fit 32 bits.
+static uint64_t chunk_bases()
+{
+    static uint64_t c = [] {
+        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 32ull << 20);
+        v = std::max<uint64_t>(TILE, std::min<uint64_t>(v, 1ull << 31));
+        return (v / TILE) * TILE;
+    }();
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// growable device / pinned buffers
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return KMGPU_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = std::max<size_t>(n, cap + cap / 2);
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return KMGPU_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return KMGPU_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = std::max<size_t>(n, cap + cap / 2);
+        CK(cudaMallocHost(&p, want * sizeof(T)));
+        cap = want;
+        return KMGPU_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// a chunk of reads staged on the device
+struct ChunkDev {
+    const uint64_t* words = nullptr;
+    const uint32_t* offs = nullptr;
+    uint32_t n_reads = 0;
+    uint32_t n_pos = 0;
+};
+
+struct kmgpu_batch {
+    int device = 0;
+    int ksize = 0;
+    uint64_t n_reads = 0, n_bases = 0, bytes = 0;
+    struct Piece {
+        uint64_t* words;
+        uint32_t* offs;
+        uint32_t n_reads, n_pos;
+    };
+    std::vector<Piece> pieces;
+};
+
+struct Peer {
+    uint8_t* tables[MAX_TABLES];
+};
+
+struct kmgpu_sketch {
+    int device = 0;
+    int kind = 0, hash = 0, k = 0, nt = 0;
+    uint64_t sizes[MAX_TABLES];
+    uint64_t nbytes[MAX_TABLES];
+    uint64_t alloc_bytes[MAX_TABLES];
+    SketchDev dev;
+    uint64_t n_occupied = 0, n_unique = 0;
+    bool use_bigcount = false;
+    std::unordered_map<uint64_t, uint16_t> big;  // same container as the reference (storage.hh:50)
+    bool big_dirty = true;
+    DevBuf<uint64_t> big_keys;
+    DevBuf<uint16_t> big_vals;
+    uint32_t n_big_dev = 0;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+
+    // workspace
+    DevBuf<uint8_t> d_ascii;
+    DevBuf<uint64_t> d_words;
+    DevBuf<uint32_t> d_offs;
+    DevBuf<uint32_t> d_flags;
+    DevBuf<uint32_t> d_newbits;
+    DevBuf<uint64_t> d_htkeys;
+    DevBuf<uint32_t> d_htvals;
+    DevBuf<Event> d_events;
+    DevBuf<uint16_t> d_counts;
+    DevBuf<uint64_t> d_hashes;
+    DevBuf<uint64_t> d_hashin;
+    DevBuf<uint16_t> d_stat_med;
+    DevBuf<float> d_stat_f;
+    DevBuf<uint32_t> d_stat_n;
+    DevBuf<uint8_t> d_stat_b;
+    DevBuf<unsigned long long> d_hist;
+    Ctrl* d_ctrl = nullptr;
+    Ctrl* h_ctrl = nullptr;  // pinned
+    PinBuf<uint32_t> h_offs;
+    PinBuf<Event> h_events;
+
+    // profile
+    double ingest_ms = 0;
+    uint64_t ingest_launches = 0, all_launches = 0;
+
+    // peers (multi-GPU)
+    int rank = 0, world = 1;
+    std::vector<Peer> peers;
+    bool peers_ipc = false;
+};
+
+static int set_device(int dev) { CK(cudaSetDevice(dev)); return KMGPU_OK; }
+
+// ------------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------------
+static Input make_input(const ChunkDev& c)
+{
+    Input in;
+    in.words = c.words;
+    in.offs = c.offs;
+    in.n_reads = c.n_reads;
+    in.hashes = nullptr;
+    in.n_pos = c.n_pos;
+    return in;
+}
+static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
+{
+    Input in;
+    in.words = nullptr;
+    in.offs = nullptr;
+    in.n_reads = 0;
+    in.hashes = d_hashes;
+    in.n_pos = n;
+    return in;
+}
+
+static inline unsigned n_tiles(uint32_t n_pos) { return (n_pos + TILE - 1) / TILE; }
+
+template <int KIND, int HK, int SRC>
+static void launch_ingest_nt(const SketchDev& S, const SketchDev& M, HashCfg H, const Pred& P, bool pred, const Input& in,
+                             uint32_t* flags, Ctrl* ctrl, cudaStream_t st)
+{
+    unsigned g = n_tiles(in.n_pos);
+    if (pred) {
+        k_ingest<KIND, HK, SRC, 0, true><<<g, THREADS, 0, st>>>(S, M, H, P, in, flags, ctrl);
+    } else if (S.n_tables == 4) {
+        k_ingest<KIND, HK, SRC, 4, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, flags, ctrl);
+    } else if (S.n_tables == 2) {
+        k_ingest<KIND, HK, SRC, 2, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, flags, ctrl);
+    } else {
+        k_ingest<KIND, HK, SRC, 0, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, flags, ctrl);
+    }
+}
+
+template <int KIND>
+static void launch_ingest_kind(int hk, int src, const SketchDev& S, const SketchDev& M, HashCfg H, const Pred& P, bool pred,
+                               const Input& in, uint32_t* flags, Ctrl* ctrl, cudaStream_t st)
+{
+    if (src == 1) launch_ingest_nt<KIND, TWOBIT, 1>(S, M, H, P, pred, in, flags, ctrl, st);
+    else if (hk == TWOBIT) launch_ingest_nt<KIND, TWOBIT, 0>(S, M, H, P, pred, in, flags, ctrl, st);
+    else launch_ingest_nt<KIND, MURMUR, 0>(S, M, H, P, pred, in, flags, ctrl, st);
+}
+
+static void launch_ingest(int src, const SketchDev& S, const SketchDev& M, HashCfg H, const Pred& P, bool pred, const Input& in,
+                          uint32_t* flags, Ctrl* ctrl, cudaStream_t st)
+{
+    if (S.kind == BYTE) launch_ingest_kind<BYTE>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
+    else if (S.kind == NIBBLE) launch_ingest_kind<NIBBLE>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
+    else launch_ingest_kind<BIT>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
+}
+
+#define DISPATCH_HK_SRC(KERNEL, hk, src, grid, st, ...)                                        \
+    do {                                                                                       \
+        if ((src) == 1) KERNEL<TWOBIT, 1><<<grid, THREADS, 0, st>>>(__VA_ARGS__);              \
+        else if ((hk) == TWOBIT) KERNEL<TWOBIT, 0><<<grid, THREADS, 0, st>>>(__VA_ARGS__);     \
+        else KERNEL<MURMUR, 0><<<grid, THREADS, 0, st>>>(__VA_ARGS__);                         \
+    } while (0)
+
+static void launch_counts(int src, const SketchDev& S, HashCfg H, const Input& in, const uint64_t* bk, const uint16_t* bv,
+                          uint32_t nb, uint16_t* counts, uint64_t* hashes, const uint32_t* only_bits, cudaStream_t st)
+{
+    unsigned g = n_tiles(in.n_pos);
+#define LC(KIND)                                                                                                          \
+    do {                                                                                                                  \
+        if (src == 1) k_counts<KIND, TWOBIT, 1><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits);   \
+        else if (H.kind == TWOBIT) k_counts<KIND, TWOBIT, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits); \
+        else k_counts<KIND, MURMUR, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits);            \
+    } while (0)
+    if (S.kind == BYTE) LC(BYTE);
+    else if (S.kind == NIBBLE) LC(NIBBLE);
+    else LC(BIT);
+#undef LC
+}
+
+// ------------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------------
+extern "C" const char* kmgpu_last_error(void) { return g_err.c_str(); }
+extern "C" int kmgpu_abi_version(void) { return KMGPU_ABI_VERSION; }
+
+extern "C" int kmgpu_device_count(int* n)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(KMGPU_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return KMGPU_OK;
+}
+
+static uint64_t table_nbytes(int kind, uint64_t size)
+{
+    // ByteStorage: size; NibbleStorage: size/2+1; BitStorage: size/8+1 (storage.hh:505-507, :290, :118)
+    return kind == BYTE ? size : kind == NIBBLE ? size / 2 + 1 : size / 8 + 1;
+}
+
+static void refresh_dev(kmgpu_sketch* h)
+{
+    h->dev.n_tables = h->nt;
+    h->dev.kind = h->kind;
+    for (int i = 0; i < h->nt; i++) {
+        h->dev.sizes[i] = h->sizes[i];
+        h->dev.magic[i] = ~0ull / h->sizes[i];
+    }
+}
+
+extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, const uint64_t* sizes, int device, kmgpu_t** out)
+{
+    if (!out) return fail(KMGPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (storage < 0 || storage > 2) return fail(KMGPU_EINVAL, "bad storage kind %d", storage);
+    if (hash < 0 || hash > 1) return fail(KMGPU_EINVAL, "bad hash kind %d", hash);
+    if (ksize < 1 || ksize > MAX_K) return fail(KMGPU_EINVAL, "ksize %d out of range", ksize);
+    if (hash == KMGPU_TWOBIT && ksize > 32)
+        return fail(KMGPU_EINVAL, "Supplied kmer string doesn't match the underlying k-size.");  // kmer_hash.cc:70-72
+    if (n_tables < 1 || n_tables > F_MAXT)
+        return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported (1..%d)", n_tables, F_MAXT);
+    for (int i = 0; i < n_tables; i++)
+        if (sizes[i] == 0 || sizes[i] >= (1ull << 55)) return fail(KMGPU_EINVAL, "table size %llu out of range", (unsigned long long)sizes[i]);
+    int ndev = 0;
+    CKR(kmgpu_device_count(&ndev));
+    if (ndev == 0) return fail(KMGPU_ENODEV, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(KMGPU_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CKR(set_device(device));
+    kmgpu_sketch* h = new kmgpu_sketch();
+    h->device = device;
+    h->kind = storage;
+    h->hash = hash;
+    h->k = ksize;
+    h->nt = n_tables;
+    memset(&h->dev, 0, sizeof h->dev);
+    for (int i = 0; i < n_tables; i++) {
+        h->sizes[i] = sizes[i];
+        h->nbytes[i] = table_nbytes(storage, sizes[i]);
+        h->alloc_bytes[i] = (h->nbytes[i] + 15) & ~15ull;
+        cudaError_t e = cudaMalloc(&h->dev.tables[i], h->alloc_bytes[i]);
+        if (e == cudaSuccess) e = cudaMemset(h->dev.tables[i], 0, h->alloc_bytes[i]);
+        if (e != cudaSuccess) {
+            for (int j = 0; j <= i; j++)
+                if (h->dev.tables[j]) cudaFree(h->dev.tables[j]);
+            delete h;
+            return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "table %d (%llu bytes): %s", i,
+                        (unsigned long long)h->alloc_bytes[i], cudaGetErrorString(e));
+        }
+    }
+    refresh_dev(h);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl));
+    if (e != cudaSuccess) {
+        kmgpu_destroy(h);
+        return fail(KMGPU_ECUDA, "handle setup: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_ipc_detach(kmgpu_t* h);
+
+extern "C" int kmgpu_destroy(kmgpu_t* h)
+{
+    if (!h) return KMGPU_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    kmgpu_ipc_detach(h);
+    for (int i = 0; i < h->nt; i++)
+        if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
+    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_flags.release(); h->d_newbits.release();
+    h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
+    h->d_hashin.release(); h->d_stat_med.release(); h->d_stat_f.release(); h->d_stat_n.release(); h->d_stat_b.release();
+    h->d_hist.release(); h->big_keys.release(); h->big_vals.release();
+    h->h_offs.release(); h->h_events.release();
+    if (h->d_ctrl) cudaFree(h->d_ctrl);
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_set_use_bigcount(kmgpu_t* h, int on)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (h->kind != KMGPU_BYTE) return fail(KMGPU_EUNSUPPORTED, "bigcount is not supported for this storage.");  // storage.cc:52-54
+    std::lock_guard<std::mutex> g(h->mu);
+    h->use_bigcount = on != 0;
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_get_use_bigcount(kmgpu_t* h, int* on)
+{
+    if (!h || !on) return fail(KMGPU_EINVAL, "null argument");
+    *on = h->use_bigcount ? 1 : 0;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_stats(kmgpu_t* h, uint64_t* n_occupied, uint64_t* n_unique)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n_occupied) *n_occupied = h->n_occupied;
+    if (n_unique) *n_unique = h->n_unique;
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_set_stats(kmgpu_t* h, uint64_t n_occupied, uint64_t n_unique)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->n_occupied = n_occupied;
+    h->n_unique = n_unique;
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_shape(kmgpu_t* h, int* storage, int* hash, int* ksize, int* n_tables, uint64_t* sizes)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (storage) *storage = h->kind;
+    if (hash) *hash = h->hash;
+    if (ksize) *ksize = h->k;
+    if (n_tables) *n_tables = h->nt;
+    if (sizes) for (int i = 0; i < h->nt; i++) sizes[i] = h->sizes[i];
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_set_ksize(kmgpu_t* h, int ksize)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (ksize < 1 || ksize > MAX_K || (h->hash == KMGPU_TWOBIT && ksize > 32)) return fail(KMGPU_EINVAL, "ksize %d out of range", ksize);
+    std::lock_guard<std::mutex> g(h->mu);
+    h->k = ksize;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_table_nbytes(kmgpu_t* h, int table, uint64_t* nbytes)
+{
+    if (!h || table < 0 || table >= h->nt) return fail(KMGPU_EINVAL, "bad table index");
+    *nbytes = h->nbytes[table];
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_download_table(kmgpu_t* h, int table, uint8_t* dst, uint64_t offset, uint64_t nbytes)
+{
+    if (!h || table < 0 || table >= h->nt) return fail(KMGPU_EINVAL, "bad table index");
+    if (offset + nbytes > h->nbytes[table]) return fail(KMGPU_EINVAL, "range past end of table");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, h->dev.tables[table] + offset, nbytes, cudaMemcpyDeviceToHost));
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_upload_table(kmgpu_t* h, int table, const uint8_t* src, uint64_t offset, uint64_t nbytes)
+{
+    if (!h || table < 0 || table >= h->nt) return fail(KMGPU_EINVAL, "bad table index");
+    if (offset + nbytes > h->nbytes[table]) return fail(KMGPU_EINVAL, "range past end of table");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->dev.tables[table] + offset, src, nbytes, cudaMemcpyHostToDevice));
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_sync(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    CKR(set_device(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_profile_reset(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    h->ingest_ms = 0;
+    h->ingest_launches = 0;
+    h->all_launches = 0;
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_profile_get(kmgpu_t* h, double* ms, uint64_t* launches, uint64_t* all_launches)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (ms) *ms = h->ingest_ms;
+    if (launches) *launches = h->ingest_launches;
+    if (all_launches) *all_launches = h->all_launches;
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bigcount map
+// ------------------------------------------------------------------------------------------------------
+extern "C" int kmgpu_bigcount_size(kmgpu_t* h, uint64_t* n)
+{
+    if (!h || !n) return fail(KMGPU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    *n = h->big.size();
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_bigcount_export(kmgpu_t* h, uint64_t* hashes, uint16_t* counts, uint64_t cap)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    uint64_t i = 0;
+    for (auto it = h->big.begin(); it != h->big.end() && i < cap; ++it, ++i) {  // writer order, storage.cc:623-632
+        hashes[i] = it->first;
+        counts[i] = it->second;
+    }
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_bigcount_import(kmgpu_t* h, const uint64_t* hashes, const uint16_t* counts, uint64_t n)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n) h->big.clear();  // reader clears only when the file holds entries (storage.cc:369-379)
+    for (uint64_t i = 0; i < n; i++) h->big[hashes[i]] = counts[i];
+    h->big_dirty = true;
+    return KMGPU_OK;
+}
+
+// ByteStorage::add tail (storage.hh:606-617)
+static inline void big_event(kmgpu_sketch* h, uint64_t hash)
+{
+    uint16_t& v = h->big[hash];
+    if (v == 0) v = 256;
+    else if (v < 65535) v++;
+    h->big_dirty = true;
+}
+
+static int sync_big_to_device(kmgpu_sketch* h)
+{
+    if (!h->big_dirty) return KMGPU_OK;
+    std::vector<std::pair<uint64_t, uint16_t>> v(h->big.begin(), h->big.end());
+    std::sort(v.begin(), v.end());
+    std::vector<uint64_t> kk(v.size());
+    std::vector<uint16_t> vv(v.size());
+    for (size_t i = 0; i < v.size(); i++) { kk[i] = v[i].first; vv[i] = v[i].second; }
+    CKR(h->big_keys.ensure(std::max<size_t>(1, v.size())));
+    CKR(h->big_vals.ensure(std::max<size_t>(1, v.size())));
+    if (!v.empty()) {
+        CK(cudaMemcpyAsync(h->big_keys.p, kk.data(), 8 * v.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->big_vals.p, vv.data(), 2 * v.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->n_big_dev = (uint32_t)v.size();
+    h->big_dirty = false;
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// chunk processing
+// ------------------------------------------------------------------------------------------------------
+static uint64_t pow2_at_least(uint64_t n)
+{
+    uint64_t p = 1024;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+static int read_ctrl(kmgpu_sketch* h)
+{
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+
+// first-toucher resolution for the chunk whose flags are in d_flags: leaves the "new" bitmap in
+// d_newbits and returns the number of new k-mers.
+static int resolve_new(kmgpu_sketch* h, int src, const SketchDev& S, HashCfg H, const Input& in, uint64_t n_keys, uint64_t* n_new)
+{
+    cudaStream_t st = h->stream;
+    uint64_t slots = pow2_at_least(2 * n_keys);
+    CKR(h->d_htkeys.ensure(slots));
+    CKR(h->d_htvals.ensure(slots));
+    size_t nb_words = (in.n_pos + 31) / 32;
+    CKR(h->d_newbits.ensure(nb_words));
+    CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
+    CK(cudaMemsetAsync(h->d_htvals.p, 0xFF, slots * 4, st));
+    CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
+    CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+    unsigned g = n_tiles(in.n_pos);
+    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 0, h->d_htkeys.p, slots - 1);
+    DISPATCH_HK_SRC(k_replay, H.kind, src, g, st, S, H, in, h->d_flags.p, h->d_htkeys.p, h->d_htvals.p, slots - 1);
+    unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
+    k_mark<<<gm, 256, 0, st>>>(h->d_htkeys.p, h->d_htvals.p, slots, h->d_newbits.p, h->d_ctrl);
+    h->all_launches += 3;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    *n_new = h->h_ctrl->n_unique;
+    return KMGPU_OK;
+}
+
+// bigcount after a chunk (ByteStorage with use_bigcount).  See DESIGN.md "bigcount exactness".
+static int resolve_bigcount(kmgpu_sketch* h, int src, HashCfg H, const Input& in, uint64_t n_allsat, uint64_t n_cross)
+{
+    cudaStream_t st = h->stream;
+    const SketchDev& S = h->dev;
+    unsigned g = n_tiles(in.n_pos);
+    std::vector<Event> certain;
+    if (n_allsat) {
+        CKR(h->d_events.ensure(n_allsat));
+        CKR(h->h_events.ensure(n_allsat));
+        CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+        DISPATCH_HK_SRC(k_events, H.kind, src, g, st, S, H, in, h->d_flags.p, h->d_events.p, h->d_ctrl);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_events.p, h->d_events.p, n_allsat * sizeof(Event), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        certain.assign(h->h_events.p, h->h_events.p + n_allsat);
+        std::sort(certain.begin(), certain.end(), [](const Event& a, const Event& b) { return a.pos < b.pos; });
+    }
+    if (!n_cross) {
+        // every saturated bin was saturated before the chunk began: memory order == stream order for the test
+        for (const Event& e : certain) big_event(h, e.hash);
+        return KMGPU_OK;
+    }
+    // some bins reached 255 inside this chunk: rebuild, per such bin, the stream position T of the update
+    // that saturated it.  If E updates of the chunk found the bin already saturated (a count that does not
+    // depend on the order), T is the update with exactly E later updates of that bin.
+    uint64_t slots = pow2_at_least(2 * n_cross);
+    CKR(h->d_htkeys.ensure(slots));
+    CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
+    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 20, h->d_htkeys.p, slots - 1);
+    uint64_t cap = in.n_pos;
+    CKR(h->d_events.ensure(cap));
+    CKR(h->h_events.ensure(cap));
+    CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+    DISPATCH_HK_SRC(k_cross_replay, H.kind, src, g, st, S, H, in, h->d_flags.p, h->d_htkeys.p, slots - 1, h->d_events.p,
+                    (unsigned long long)cap, h->d_ctrl);
+    h->all_launches += 2;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    uint64_t n_rec = h->h_ctrl->n_events;
+    if (n_rec > cap) return fail(KMGPU_ECUDA, "internal: cross replay overflow");
+    if (n_rec) {
+        CK(cudaMemcpyAsync(h->h_events.p, h->d_events.p, n_rec * sizeof(Event), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    std::vector<Event> recs(h->h_events.p, h->h_events.p + n_rec);
+    std::sort(recs.begin(), recs.end(), [](const Event& a, const Event& b) { return a.pos < b.pos; });
+    struct BinInfo {
+        std::vector<uint32_t> touches;
+        uint64_t later = 0;  // E
+        uint32_t T = 0;
+    };
+    std::unordered_map<uint64_t, BinInfo> bins;  // key = bin << 8 | table
+    for (const Event& e : recs) {
+        uint32_t cross = e.info & 0x3ff, sat = (e.info >> 10) & 0x3ff;
+        for (int i = 0; i < h->nt; i++) {
+            if (!(cross >> i & 1)) continue;
+            BinInfo& b = bins[((e.hash % h->sizes[i]) << 8) | (uint64_t)i];
+            b.touches.push_back(e.pos);  // ascending
+            b.later += (sat >> i) & 1;
+        }
+    }
+    for (auto& kv : bins) {
+        BinInfo& b = kv.second;
+        if (b.later >= b.touches.size()) return fail(KMGPU_ECUDA, "internal: inconsistent saturation record");
+        b.T = b.touches[b.touches.size() - 1 - b.later];
+    }
+    // merge: records decide k-mers touching a crossing bin, `certain` decides the rest
+    std::vector<Event> events;
+    size_t ci = 0;
+    for (const Event& e : recs) {
+        while (ci < certain.size() && certain[ci].pos < e.pos) events.push_back(certain[ci++]);
+        if (ci < certain.size() && certain[ci].pos == e.pos) ci++;  // decided here instead
+        if (!(e.info >> 30 & 1)) continue;
+        bool after_all = true;
+        uint32_t cross = e.info & 0x3ff;
+        for (int i = 0; i < h->nt && after_all; i++) {
+            if (!(cross >> i & 1)) continue;
+            const BinInfo& b = bins[((e.hash % h->sizes[i]) << 8) | (uint64_t)i];
+            if (!(e.pos > b.T)) after_all = false;
+        }
+        if (after_all) events.push_back(e);
+    }
+    while (ci < certain.size()) events.push_back(certain[ci++]);
+    for (const Event& e : events) big_event(h, e.hash);
+    return KMGPU_OK;
+}
+
+struct ChunkResult {
+    uint64_t n_kmers = 0, n_new = 0;
+    bool have_newbits = false;
+};
+
+// ingest one staged chunk into sketch `h` (hash config may come from another sketch: abundance tracking)
+static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, const Pred& P, bool pred, const SketchDev* M,
+                        ChunkResult* res)
+{
+    if (in.n_pos == 0) return KMGPU_OK;
+    cudaStream_t st = h->stream;
+    CKR(h->d_flags.ensure(in.n_pos));
+    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    CK(cudaEventRecord(h->ev0, st));
+    launch_ingest(src, h->dev, M ? *M : h->dev, H, P, pred, in, h->d_flags.p, h->d_ctrl, st);
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ingest_ms += ms;
+    h->ingest_launches += 1;
+    h->all_launches += 1;
+    Ctrl c = *h->h_ctrl;
+    res->n_kmers += c.n_kmers;
+    h->n_occupied += c.n_z0;
+    if (c.n_zbits) {
+        uint64_t n_new = 0;
+        CKR(resolve_new(h, src, h->dev, H, in, c.n_zbits, &n_new));
+        h->n_unique += n_new;
+        res->n_new += n_new;
+        res->have_newbits = true;
+    }
+    if (h->kind == BYTE && h->use_bigcount && (c.n_allsat || c.n_cross))
+        CKR(resolve_bigcount(h, src, H, in, c.n_allsat, c.n_cross));
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// staging reads: split [seqs, offsets] into chunks of <= chunk_bases() positions, cutting at read
+// boundaries where possible; a read longer than a chunk continues in the next chunk with k-1 bases of
+// overlap, which yields exactly the same k-mer stream.
+// ------------------------------------------------------------------------------------------------------
+struct ChunkPlan {
+    uint64_t base0, base1;          // range of the concatenated buffer
+    std::vector<uint32_t> offs;     // chunk-relative read offsets (n+1)
+};
+
+static void plan_chunks(const uint64_t* offsets, uint64_t n_reads, int k, uint64_t cap, std::vector<ChunkPlan>& out)
+{
+    uint64_t r = 0;
+    uint64_t carry_start = 0;  // start (absolute base) of the current piece of read r
+    bool in_piece = false;
+    while (r < n_reads) {
+        ChunkPlan c;
+        c.base0 = in_piece ? carry_start : offsets[r];
+        c.offs.push_back(0);
+        uint64_t used = 0;
+        while (r < n_reads) {
+            uint64_t s = in_piece ? carry_start : offsets[r];
+            uint64_t e = offsets[r + 1];
+            uint64_t len = e - s;
+            if (used + len <= cap && c.offs.size() <= cap / 4 + 1) {
+                used += len;
+                c.offs.push_back((uint32_t)used);
+                r++;
+                in_piece = false;
+                continue;
+            }
+            if (used == 0) {
+                // a single read longer than the chunk: take cap bases, continue k-1 before the cut
+                uint64_t cut = s + cap;
+                used = cap;
+                c.offs.push_back((uint32_t)used);
+                carry_start = cut - (uint64_t)(k - 1);
+                in_piece = true;
+            }
+            break;
+        }
+        c.base1 = c.base0 + used;
+        out.push_back(std::move(c));
+    }
+}
+
+// upload chunk (ASCII -> device -> 2-bit)
+static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, uint32_t flags, ChunkDev* out, bool need_acgt_check)
+{
+    cudaStream_t st = h->stream;
+    uint32_t n_pos = (uint32_t)(c.base1 - c.base0);
+    uint32_t n_reads = (uint32_t)c.offs.size() - 1;
+    size_t n_words = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
+    CKR(h->d_ascii.ensure(std::max<size_t>(n_pos, 1)));
+    CKR(h->d_words.ensure(n_words));
+    CKR(h->d_offs.ensure(n_reads + 1));
+    CKR(h->h_offs.ensure(n_reads + 1));
+    memcpy(h->h_offs.p, c.offs.data(), (n_reads + 1) * sizeof(uint32_t));
+    if (n_pos) CK(cudaMemcpyAsync(h->d_ascii.p, seqs + c.base0, n_pos, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_offs.p, h->h_offs.p, (n_reads + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(h->d_ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, h->d_words.p,
+                                                             (uint32_t)n_words, h->d_ctrl);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    if (need_acgt_check) {
+        CKR(read_ctrl(h));
+        if (h->h_ctrl->non_acgt)
+            return fail(KMGPU_ENONACGT, "sequence holds %llu bytes outside ACGT; the Murmur hash of uncleaned sequences is not computed on the device",
+                        (unsigned long long)h->h_ctrl->non_acgt);
+    }
+    out->words = h->d_words.p;
+    out->offs = h->d_offs.p;
+    out->n_reads = n_reads;
+    out->n_pos = n_pos;
+    return KMGPU_OK;
+}
+
+static int make_pred(kmgpu_sketch* h, const kmgpu_band_t* band, const kmgpu_mask_t* mask, Pred* P, bool* pred, const SketchDev** M)
+{
+    memset(P, 0, sizeof *P);
+    *pred = false;
+    *M = nullptr;
+    if (band) {
+        P->band_on = 1;
+        P->band_lo = band->lo;
+        P->band_hi = band->hi;
+        *pred = true;
+    }
+    if (mask) {
+        if (!mask->mask) return fail(KMGPU_EINVAL, "mask sketch is NULL");
+        if (mask->mask->device != h->device) return fail(KMGPU_EINVAL, "mask sketch lives on another device");
+        P->mask_on = 1;
+        P->mask_threshold = mask->threshold;
+        P->mask_ge = mask->consume_masked ? 1 : 0;
+        *M = &mask->mask->dev;
+        *pred = true;
+    }
+    return KMGPU_OK;
+}
+
+static bool needs_acgt_check(const kmgpu_sketch* h, uint32_t flags) { return h->hash == KMGPU_MURMUR && !(flags & KMGPU_CLEAN); }
+
+extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                   const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    Pred P;
+    bool pred;
+    const SketchDev* M;
+    CKR(make_pred(h, band, mask, &P, &pred, &M));
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
+    HashCfg H{h->hash, h->k};
+    ChunkResult res;
+    for (const ChunkPlan& c : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
+        CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));
+    }
+    if (n_kmers_out) *n_kmers_out = res.n_kmers;
+    return KMGPU_OK;
+}
+
+// clipped, chunk-relative offsets of the reads overlapping [b0, b1); r0 is advanced past finished reads
+static void clip_offsets(const uint64_t* offsets, uint64_t n_reads, uint64_t b0, uint64_t b1, uint64_t* r0, std::vector<uint32_t>& out)
+{
+    out.clear();
+    while (*r0 < n_reads && offsets[*r0 + 1] <= b0) (*r0)++;
+    out.push_back(0);
+    for (uint64_t r = *r0; r < n_reads && offsets[r] < b1; r++) {
+        uint64_t e = std::min(offsets[r + 1], b1);
+        out.push_back((uint32_t)(e - b0));
+    }
+    // leading gap (possible only before the first read) and trailing part are covered by the first/last piece
+    if (out.size() == 1) out.push_back((uint32_t)(b1 - b0));
+}
+
+// Packed input is consumed in place: chunk i covers bases [i*cap, i*cap + cap + k-1) of the caller's stream
+// (cap a multiple of 32, so every chunk starts on a word of the caller's buffer).  Reads are clipped to
+// the chunk; a clipped piece inside the k-1 overlap is shorter than k and yields nothing, the piece that
+// continues past it starts exactly at the first k-mer the previous chunk could not hold.
+template <class Fn>
+static int for_each_packed_chunk(kmgpu_sketch* h, const uint64_t* words, uint64_t n_words, const uint64_t* offsets, uint64_t n_reads,
+                                 bool device_src, Fn fn)
+{
+    cudaStream_t st = h->stream;
+    const uint64_t n_bases = offsets[n_reads];
+    const uint64_t cap = chunk_bases();
+    uint64_t r0 = 0;
+    std::vector<uint32_t> offs;
+    for (uint64_t b0 = 0; b0 < n_bases; b0 += cap) {
+        uint64_t b1 = std::min(n_bases, b0 + cap + (uint64_t)(h->k - 1));
+        clip_offsets(offsets, n_reads, b0, b1, &r0, offs);
+        uint32_t n_pos = (uint32_t)(b1 - b0);
+        size_t nw = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
+        uint64_t w0 = b0 / 32, w1 = std::min<uint64_t>(n_words, w0 + nw);
+        CKR(h->d_words.ensure(nw));
+        if (w1 - w0 < nw) CK(cudaMemsetAsync(h->d_words.p + (w1 - w0), 0, (nw - (w1 - w0)) * 8, st));
+        CK(cudaMemcpyAsync(h->d_words.p, words + w0, (w1 - w0) * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        CKR(h->d_offs.ensure(offs.size()));
+        CKR(h->h_offs.ensure(offs.size()));
+        memcpy(h->h_offs.p, offs.data(), offs.size() * 4);
+        CK(cudaMemcpyAsync(h->d_offs.p, h->h_offs.p, offs.size() * 4, cudaMemcpyHostToDevice, st));
+        ChunkDev cd;
+        cd.words = h->d_words.p;
+        cd.offs = h->d_offs.p;
+        cd.n_reads = (uint32_t)offs.size() - 1;
+        cd.n_pos = n_pos;
+        CKR(fn(cd));
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_consume_packed(kmgpu_t* h, const uint64_t* words, uint64_t n_words, const uint64_t* offsets, uint64_t n_reads,
+                                    const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!words || !offsets) return fail(KMGPU_EINVAL, "null input");
+    if (n_words * 32 < offsets[n_reads]) return fail(KMGPU_EINVAL, "packed buffer shorter than offsets[n_reads]");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    Pred P;
+    bool pred;
+    const SketchDev* M;
+    CKR(make_pred(h, band, mask, &P, &pred, &M));
+    HashCfg H{h->hash, h->k};
+    ChunkResult res;
+    CKR(for_each_packed_chunk(h, words, n_words, offsets, n_reads, false, [&](const ChunkDev& cd) {
+        return ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res);
+    }));
+    if (n_kmers_out) *n_kmers_out = res.n_kmers;
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device-resident batches
+// ------------------------------------------------------------------------------------------------------
+extern "C" int kmgpu_batch_create(int device, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags, int ksize,
+                                  kmgpu_batch_t** out)
+{
+    if (!out) return fail(KMGPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (ksize < 1 || ksize > MAX_K) return fail(KMGPU_EINVAL, "ksize out of range");
+    if (n_reads && (!seqs || !offsets)) return fail(KMGPU_EINVAL, "null input");
+    CKR(set_device(device));
+    kmgpu_batch* b = new kmgpu_batch();
+    b->device = device;
+    b->ksize = ksize;
+    b->n_reads = n_reads;
+    b->n_bases = n_reads ? offsets[n_reads] - offsets[0] : 0;
+    std::vector<ChunkPlan> plan;
+    if (n_reads) plan_chunks(offsets, n_reads, ksize, chunk_bases(), plan);
+    uint8_t* d_ascii = nullptr;
+    Ctrl* d_ctrl = nullptr;
+    size_t ascii_cap = 0;
+    int rc = KMGPU_OK;
+    auto bail = [&](cudaError_t e) {
+        rc = fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "batch upload: %s", cudaGetErrorString(e));
+    };
+    cudaError_t e = cudaMalloc(&d_ctrl, sizeof(Ctrl));
+    if (e != cudaSuccess) bail(e);
+    for (size_t ci = 0; rc == KMGPU_OK && ci < plan.size(); ci++) {
+        const ChunkPlan& c = plan[ci];
+        uint32_t n_pos = (uint32_t)(c.base1 - c.base0);
+        uint32_t nr = (uint32_t)c.offs.size() - 1;
+        size_t nw = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
+        if (n_pos > ascii_cap) {
+            if (d_ascii) cudaFree(d_ascii);
+            d_ascii = nullptr;
+            if ((e = cudaMalloc(&d_ascii, n_pos)) != cudaSuccess) { bail(e); break; }
+            ascii_cap = n_pos;
+        }
+        kmgpu_batch::Piece p{nullptr, nullptr, nr, n_pos};
+        if ((e = cudaMalloc(&p.words, nw * 8)) != cudaSuccess) { bail(e); break; }
+        if ((e = cudaMalloc(&p.offs, (nr + 1) * 4)) != cudaSuccess) { cudaFree(p.words); bail(e); break; }
+        b->pieces.push_back(p);
+        b->bytes += nw * 8 + (nr + 1) * 4;
+        if (n_pos && (e = cudaMemcpy(d_ascii, seqs + c.base0, n_pos, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e); break; }
+        if ((e = cudaMemcpy(p.offs, c.offs.data(), (nr + 1) * 4, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e); break; }
+        cudaMemset(d_ctrl, 0, sizeof(Ctrl));
+        k_pack<<<(unsigned)((nw + 255) / 256), 256>>>(d_ascii, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, p.words, (uint32_t)nw, d_ctrl);
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e); break; }
+    }
+    if (d_ascii) cudaFree(d_ascii);
+    if (d_ctrl) cudaFree(d_ctrl);
+    if (rc != KMGPU_OK) {
+        kmgpu_batch_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_batch_destroy(kmgpu_batch_t* b)
+{
+    if (!b) return KMGPU_OK;
+    cudaSetDevice(b->device);
+    for (auto& p : b->pieces) {
+        if (p.words) cudaFree(p.words);
+        if (p.offs) cudaFree(p.offs);
+    }
+    delete b;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_batch_info(const kmgpu_batch_t* b, uint64_t* n_reads, uint64_t* n_bases, uint64_t* device_bytes)
+{
+    if (!b) return fail(KMGPU_EINVAL, "null batch");
+    if (n_reads) *n_reads = b->n_reads;
+    if (n_bases) *n_bases = b->n_bases;
+    if (device_bytes) *device_bytes = b->bytes;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmgpu_band_t* band, const kmgpu_mask_t* mask,
+                                   uint64_t* n_kmers_out)
+{
+    if (!h || !b) return fail(KMGPU_EINVAL, "null argument");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (b->device != h->device) return fail(KMGPU_EINVAL, "batch lives on another device");
+    if (b->ksize != h->k) return fail(KMGPU_EINVAL, "batch was cut for k=%d, sketch has k=%d", b->ksize, h->k);
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    Pred P;
+    bool pred;
+    const SketchDev* M;
+    CKR(make_pred(h, band, mask, &P, &pred, &M));
+    HashCfg H{h->hash, h->k};
+    ChunkResult res;
+    for (const auto& p : b->pieces) {
+        ChunkDev cd;
+        cd.words = p.words;
+        cd.offs = p.offs;
+        cd.n_reads = p.n_reads;
+        cd.n_pos = p.n_pos;
+        CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));
+    }
+    if (n_kmers_out) *n_kmers_out = res.n_kmers;
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// hashed k-mers
+// ------------------------------------------------------------------------------------------------------
+extern "C" int kmgpu_add_hashes(kmgpu_t* h, const uint64_t* hashes, uint64_t n, uint8_t* is_new_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n == 0) return KMGPU_OK;
+    if (!hashes) return fail(KMGPU_EINVAL, "null input");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    HashCfg H{h->hash, h->k};
+    Pred P;
+    memset(&P, 0, sizeof P);
+    const uint64_t cap = chunk_bases();
+    std::vector<uint32_t> bits;
+    for (uint64_t i0 = 0; i0 < n; i0 += cap) {
+        uint32_t m = (uint32_t)std::min<uint64_t>(cap, n - i0);
+        CKR(h->d_hashin.ensure(m));
+        CK(cudaMemcpyAsync(h->d_hashin.p, hashes + i0, 8ull * m, cudaMemcpyHostToDevice, h->stream));
+        ChunkResult res;
+        CKR(ingest_chunk(h, 1, H, make_hash_input(h->d_hashin.p, m), P, false, nullptr, &res));
+        if (is_new_out) {
+            if (res.have_newbits) {
+                bits.resize((m + 31) / 32);
+                CK(cudaMemcpy(bits.data(), h->d_newbits.p, bits.size() * 4, cudaMemcpyDeviceToHost));
+                for (uint32_t j = 0; j < m; j++) is_new_out[i0 + j] = (bits[j >> 5] >> (j & 31)) & 1u;
+            } else {
+                memset(is_new_out + i0, 0, m);
+            }
+        }
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_get_counts(kmgpu_t* h, const uint64_t* hashes, uint64_t n, uint16_t* counts_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n == 0) return KMGPU_OK;
+    if (!hashes || !counts_out) return fail(KMGPU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+    uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+    HashCfg H{h->hash, h->k};
+    const uint64_t cap = chunk_bases();
+    for (uint64_t i0 = 0; i0 < n; i0 += cap) {
+        uint32_t m = (uint32_t)std::min<uint64_t>(cap, n - i0);
+        CKR(h->d_hashin.ensure(m));
+        CKR(h->d_counts.ensure(m));
+        CK(cudaMemcpyAsync(h->d_hashin.p, hashes + i0, 8ull * m, cudaMemcpyHostToDevice, h->stream));
+        launch_counts(1, h->dev, H, make_hash_input(h->d_hashin.p, m), h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr,
+                      h->stream);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(counts_out + i0, h->d_counts.p, 2ull * m, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-k-mer and per-read queries over sequences
+// ------------------------------------------------------------------------------------------------------
+static int per_kmer_query(kmgpu_sketch* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                          uint16_t* counts_out, uint64_t* hashes_out, uint64_t* n_kmers_out)
+{
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    bool want_c = counts_out != nullptr;
+    if (want_c && h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+    uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+    HashCfg H{h->hash, h->k};
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
+    std::vector<uint16_t> hc;
+    std::vector<uint64_t> hh;
+    uint64_t w = 0;
+    for (const ChunkPlan& c : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
+        if (cd.n_pos == 0) continue;
+        if (want_c) CKR(h->d_counts.ensure(cd.n_pos));
+        if (hashes_out) CKR(h->d_hashes.ensure(cd.n_pos));
+        launch_counts(0, h->dev, H, make_input(cd), h->big_keys.p, h->big_vals.p, nb, want_c ? h->d_counts.p : nullptr,
+                      hashes_out ? h->d_hashes.p : nullptr, nullptr, h->stream);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        if (want_c) {
+            hc.resize(cd.n_pos);
+            CK(cudaMemcpyAsync(hc.data(), h->d_counts.p, 2ull * cd.n_pos, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (hashes_out) {
+            hh.resize(cd.n_pos);
+            CK(cudaMemcpyAsync(hh.data(), h->d_hashes.p, 8ull * cd.n_pos, cudaMemcpyDeviceToHost, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        for (size_t j = 0; j + 1 < c.offs.size(); j++) {
+            uint32_t s = c.offs[j], e = c.offs[j + 1];
+            if (e - s < (uint32_t)h->k) continue;
+            uint32_t n = e - s - h->k + 1;
+            if (want_c) memcpy(counts_out + w, hc.data() + s, 2ull * n);
+            if (hashes_out) memcpy(hashes_out + w, hh.data() + s, 8ull * n);
+            w += n;
+        }
+    }
+    if (n_kmers_out) *n_kmers_out = w;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_kmer_counts(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                 uint16_t* counts_out, uint64_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (!counts_out && n_reads) return fail(KMGPU_EINVAL, "null output");
+    return per_kmer_query(h, seqs, offsets, n_reads, flags, counts_out, nullptr, n_kmers_out);
+}
+
+extern "C" int kmgpu_kmer_hashes(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                 uint64_t* hashes_out, uint64_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (!hashes_out && n_reads) return fail(KMGPU_EINVAL, "null output");
+    return per_kmer_query(h, seqs, offsets, n_reads, flags, nullptr, hashes_out, n_kmers_out);
+}
+
+static int per_read_query(kmgpu_sketch* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                          uint16_t* median_out, float* average_out, float* stddev_out, uint32_t* n_kmers_out, bool at_least,
+                          uint32_t cutoff, uint8_t* at_least_out)
+{
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] - offsets[r] > chunk_bases())
+            return fail(KMGPU_EUNSUPPORTED, "read %llu is longer than a device chunk (%llu bases); per-read statistics need whole reads",
+                        (unsigned long long)r, (unsigned long long)chunk_bases());
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+    uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+    HashCfg H{h->hash, h->k};
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
+    uint64_t r0 = 0;
+    cudaStream_t st = h->stream;
+    for (const ChunkPlan& c : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
+        uint32_t nr = cd.n_reads;
+        CKR(h->d_counts.ensure(std::max<uint32_t>(cd.n_pos, 1)));
+        if (cd.n_pos) {
+            launch_counts(0, h->dev, H, make_input(cd), h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr, st);
+            h->all_launches += 1;
+        }
+        CKR(h->d_stat_med.ensure(nr));
+        CKR(h->d_stat_f.ensure(2ull * nr));
+        CKR(h->d_stat_n.ensure(nr));
+        CKR(h->d_stat_b.ensure(nr));
+        bool want_med = !at_least;
+        k_read_stats<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, want_med ? h->d_stat_med.p : nullptr,
+                                                  want_med ? h->d_stat_f.p : nullptr, want_med ? h->d_stat_f.p + nr : nullptr,
+                                                  h->d_stat_n.p, cutoff, at_least ? h->d_stat_b.p : nullptr);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        if (want_med) {
+            if (median_out) CK(cudaMemcpyAsync(median_out + r0, h->d_stat_med.p, 2ull * nr, cudaMemcpyDeviceToHost, st));
+            if (average_out) CK(cudaMemcpyAsync(average_out + r0, h->d_stat_f.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
+            if (stddev_out) CK(cudaMemcpyAsync(stddev_out + r0, h->d_stat_f.p + nr, 4ull * nr, cudaMemcpyDeviceToHost, st));
+        } else {
+            CK(cudaMemcpyAsync(at_least_out + r0, h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
+        }
+        if (n_kmers_out) CK(cudaMemcpyAsync(n_kmers_out + r0, h->d_stat_n.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        r0 += nr;
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_read_medians(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                  uint16_t* median_out, float* average_out, float* stddev_out, uint32_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    return per_read_query(h, seqs, offsets, n_reads, flags, median_out, average_out, stddev_out, n_kmers_out, false, 0, nullptr);
+}
+
+extern "C" int kmgpu_median_at_least(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                     uint32_t cutoff, uint8_t* out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (!out && n_reads) return fail(KMGPU_EINVAL, "null output");
+    return per_read_query(h, seqs, offsets, n_reads, flags, nullptr, nullptr, nullptr, nullptr, true, cutoff, out);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// abundance distribution
+// ------------------------------------------------------------------------------------------------------
+extern "C" int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, const char* seqs, const uint64_t* offsets,
+                                            uint64_t n_reads, uint32_t flags, uint64_t* hist)
+{
+    if (!counts || !tracking || !hist) return fail(KMGPU_EINVAL, "null argument");
+    if (counts == tracking) return fail(KMGPU_EINVAL, "tracking sketch must differ from the counting sketch");
+    if (counts->device != tracking->device) return fail(KMGPU_EINVAL, "sketches live on different devices");
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    kmgpu_sketch* a = counts < tracking ? counts : tracking;
+    kmgpu_sketch* b = counts < tracking ? tracking : counts;
+    std::lock_guard<std::mutex> ga(a->mu);
+    std::lock_guard<std::mutex> gb(b->mu);
+    CKR(set_device(counts->device));
+    CK(cudaStreamSynchronize(counts->stream));
+    if (counts->kind == BYTE && counts->use_bigcount) CKR(sync_big_to_device(counts));
+    uint32_t nb = (counts->kind == BYTE && counts->use_bigcount) ? counts->n_big_dev : 0;
+    kmgpu_sketch* t = tracking;
+    cudaStream_t st = t->stream;
+    HashCfg H{counts->hash, counts->k};  // k-mers are hashed by the counting table (hashtable.cc:478-480)
+    Pred P;
+    memset(&P, 0, sizeof P);
+    CKR(t->d_hist.ensure(65536));
+    CK(cudaMemsetAsync(t->d_hist.p, 0, 65536 * 8, st));
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, counts->k, chunk_bases(), plan);
+    bool acgt = counts->hash == KMGPU_MURMUR && !(flags & KMGPU_CLEAN);
+    for (const ChunkPlan& c : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(t, seqs, c, flags, &cd, acgt));
+        if (cd.n_pos == 0) continue;
+        ChunkResult res;
+        Input in = make_input(cd);
+        CKR(ingest_chunk(t, 0, H, in, P, false, nullptr, &res));
+        if (!res.have_newbits || res.n_new == 0) continue;
+        CKR(t->d_counts.ensure(cd.n_pos));
+        launch_counts(0, counts->dev, H, in, counts->big_keys.p, counts->big_vals.p, nb, t->d_counts.p, nullptr, t->d_newbits.p, st);
+        k_hist<<<148 * 4, 256, 0, st>>>(t->d_counts.p, t->d_newbits.p, cd.n_pos, t->d_hist.p);
+        t->all_launches += 2;
+        CK(cudaGetLastError());
+    }
+    std::vector<unsigned long long> hh(65536);
+    CK(cudaMemcpyAsync(hh.data(), t->d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 65536; i++) hist[i] += hh[i];
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// merges
+// ------------------------------------------------------------------------------------------------------
+static int recount_occupied_locked(kmgpu_sketch* h)
+{
+    cudaStream_t st = h->stream;
+    CK(cudaMemsetAsync(&h->d_ctrl->n_z0, 0, sizeof(unsigned long long), st));
+    uint64_t nw = h->alloc_bytes[0] / 4;
+    unsigned g = (unsigned)std::min<uint64_t>((nw + 255) / 256, 148 * 16);
+    k_count_occupied<<<g, 256, 0, st>>>(h->kind, reinterpret_cast<const uint32_t*>(h->dev.tables[0]), nw, &h->d_ctrl->n_z0);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    h->n_occupied = h->h_ctrl->n_z0;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_recount_occupied(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    return recount_occupied_locked(h);
+}
+
+static bool same_shape(const kmgpu_sketch* a, const kmgpu_sketch* b)
+{
+    if (a->kind != b->kind || a->nt != b->nt) return false;
+    for (int i = 0; i < a->nt; i++)
+        if (a->sizes[i] != b->sizes[i]) return false;
+    return true;
+}
+
+extern "C" int kmgpu_merge(kmgpu_t* dst, kmgpu_t* src)
+{
+    if (!dst || !src) return fail(KMGPU_EINVAL, "null handle");
+    if (dst == src) return fail(KMGPU_EINVAL, "cannot merge a sketch into itself");
+    if (!same_shape(dst, src)) return fail(KMGPU_ESHAPE, "both nodegraphs must have same table sizes");  // storage.cc:65-67
+    kmgpu_sketch* a = dst < src ? dst : src;
+    kmgpu_sketch* b = dst < src ? src : dst;
+    std::lock_guard<std::mutex> ga(a->mu);
+    std::lock_guard<std::mutex> gb(b->mu);
+    if (dst->device != src->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+        if (!can) return fail(KMGPU_EUNSUPPORTED, "devices %d and %d have no peer access", dst->device, src->device);
+        CKR(set_device(dst->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+    }
+    CKR(set_device(src->device));
+    CK(cudaStreamSynchronize(src->stream));
+    CKR(set_device(dst->device));
+    for (int i = 0; i < dst->nt; i++) {
+        uint64_t nw = dst->alloc_bytes[i] / 4;
+        unsigned g = (unsigned)std::min<uint64_t>((nw + 255) / 256, 148 * 16);
+        k_merge<<<g, 256, 0, dst->stream>>>(dst->kind, reinterpret_cast<uint32_t*>(dst->dev.tables[i]),
+                                            reinterpret_cast<const uint32_t*>(src->dev.tables[i]), nw);
+        dst->all_launches += 1;
+    }
+    CK(cudaGetLastError());
+    return recount_occupied_locked(dst);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU: replicated sketches folded over NVLink peer memory
+// ------------------------------------------------------------------------------------------------------
+extern "C" int kmgpu_ipc_export(kmgpu_t* h, uint8_t* handles)
+{
+    if (!h || !handles) return fail(KMGPU_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KMGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    for (int i = 0; i < h->nt; i++) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, h->dev.tables[i]));
+        memcpy(handles + (size_t)i * KMGPU_IPC_HANDLE_BYTES, &mh, KMGPU_IPC_HANDLE_BYTES);
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_ipc_attach(kmgpu_t* h, int rank, int world, const uint8_t* all_handles)
+{
+    if (!h || !all_handles) return fail(KMGPU_EINVAL, "null argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
+    kmgpu_ipc_detach(h);
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    h->rank = rank;
+    h->world = world;
+    h->peers.assign(world, Peer());
+    for (int q = 0; q < world; q++) {
+        for (int i = 0; i < h->nt; i++) {
+            if (q == rank) {
+                h->peers[q].tables[i] = h->dev.tables[i];
+                continue;
+            }
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, all_handles + ((size_t)q * h->nt + i) * KMGPU_IPC_HANDLE_BYTES, KMGPU_IPC_HANDLE_BYTES);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+            h->peers[q].tables[i] = (uint8_t*)p;
+        }
+    }
+    h->peers_ipc = true;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_ipc_detach(kmgpu_t* h)
+{
+    if (!h) return KMGPU_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->peers_ipc) {
+        cudaSetDevice(h->device);
+        for (int q = 0; q < (int)h->peers.size(); q++) {
+            if (q == h->rank) continue;
+            for (int i = 0; i < h->nt; i++)
+                if (h->peers[q].tables[i]) cudaIpcCloseMemHandle(h->peers[q].tables[i]);
+        }
+    }
+    h->peers.clear();
+    h->peers_ipc = false;
+    h->rank = 0;
+    h->world = 1;
+    return KMGPU_OK;
+}
+
+static void slice_words(uint64_t n_words, int world, int r, uint64_t* w0, uint64_t* w1)
+{
+    uint64_t per = (n_words + world - 1) / world;
+    per = (per + 3) & ~3ull;  // 16-byte granules
+    *w0 = std::min<uint64_t>(n_words, per * r);
+    *w1 = std::min<uint64_t>(n_words, per * (r + 1));
+}
+
+// rank r folds word slice r of every peer's tables into its own copy
+static int reduce_scatter_locked(kmgpu_sketch* h)
+{
+    CKR(set_device(h->device));
+    for (int i = 0; i < h->nt; i++) {
+        uint64_t nw = h->alloc_bytes[i] / 4, w0, w1;
+        slice_words(nw, h->world, h->rank, &w0, &w1);
+        if (w1 <= w0) continue;
+        PeerPtrs pp;
+        pp.n = 0;
+        for (int q = 0; q < h->world; q++)
+            if (q != h->rank) pp.p[pp.n++] = reinterpret_cast<const uint32_t*>(h->peers[q].tables[i]);
+        unsigned g = (unsigned)std::min<uint64_t>((w1 - w0 + 255) / 256, 148 * 16);
+        k_merge_peers<<<g, 256, 0, h->stream>>>(h->kind, reinterpret_cast<uint32_t*>(h->dev.tables[i]), pp, w0, w1);
+        h->all_launches += 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+
+// rank r pulls every other slice from its owner
+static int all_gather_locked(kmgpu_sketch* h)
+{
+    CKR(set_device(h->device));
+    for (int i = 0; i < h->nt; i++) {
+        uint64_t nw = h->alloc_bytes[i] / 4;
+        for (int q = 0; q < h->world; q++) {
+            if (q == h->rank) continue;
+            uint64_t w0, w1;
+            slice_words(nw, h->world, q, &w0, &w1);
+            if (w1 <= w0) continue;
+            CK(cudaMemcpyAsync(h->dev.tables[i] + w0 * 4, h->peers[q].tables[i] + w0 * 4, (w1 - w0) * 4, cudaMemcpyDefault, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return recount_occupied_locked(h);
+}
+
+extern "C" int kmgpu_reduce_scatter_peers(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->peers.empty()) return fail(KMGPU_EINVAL, "no peers attached");
+    return reduce_scatter_locked(h);
+}
+
+extern "C" int kmgpu_all_gather_peers(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->peers.empty()) return fail(KMGPU_EINVAL, "no peers attached");
+    return all_gather_locked(h);
+}
+
+extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
+{
+    if (!reps || n < 1 || n > 8) return fail(KMGPU_EINVAL, "bad replica list");
+    for (int r = 1; r < n; r++)
+        if (!same_shape(reps[0], reps[r])) return fail(KMGPU_ESHAPE, "replicas must have the same shape");
+    if (n == 1) return KMGPU_OK;
+    // same-process peers: direct pointers, peer access enabled pairwise
+    for (int a = 0; a < n; a++) {
+        CKR(set_device(reps[a]->device));
+        for (int b = 0; b < n; b++) {
+            if (reps[b]->device == reps[a]->device) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, reps[a]->device, reps[b]->device));
+            if (!can) return fail(KMGPU_EUNSUPPORTED, "devices %d and %d have no peer access", reps[a]->device, reps[b]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(reps[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < n; r++) {
+        kmgpu_ipc_detach(reps[r]);
+        std::lock_guard<std::mutex> g(reps[r]->mu);
+        CKR(set_device(reps[r]->device));
+        CK(cudaStreamSynchronize(reps[r]->stream));
+        reps[r]->rank = r;
+        reps[r]->world = n;
+        reps[r]->peers.assign(n, Peer());
+        for (int q = 0; q < n; q++)
+            for (int i = 0; i < reps[r]->nt; i++) reps[r]->peers[q].tables[i] = reps[q]->dev.tables[i];
+        reps[r]->peers_ipc = false;
+    }
+    for (int r = 0; r < n; r++) {
+        std::lock_guard<std::mutex> g(reps[r]->mu);
+        CKR(reduce_scatter_locked(reps[r]));
+    }
+    for (int r = 0; r < n; r++) {
+        std::lock_guard<std::mutex> g(reps[r]->mu);
+        CKR(all_gather_locked(reps[r]));
+    }
+    for (int r = 0; r < n; r++) {
+        std::lock_guard<std::mutex> g(reps[r]->mu);
+        reps[r]->peers.clear();
+        reps[r]->rank = 0;
+        reps[r]->world = 1;
+    }
+    return KMGPU_OK;
+}

@@ -1,0 +1,580 @@
+// Kernels of the k-mer ingestion path.  Every kernel walks the 2-bit read stream (or a hash array) in
+// CTA tiles of TILE positions; a "position" is a base index of the chunk's concatenated stream and
+// doubles as the k-mer's rank in stream order (the order the reference consumes k-mers at one thread).
+#pragma once
+#include "kmgpu_device.cuh"
+
+namespace kmgpu {
+
+// per-chunk control block (device), zeroed before each chunk
+struct Ctrl {
+    unsigned long long n_kmers;   // k-mers consumed (valid and passing band/mask)
+    unsigned long long n_z0;      // updates that occupied a bin of table 0      -> n_occupied
+    unsigned long long n_zbits;   // updates that occupied a bin of any table    -> #keys for resolution
+    unsigned long long n_allsat;  // k-mers that saw every table saturated (bigcount candidates)
+    unsigned long long n_cross;   // updates that moved a byte 254 -> 255 in this chunk
+    unsigned long long n_unique;  // result of the first-toucher resolution
+    unsigned long long n_events;  // records appended by k_events / k_cross_replay
+    unsigned long long non_acgt;  // pack kernel: bytes outside ACGT seen in raw mode
+};
+
+// flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
+constexpr uint32_t F_CONSUMED = 1u << 31;
+constexpr int F_MAXT = 10;
+
+struct Input {
+    const uint64_t* words;   // SRC 0: packed stream of the chunk (+ TILE_PAD_WORDS zero words)
+    const uint32_t* offs;    //        read offsets (n_reads + 1), chunk relative
+    uint32_t n_reads;
+    const uint64_t* hashes;  // SRC 1: hash array
+    uint32_t n_pos;          // stream positions (bases) or number of hashes
+};
+
+struct TileSmem {
+    uint64_t words[TILE / 32 + TILE_PAD_WORDS];
+    uint32_t valid[TILE / 32];
+    uint32_t lut[256];
+    uint32_t r_lo, r_hi;
+    unsigned long long acc[8];
+};
+
+// ---- tile staging --------------------------------------------------------------------------------
+// Loads the tile's slice of the packed stream into shared memory (coalesced 8-byte loads), finds the
+// reads overlapping the tile with two binary searches, and builds the bitmap of positions where a
+// k-mer starts (start + k <= end of its read; reads shorter than k yield none, kmer_hash.cc:278-296).
+template <int HK, int SRC>
+__device__ __forceinline__ void tile_begin(const Input& in, int k, uint32_t t0, TileSmem& sm)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < TILE / 32; i += THREADS) sm.valid[i] = 0;
+    if (tid < 8) sm.acc[tid] = 0;
+    if (SRC == 1) {
+        __syncthreads();
+        uint32_t n = in.n_pos - t0 < (uint32_t)TILE ? in.n_pos - t0 : (uint32_t)TILE;
+        for (int i = tid; i < TILE / 32; i += THREADS) {
+            uint32_t lo = i * 32;
+            sm.valid[i] = lo >= n ? 0u : (n - lo >= 32 ? ~0u : ((1u << (n - lo)) - 1));
+        }
+        __syncthreads();
+        return;
+    }
+    if (HK == MURMUR) fill_lut4(sm.lut, tid, THREADS);
+    const uint64_t* src = in.words + (t0 >> 5);
+    for (int i = tid; i < TILE / 32 + TILE_PAD_WORDS; i += THREADS) sm.words[i] = __ldg(src + i);
+    if (tid == 0) {
+        // r_lo = last read with offs[r] <= t0 ; r_hi = first read with offs[r] >= t0 + TILE
+        uint32_t lo = 0, hi = in.n_reads;  // search in offs[0..n_reads]
+        while (lo < hi) {
+            uint32_t mid = (lo + hi + 1) >> 1;
+            if (in.offs[mid] <= t0) lo = mid; else hi = mid - 1;
+        }
+        sm.r_lo = lo;
+        uint32_t end = t0 + TILE;
+        uint32_t a = lo, b = in.n_reads;
+        while (a < b) {
+            uint32_t mid = (a + b) >> 1;
+            if (in.offs[mid] >= end) b = mid; else a = mid + 1;
+        }
+        sm.r_hi = a;
+    }
+    __syncthreads();
+    for (uint32_t r = sm.r_lo + tid; r < sm.r_hi; r += THREADS) {
+        uint32_t s = in.offs[r], e = in.offs[r + 1];
+        if (e - s < (uint32_t)k) continue;
+        uint32_t first = s > t0 ? s : t0;
+        uint32_t last = e - k;  // inclusive
+        if (last >= t0 + TILE) last = t0 + TILE - 1;
+        if (first > last) continue;
+        uint32_t a = first - t0, b = last - t0;
+        for (uint32_t wd = a >> 5; wd <= (b >> 5); wd++) {
+            uint32_t lo = wd == (a >> 5) ? (a & 31) : 0;
+            uint32_t hi = wd == (b >> 5) ? (b & 31) : 31;
+            uint32_t m = (hi == 31 ? ~0u : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+            atomicOr(&sm.valid[wd], m);
+        }
+    }
+    __syncthreads();
+}
+
+template <int HK, int SRC>
+__device__ __forceinline__ bool tile_valid(const TileSmem& sm, uint32_t lp)
+{
+    return (sm.valid[lp >> 5] >> (lp & 31)) & 1u;
+}
+
+template <int HK, int SRC>
+__device__ __forceinline__ uint64_t tile_hash(const Input& in, const TileSmem& sm, int k, uint32_t t0, uint32_t lp)
+{
+    if (SRC == 1) return in.hashes[t0 + lp];
+    if (HK == TWOBIT) return hash_twobit(sm.words, lp, k);
+    return hash_murmur(sm.words, sm.lut, lp, k);
+}
+
+__device__ __forceinline__ void tile_accumulate(TileSmem& sm, int slot, unsigned long long v)
+{
+    v = __reduce_add_sync(0xffffffffu, (unsigned)v);  // per-thread values are < 2^32 per tile
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm.acc[slot], v);
+}
+
+// count of a k-mer in an arbitrary sketch: min over tables (Storage::get_count); no bigcount here
+__device__ __forceinline__ uint32_t sketch_count(const SketchDev& S, uint64_t h)
+{
+    uint32_t mn = S.kind == BYTE ? 255u : S.kind == NIBBLE ? 15u : 1u;
+    for (int i = 0; i < S.n_tables; i++) {
+        uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+        uint32_t c = S.kind == BYTE ? read_byte(S.tables[i], bin)
+                   : S.kind == NIBBLE ? read_nibble(S.tables[i], bin) : read_bit(S.tables[i], bin);
+        mn = c < mn ? c : mn;
+    }
+    return mn;
+}
+
+__device__ __forceinline__ bool pred_pass(const Pred& P, const SketchDev& M, uint64_t h)
+{
+    if (P.band_on && !(h >= P.band_lo && h < P.band_hi)) return false;
+    if (P.mask_on) {
+        uint32_t c = sketch_count(M, h);
+        return P.mask_ge ? c >= P.mask_threshold : c <= P.mask_threshold;
+    }
+    return true;
+}
+
+// ---- ingest --------------------------------------------------------------------------------------
+// The hot kernel.  For every k-mer of the tile: hash, N x (mod, saturating update).  Per position it
+// leaves a flags word (which tables it saw empty / saturated / about to saturate) used by the exact
+// resolutions that follow only when needed.  Replaces consume_string + Storage::add
+// (src/oxli/hashtable.cc:280-294, include/oxli/storage.hh:571-624).
+template <int KIND, int HK, int SRC, int NT, bool PRED>
+__global__ void __launch_bounds__(THREADS)
+k_ingest(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __restrict__ flags, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    const int nt = NT > 0 ? NT : S.n_tables;
+    unsigned n_k = 0, n_z0 = 0, n_zb = 0, n_as = 0, n_cr = 0;
+    const uint32_t allmask = (1u << nt) - 1;
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        uint32_t fl = 0;
+        if (tile_valid<HK, SRC>(sm, lp)) {
+            uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+            if (!PRED || pred_pass(P, M, h)) {
+                uint32_t z = 0, s = 0, c = 0;
+                if (NT > 0) {
+                    uint64_t bins[NT > 0 ? NT : 1];
+#pragma unroll
+                    for (int i = 0; i < NT; i++) bins[i] = mod_magic(h, S.sizes[i], S.magic[i]);
+#pragma unroll
+                    for (int i = 0; i < NT; i++) {
+                        uint32_t old = update_counter<KIND>(S.tables[i], bins[i]);
+                        z |= (old == 0) << i;
+                        if (KIND == BYTE) {
+                            s |= (old == 255u) << i;
+                            c |= (old == 254u) << i;
+                        }
+                    }
+                } else {
+                    for (int i = 0; i < nt; i++) {
+                        uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+                        uint32_t old = update_counter<KIND>(S.tables[i], bin);
+                        z |= (old == 0) << i;
+                        if (KIND == BYTE) {
+                            s |= (old == 255u) << i;
+                            c |= (old == 254u) << i;
+                        }
+                    }
+                }
+                fl = F_CONSUMED | z | (s << 10) | (c << 20);
+                n_k++;
+                n_z0 += z & 1;
+                n_zb += __popc(z);
+                n_as += (s == allmask);
+                n_cr += __popc(c);
+            }
+        }
+        flags[t0 + lp] = fl;
+    }
+    tile_accumulate(sm, 0, n_k);
+    tile_accumulate(sm, 1, n_z0);
+    tile_accumulate(sm, 2, n_zb);
+    tile_accumulate(sm, 3, n_as);
+    tile_accumulate(sm, 4, n_cr);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sm.acc[0]) atomicAdd(&ctrl->n_kmers, sm.acc[0]);
+        if (sm.acc[1]) atomicAdd(&ctrl->n_z0, sm.acc[1]);
+        if (sm.acc[2]) atomicAdd(&ctrl->n_zbits, sm.acc[2]);
+        if (sm.acc[3]) atomicAdd(&ctrl->n_allsat, sm.acc[3]);
+        if (sm.acc[4]) atomicAdd(&ctrl->n_cross, sm.acc[4]);
+    }
+}
+
+// ---- exact "is new" resolution ----------------------------------------------------------------------
+// Storage::add reports a k-mer as new iff one of its bins was empty when it arrived IN STREAM ORDER
+// (storage.hh:581-591,619-621; bits: :185-195).  Atomics give arrival in memory order instead, so the
+// bins occupied during this chunk (flags "saw 0", exactly one update per such bin) are registered in a
+// hash table, every consumed k-mer of the chunk then lowers the stamp of each registered bin it
+// touches to its own position, and the distinct stamps are the new k-mers.
+//   which = 0: register bins flagged "saw 0" (shift 0) ; which = 2: bins flagged "saw 254" (shift 20)
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_register(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, int shift, uint64_t* keys, uint64_t mask)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    // cheap pre-check: does any position of the tile carry the flag?
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int mine = 0;
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS)
+        mine |= ((flags[t0 + lp] >> shift) & 0x3ffu) != 0;
+    if (mine) any = 1;
+    __syncthreads();
+    if (!any) return;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        uint32_t m = (flags[t0 + lp] >> shift) & 0x3ffu;
+        if (!m) continue;
+        uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        while (m) {
+            int i = __ffs(m) - 1;
+            m &= m - 1;
+            ht_insert(keys, mask, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+        }
+    }
+}
+
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_replay(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, const uint64_t* __restrict__ keys,
+         uint32_t* __restrict__ stamps, uint64_t mask)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        if (!(flags[t0 + lp] & F_CONSUMED)) continue;
+        uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        for (int i = 0; i < S.n_tables; i++) {
+            uint64_t s = ht_find(keys, mask, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+            if (s != ~0ull) atomicMin(&stamps[s], t0 + lp);
+        }
+    }
+}
+
+// one bit per position that is the first toucher of at least one newly occupied bin
+__global__ void k_mark(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ stamps, uint64_t n_slots,
+                       uint32_t* newbits, Ctrl* ctrl)
+{
+    unsigned cnt = 0;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        if (keys[s] == HT_EMPTY) continue;
+        uint32_t p = stamps[s];
+        uint32_t bit = 1u << (p & 31);
+        uint32_t old = atomicOr(&newbits[p >> 5], bit);
+        cnt += !(old & bit);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_unique, (unsigned long long)cnt);
+}
+
+// ---- bigcount support --------------------------------------------------------------------------------
+// k-mers that found all N bytes saturated (ByteStorage::add storage.hh:606-617) are shipped to the host,
+// which owns the std::unordered_map and applies them in stream order.
+struct Event {
+    uint64_t hash;
+    uint32_t pos;
+    uint32_t info;  // k_cross_replay: crossmask | satmask << 10 | allsat_after << 30
+};
+
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_events(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, Event* out, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    const uint32_t allmask = (1u << S.n_tables) - 1;
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int mine = 0;
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS)
+        mine |= ((flags[t0 + lp] >> 10) & 0x3ffu) == allmask;
+    if (mine) any = 1;
+    __syncthreads();
+    if (!any) return;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        uint32_t f = flags[t0 + lp];
+        if (((f >> 10) & 0x3ffu) != allmask || !(f & F_CONSUMED)) continue;
+        Event e;
+        e.hash = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        e.pos = t0 + lp;
+        e.info = 0;
+        out[atomicAdd(&ctrl->n_events, 1ull)] = e;
+    }
+}
+
+// chunk in which some byte went 254 -> 255: every consumed k-mer touching such a bin is reported with
+// what it saw, so the host can rebuild the stream-order moment each bin saturated.
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_cross_replay(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, const uint64_t* __restrict__ keys,
+               uint64_t mask, Event* out, unsigned long long cap, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        uint32_t f = flags[t0 + lp];
+        if (!(f & F_CONSUMED)) continue;
+        uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        uint32_t cross = 0, allsat = 1;
+        for (int i = 0; i < S.n_tables; i++) {
+            uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+            if (ht_find(keys, mask, ht_key(bin, i)) != ~0ull) cross |= 1u << i;
+            else if (read_byte(S.tables[i], bin) != 255u) allsat = 0;
+        }
+        if (!cross) continue;
+        Event e;
+        e.hash = h;
+        e.pos = t0 + lp;
+        e.info = cross | (((f >> 10) & 0x3ffu) << 10) | (allsat << 30);
+        unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+        if (at < cap) out[at] = e;
+    }
+}
+
+// ---- queries ---------------------------------------------------------------------------------------
+// Storage::get_count per position (min over tables; saturated bytes looked up in the sorted device copy
+// of the bigcount map, storage.hh:640-647), optionally also the hash.
+template <int KIND, int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_counts(SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ big_keys, const uint16_t* __restrict__ big_vals,
+         uint32_t n_big, uint16_t* __restrict__ counts, uint64_t* __restrict__ hashes, const uint32_t* __restrict__ only_bits)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        uint32_t p = t0 + lp;
+        if (only_bits && !((only_bits[p >> 5] >> (p & 31)) & 1u)) continue;
+        uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        if (hashes) hashes[p] = h;
+        if (!counts) continue;
+        uint32_t mn = counter_cap<KIND>();
+        for (int i = 0; i < S.n_tables; i++) {
+            uint32_t c = read_counter<KIND>(S.tables[i], mod_magic(h, S.sizes[i], S.magic[i]));
+            mn = c < mn ? c : mn;
+        }
+        if (KIND == BYTE && mn == 255u && n_big) {
+            uint32_t lo = 0, hi = n_big;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (big_keys[mid] < h) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n_big && big_keys[lo] == h) mn = big_vals[lo];
+        }
+        counts[p] = (uint16_t)mn;
+    }
+}
+
+// abundance histogram over the positions marked new in the tracking filter
+// (Hashtable::abundance_distribution, src/oxli/hashtable.cc:480-489)
+__global__ void k_hist(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ newbits, uint32_t n_pos,
+                       unsigned long long* hist)
+{
+    __shared__ unsigned int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
+        if (!((newbits[p >> 5] >> (p & 31)) & 1u)) continue;
+        uint32_t c = counts[p];
+        if (c < 256) atomicAdd(&sh[c], 1u);
+        else atomicAdd(&hist[c], 1ull);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// per-read statistics over the per-position counts: one warp per read.
+//   get_median_count (src/oxli/hashtable.cc:299-328): median = sorted[n/2]; mean and population stddev in
+//   float with the reference's left-to-right summation order (no FMA contraction);
+//   median_at_least (hashtable.cc:333-364): #(count >= cutoff) >= (unsigned)(0.5 + float(n)/2).
+__global__ void __launch_bounds__(256)
+k_read_stats(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ offs, uint32_t n_reads, int k,
+             uint16_t* median, float* average, float* stddev, uint32_t* n_kmers, uint32_t cutoff, uint8_t* at_least)
+{
+    __shared__ unsigned int hist[8][256];
+    __shared__ uint16_t buf[8][256];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * 8 + wid;
+    if (r >= n_reads) return;
+    const uint32_t s = offs[r], e = offs[r + 1];
+    const uint32_t n = e - s >= (uint32_t)k ? e - s - k + 1 : 0;
+    if (n_kmers && lane == 0) n_kmers[r] = n;
+    if (n == 0) {
+        if (lane == 0) {
+            if (median) median[r] = 0;
+            if (average) average[r] = 0.f;
+            if (stddev) stddev[r] = 0.f;
+            if (at_least) at_least[r] = 2;
+        }
+        return;
+    }
+    const uint16_t* c = counts + s;
+    if (at_least) {
+        unsigned hit = 0;
+        for (uint32_t i = lane; i < n; i += 32) hit += c[i] >= cutoff;
+        hit = __reduce_add_sync(0xffffffffu, hit);
+        unsigned min_req = (unsigned)(0.5 + (double)((float)n / 2));
+        if (lane == 0) at_least[r] = hit >= min_req;
+    }
+    if (!median) return;
+    // radix select of rank n/2 over 16-bit values: high byte, then low byte
+    const uint32_t rank = n / 2;
+    uint32_t prefix = 0, remaining = rank;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = lane; i < 256; i += 32) hist[wid][i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            uint32_t v = c[i];
+            if (pass == 0) atomicAdd(&hist[wid][v >> 8], 1u);
+            else if ((v >> 8) == prefix) atomicAdd(&hist[wid][v & 255], 1u);
+        }
+        __syncwarp();
+        // lane 0 walks the histogram (256 steps, negligible next to the table lookups that fed it)
+        uint32_t sel = 0;
+        if (lane == 0) {
+            uint32_t acc = 0;
+            for (int b = 0; b < 256; b++) {
+                uint32_t hb = hist[wid][b];
+                if (remaining < acc + hb) { sel = b; remaining -= acc; break; }
+                acc += hb;
+            }
+        }
+        sel = __shfl_sync(0xffffffffu, sel, 0);
+        remaining = __shfl_sync(0xffffffffu, remaining, 0);
+        prefix = pass == 0 ? sel : ((prefix << 8) | sel);
+        __syncwarp();
+    }
+    if (lane == 0) median[r] = (uint16_t)prefix;
+    // float mean / stddev, strictly sequential like the reference
+    float avg = 0.f;
+    for (uint32_t base = 0; base < n; base += 256) {
+        uint32_t m = n - base < 256 ? n - base : 256;
+        for (uint32_t i = lane; i < m; i += 32) buf[wid][i] = c[base + i];
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t i = 0; i < m; i++) avg = __fadd_rn(avg, (float)buf[wid][i]);
+        __syncwarp();
+    }
+    avg = __shfl_sync(0xffffffffu, avg, 0);
+    avg = __fdiv_rn(avg, (float)n);
+    float var = 0.f;
+    for (uint32_t base = 0; base < n; base += 256) {
+        uint32_t m = n - base < 256 ? n - base : 256;
+        for (uint32_t i = lane; i < m; i += 32) buf[wid][i] = c[base + i];
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t i = 0; i < m; i++) {
+                float d = __fsub_rn((float)buf[wid][i], avg);
+                var = __fadd_rn(var, __fmul_rn(d, d));
+            }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        var = __fdiv_rn(var, (float)n);
+        average[r] = avg;
+        stddev[r] = __fsqrt_rn(var);
+    }
+}
+
+// ---- host feed: ASCII -> 2-bit stream -----------------------------------------------------------------
+// One thread per output word (32 bases).  clean != 0: Read::set_clean_seq then twobit_repr
+// (read_parsers.cc:53-69, kmer_hash.hh:70-72): A/a 0, T/t 1, C/c 2, G/g 3, anything else 0 ('A').
+// clean == 0: twobit_repr alone: 'A' 0, 'T' 1, 'C' 2, anything else 3; bytes outside ACGT are counted so the
+// Murmur path (which hashes the letters themselves) can refuse them.
+__global__ void k_pack(const uint8_t* __restrict__ ascii, uint32_t n_bases, int clean, uint64_t* __restrict__ words,
+                       uint32_t n_words, Ctrl* ctrl)
+{
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint64_t v = 0;
+    unsigned bad = 0;
+    uint32_t base = w * 32;
+    if (base < n_bases) {
+        uint32_t m = n_bases - base < 32 ? n_bases - base : 32;
+        for (uint32_t j = 0; j < m; j++) {
+            uint8_t ch = ascii[base + j];
+            uint32_t code;
+            if (clean) {
+                uint8_t u = ch & 0xDF;  // fold case for letters
+                bool letter = (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z');
+                code = !letter ? 0 : u == 'T' ? 1 : u == 'C' ? 2 : u == 'G' ? 3 : 0;
+            } else {
+                code = ch == 'A' ? 0 : ch == 'T' ? 1 : ch == 'C' ? 2 : 3;
+                bad += !(ch == 'A' || ch == 'T' || ch == 'C' || ch == 'G');
+            }
+            v |= (uint64_t)code << (62 - 2 * j);
+        }
+    }
+    words[w] = v;
+    if (bad) atomicAdd(&ctrl->non_acgt, (unsigned long long)bad);
+}
+
+// ---- merges -------------------------------------------------------------------------------------------
+// dst = dst (+) src over 32-bit words: bytes saturate at 255 (__vaddus4), nibbles at 15, bits OR
+// (BitStorage::update_from, src/oxli/storage.cc:63-96, extended to the counting storages).
+__device__ __forceinline__ uint32_t merge_word(int kind, uint32_t a, uint32_t b)
+{
+    if (kind == BYTE) return __vaddus4(a, b);
+    if (kind == BIT) return a | b;
+    uint32_t lo = __vminu4((a & 0x0F0F0F0Fu) + (b & 0x0F0F0F0Fu), 0x0F0F0F0Fu);
+    uint32_t hi = __vminu4(((a >> 4) & 0x0F0F0F0Fu) + ((b >> 4) & 0x0F0F0F0Fu), 0x0F0F0F0Fu);
+    return lo | (hi << 4);
+}
+
+__global__ void k_merge(int kind, uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n_words)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = merge_word(kind, dst[i], src[i]);
+}
+
+// fold word range [w0, w1) of up to 8 peers into dst (peer pointers are NVLink-mapped device memory)
+struct PeerPtrs {
+    const uint32_t* p[8];
+    int n;
+};
+__global__ void k_merge_peers(int kind, uint32_t* __restrict__ dst, PeerPtrs peers, uint64_t w0, uint64_t w1)
+{
+    for (uint64_t i = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < w1; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t a = dst[i];
+        for (int j = 0; j < peers.n; j++) a = merge_word(kind, a, __ldcg(peers.p[j] + i));
+        dst[i] = a;
+    }
+}
+
+// number of occupied bins of a table (non-zero bytes / nibbles / set bits) — n_occupied after a merge or upload
+__global__ void k_count_occupied(int kind, const uint32_t* __restrict__ t, uint64_t n_words, unsigned long long* out)
+{
+    unsigned long long cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = t[i];
+        if (kind == BIT) cnt += __popc(v);
+        else if (kind == BYTE) cnt += __popc(__vcmpne4(v, 0) & 0x01010101u);
+        else {
+            uint32_t nz = (v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x11111111u;
+            cnt += __popc(nz);
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, (unsigned)cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+}  // namespace kmgpu
