@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — k-mers/s ingested into Countgraph (k=20, N=4) on B200, beside the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference CPU arm (rank 0 only)
+
+Workload (BASELINE.json metric): Countgraph/ByteStorage k=20, N=4 tables of ~1e8 bytes
+(get_n_primes_near_x(4, 1e8), 400 MB — larger than the 126 MB L2), bigcount on at N=1, synthetic 150 bp reads
+sampled at 30x from a uniform random genome.  A step = one pass of the hot path over one batch of R reads.
+P distinct batches are cycled; after every P steps the sketch is reset (one "job" = P batches), so no step
+ever runs on saturated counters.
+
+value  : k-mers/s with the packed batches already resident in HBM (kmgpu_consume_batch), device-timed with
+         CUDA events on the library's own stream, max over ranks.
+e2e    : the same through kmgpu_consume_reads with ASCII reads in pinned HOST memory: H2D copy, 2-bit packing
+         on the device, ingestion, D2H of the per-chunk result block — all inside the timed region.
+N > 1  : one process per GPU (torchrun), each ingests its own read shard into its own replica (weak scaling, no
+         data-path collective per step); the replicas are merged once per job by the saturating-add NVLink
+         reduction (reduce-scatter + all-gather over CUDA-IPC peer memory), inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 20
+N_TABLES = 4
+TABLE_X = int(1e8)
+READ_LEN = 150
+COVERAGE = 30
+KMERS_PER_READ = READ_LEN - K + 1
+ALGO_BYTES_PER_KMER = N_TABLES * 64          # 32 B sector in + 32 B sector out per counter update
+
+
+def primes_near_x(n, x):
+    """get_n_primes_near_x (include/oxli/hashtable.hh:99-123) — host-side sizing, same as khmer_args does."""
+    def is_prime(v):
+        if v < 2:
+            return False
+        if v % 2 == 0:
+            return v == 2
+        i = 3
+        while i * i <= v:
+            if v % i == 0:
+                return False
+            i += 2
+        return True
+    out = []
+    c = x - 1
+    if c % 2 == 0:
+        c -= 1
+    while len(out) < n and c > 0:
+        if is_prime(c):
+            out.append(c)
+        c -= 2
+    return out
+
+
+def synth_batch(seed, n_reads, pinned=False):
+    """R reads of exactly 150 bp, uniform start, random strand, genome G = 5R (30x) — SURVEY.md §8d."""
+    rng = np.random.default_rng(seed)
+    genome_len = max(READ_LEN + 1, n_reads * READ_LEN // COVERAGE)
+    g = rng.integers(0, 4, genome_len, dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    if pinned:
+        import torch
+        t = torch.empty(n_reads * READ_LEN, dtype=torch.uint8, pin_memory=True)
+        buf = t.numpy()
+    else:
+        t = None
+        buf = np.empty(n_reads * READ_LEN, dtype=np.uint8)
+    view = buf.reshape(n_reads, READ_LEN)
+    step = 1 << 18
+    for i0 in range(0, n_reads, step):
+        m = min(step, n_reads - i0)
+        starts = rng.integers(0, genome_len - READ_LEN, m)
+        strands = rng.integers(0, 2, m).astype(bool)
+        codes = g[starts[:, None] + np.arange(READ_LEN)[None, :]]
+        codes[strands] = (3 - codes[strands])[:, ::-1]
+        view[i0:i0 + m] = lut[codes]
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    return buf, off, t
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ingest_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref when it was compiled, else the port)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_reads, threads, seed=4242, repeats=1):
+    """k-mers/s of the reference's consume_seqfile on a FASTA of n_reads synthetic reads, T threads sharing one
+    parser (scripts/load-into-counting.py:145-158).  Timer around the consume loop only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    buf, off, _ = synth_batch(seed, n_reads)
+    sizes = primes_near_x(N_TABLES, TABLE_X)
+    kind = "reference" if ol.have_ref() else "port"
+    times = []
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "reads.fa")
+        if kind == "reference":
+            with open(path, "wb") as fh:
+                rows = buf.reshape(n_reads, READ_LEN)
+                hdr = np.frombuffer(b">r\n", dtype=np.uint8)
+                block = np.empty((n_reads, READ_LEN + 4), dtype=np.uint8)
+                block[:, :3] = hdr
+                block[:, 3:3 + READ_LEN] = rows
+                block[:, -1] = ord("\n")
+                fh.write(block.tobytes())
+        for _ in range(repeats):
+            if kind == "reference":
+                sk = ol.Ref("Countgraph", K, sizes)
+                sk.set_use_bigcount(True)
+                t0 = time.perf_counter()
+                _, kmers = sk.consume_seqfile(path, threads=threads)
+                times.append(time.perf_counter() - t0)
+            else:
+                threads = 1
+                sk = ol.Oracle("Countgraph", K, sizes)
+                sk.set_use_bigcount(True)
+                t0 = time.perf_counter()
+                kmers = sk.L.ko_consume_reads(sk.h, buf.ctypes.data_as(ol.C.c_char_p), off.ctypes.data_as(ol.u64p),
+                                              n_reads, 1, 0, 0, 0)
+                times.append(time.perf_counter() - t0)
+            del sk
+    return kmers, times, kind, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_reads = args.ref_reads
+    kmers, times, kind, threads = cpu_reference_run(n_reads, threads, repeats=args.steps + args.warmup)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = kmers * len(timed) / total
+    sample = "%d synthetic 150 bp reads (%d k-mers) per step from a FASTA file, Countgraph k=%d N=%d x=%d" % (
+        n_reads, kmers, K, N_TABLES, TABLE_X)
+    line = {
+        "impl": "reference", "metric": "kmers_per_sec_countgraph_k20_N4", "value": value, "unit": "k-mers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "load-into-counting Countgraph k=20 N=4 x=1e8 bigcount, synthetic 150bp 30x reads",
+                   "reads_per_step": n_reads, "threads": threads},
+        "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from khmer_b200 import cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if cabi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    R = args.reads
+    P = args.batches
+    sizes = primes_near_x(N_TABLES, TABLE_X)
+    sk = cabi.Sketch(cabi.BYTE, cabi.TWOBIT, K, sizes, device=local_rank)
+    bigcount = world == 1     # replicated sketches cannot keep bigcount exact
+    sk.set_use_bigcount(bigcount)
+
+    # synthetic batches: pinned host ASCII (e2e leg) and device-resident packed (value leg)
+    host = []
+    dev = []
+    for b in range(P):
+        buf, off, keep = synth_batch(1000 * (rank + 1) + b, R, pinned=True)
+        host.append((buf, off, keep))
+        dev.append(cabi.Batch((buf, off), K, clean=True, device=local_rank))
+
+    if world > 1:
+        handles = torch.from_numpy(sk.ipc_export()).cuda()
+        allh = [torch.empty_like(handles) for _ in range(world)]
+        dist.all_gather(allh, handles)
+        sk.ipc_attach(rank, world, torch.cat(allh).cpu().numpy())
+
+    def merge_replicas():
+        if world == 1:
+            return
+        sk.reduce_scatter_peers()
+        barrier()
+        sk.all_gather_peers()
+        barrier()
+
+    def job_boundary(step):
+        """after every P steps: fold the replicas (N > 1), then start a new job on empty tables"""
+        if (step + 1) % P == 0:
+            merge_replicas()
+            sk.reset()
+
+    def run_steps(n, leg, first):
+        kmers = 0
+        for s in range(first, first + n):
+            if leg == "hbm":
+                kmers += sk.consume_batch(dev[s % P])
+            else:
+                buf, off, _ = host[s % P]
+                kmers += sk.consume_reads((buf, off), clean=True)
+            job_boundary(s)
+        return kmers
+
+    results = {}
+    clocks = None
+    for leg in ("hbm", "e2e"):
+        sk.reset()
+        run_steps(args.warmup, leg, 0)
+        # start the timed region on a job boundary so every timed step sees the same table states
+        first = ((args.warmup + P - 1) // P) * P
+        run_steps(first - args.warmup, leg, args.warmup)
+        barrier()
+        sk.profile_reset()
+        sampler = ClockSampler(local_rank) if leg == "hbm" and rank == 0 else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        t0 = time.time()
+        sk.timer_start()
+        kmers = run_steps(args.steps, leg, first)
+        if args.steps % P != 0:
+            merge_replicas()
+        ms = sk.timer_stop()
+        barrier()
+        t1 = time.time()
+        if sampler:
+            clocks = sampler.stop(t0, t1)
+        kern_ms, kern_launches, all_launches = sk.profile_get()
+        results[leg] = {"ms": max_over_ranks(ms), "kmers": sum_over_ranks(kmers), "kern_ms": kern_ms,
+                        "kern_launches": kern_launches, "launches": all_launches, "local_kmers": kmers,
+                        "wall_ms": 1e3 * (t1 - t0)}
+
+    hbm, e2e = results["hbm"], results["e2e"]
+    value = hbm["kmers"] / (hbm["ms"] * 1e-3)
+    e2e_value = e2e["kmers"] / (e2e["ms"] * 1e-3)
+    peak, peak_src = measured_peak()
+    # dominant kernel = k_ingest; algorithmic bytes per launch = k-mers of the launch x N x 64 B
+    kmers_per_launch = hbm["local_kmers"] / max(1, hbm["kern_launches"])
+    avg_launch_ms = hbm["kern_ms"] / max(1, hbm["kern_launches"])
+    achieved = kmers_per_launch * ALGO_BYTES_PER_KMER / (avg_launch_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "kernel": "k_ingest<BYTE,TWOBIT,N=4>", "kernel_ms_per_launch": avg_launch_ms,
+                "kmers_per_launch": kmers_per_launch, "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
+                "peak_source": peak_src, "kernel_share_of_step": hbm["kern_ms"] / hbm["ms"] if world == 1 else None,
+                "traffic_source": traffic.get("source") if traffic else None}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        kmers_c, times, kind, threads = cpu_reference_run(args.cpu_reads, threads)
+        cpu = {"value": kmers_c / times[0], "unit": "k-mers/s", "cores": threads, "kind": kind,
+               "sample": "%d synthetic 150 bp reads (%d k-mers), same table shape, one timed consume_seqfile with %d "
+                         "threads sharing one parser" % (args.cpu_reads, kmers_c, threads)}
+
+    if rank == 0:
+        bases = R * READ_LEN
+        line = {
+            "metric": "kmers_per_sec_countgraph_k20_N4", "value": value, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": hbm["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "load-into-counting Countgraph k=20 N=4 x=1e8 (4 x ~100 MB byte tables), synthetic "
+                                   "150bp 30x reads", "reads_per_step_per_gpu": R, "kmers_per_step_per_gpu": R * KMERS_PER_READ,
+                       "batches_per_job": P, "bigcount": bigcount, "l2": "tables (400 MB) larger than L2 (126 MB); no flush",
+                       "parallelism": "replicated sketch per GPU, disjoint read shards, saturating-add NVLink merge per job"
+                       if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": bases + 4 * (R + 1),
+                    "d2h_bytes_per_step": 64 * ((bases + (32 << 20) - 1) // (32 << 20)), "ms_per_step": e2e["ms"] / args.steps},
+            "gpu_launches": int(hbm["launches"]), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=2_000_000, help="reads per step per GPU")
+    ap.add_argument("--batches", type=int, default=4, help="distinct batches cycled (= steps per job)")
+    ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--ref-reads", type=int, default=250_000, help="reads per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

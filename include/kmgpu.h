@@ -87,6 +87,9 @@ int kmgpu_device_count(int* n);
 int kmgpu_create(int storage, int hash, int ksize, int n_tables, const uint64_t* sizes, int device,
                  kmgpu_t** out);
 int kmgpu_destroy(kmgpu_t* h);
+/* back to the freshly constructed state: zero tables, counters and bigcount map (what constructing a new
+ * Hashtable does, without re-allocating) */
+int kmgpu_reset(kmgpu_t* h);
 
 /* Storage::set_use_bigcount / get_use_bigcount (src/oxli/storage.cc:50-61): only ByteStorage. */
 int kmgpu_set_use_bigcount(kmgpu_t* h, int on);
@@ -197,6 +200,10 @@ int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
 int kmgpu_profile_reset(kmgpu_t* h);
 int kmgpu_profile_get(kmgpu_t* h, double* ingest_kernel_ms, uint64_t* ingest_launches, uint64_t* all_launches);
 int kmgpu_sync(kmgpu_t* h);
+/* Device timer: two CUDA events on the handle's stream bracket whatever the handle executes in between
+ * (copies included); stop synchronises and returns the elapsed device time in ms. */
+int kmgpu_timer_start(kmgpu_t* h);
+int kmgpu_timer_stop(kmgpu_t* h, double* ms);
 
 #ifdef __cplusplus
 }

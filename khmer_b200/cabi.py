@@ -32,7 +32,8 @@ SYMBOLS = [
     "kmgpu_table_nbytes", "kmgpu_download_table", "kmgpu_upload_table", "kmgpu_bigcount_size",
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
-    "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync",
+    "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
+    "kmgpu_timer_start", "kmgpu_timer_stop",
 ]
 
 
@@ -107,6 +108,9 @@ def lib():
         L.kmgpu_profile_reset.argtypes = [C.c_void_p]
         L.kmgpu_profile_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), u64p, u64p]
         L.kmgpu_sync.argtypes = [C.c_void_p]
+        L.kmgpu_reset.argtypes = [C.c_void_p]
+        L.kmgpu_timer_start.argtypes = [C.c_void_p]
+        L.kmgpu_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.kmgpu_device_count.argtypes = [C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -372,6 +376,17 @@ class Sketch:
 
     def sync(self):
         check(lib().kmgpu_sync(self.h))
+
+    def reset(self):
+        check(lib().kmgpu_reset(self.h))
+
+    def timer_start(self):
+        check(lib().kmgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        check(lib().kmgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
 
 def reduce_replicas(sketches):

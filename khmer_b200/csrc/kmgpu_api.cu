@@ -157,7 +157,7 @@ struct kmgpu_sketch {
     uint32_t n_big_dev = 0;
 
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     std::mutex mu;
 
     // workspace
@@ -353,6 +353,8 @@ extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, cons
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->tev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->tev1);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl));
     if (e != cudaSuccess) {
@@ -382,6 +384,8 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->tev0) cudaEventDestroy(h->tev0);
+    if (h->tev1) cudaEventDestroy(h->tev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return KMGPU_OK;
@@ -469,6 +473,38 @@ extern "C" int kmgpu_sync(kmgpu_t* h)
     if (!h) return fail(KMGPU_EINVAL, "null handle");
     CKR(set_device(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_reset(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    for (int i = 0; i < h->nt; i++) CK(cudaMemsetAsync(h->dev.tables[i], 0, h->alloc_bytes[i], h->stream));
+    h->n_occupied = 0;
+    h->n_unique = 0;
+    h->big.clear();
+    h->big_dirty = true;
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_timer_start(kmgpu_t* h)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    CK(cudaEventRecord(h->tev0, h->stream));
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_timer_stop(kmgpu_t* h, double* ms)
+{
+    if (!h || !ms) return fail(KMGPU_EINVAL, "null argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    CK(cudaEventRecord(h->tev1, h->stream));
+    CK(cudaEventSynchronize(h->tev1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, h->tev0, h->tev1));
+    *ms = f;
     return KMGPU_OK;
 }
 extern "C" int kmgpu_profile_reset(kmgpu_t* h)
