@@ -121,6 +121,7 @@ struct PinBuf {
 struct ChunkDev {
     const uint64_t* words = nullptr;
     const uint32_t* offs = nullptr;
+    const uint32_t* tfr = nullptr;
     uint32_t n_reads = 0;
     uint32_t n_pos = 0;
 };
@@ -132,6 +133,7 @@ struct kmgpu_batch {
     struct Piece {
         uint64_t* words;
         uint32_t* offs;
+        uint32_t* tfr;
         uint32_t n_reads, n_pos;
     };
     std::vector<Piece> pieces;
@@ -164,8 +166,10 @@ struct kmgpu_sketch {
     DevBuf<uint8_t> d_ascii;
     DevBuf<uint64_t> d_words;
     DevBuf<uint32_t> d_offs;
+    DevBuf<uint32_t> d_tfr;
     DevBuf<uint32_t> d_flags;
     DevBuf<uint32_t> d_newbits;
+    DevBuf<uint32_t> d_filter;
     DevBuf<uint64_t> d_htkeys;
     DevBuf<uint32_t> d_htvals;
     DevBuf<Event> d_events;
@@ -202,6 +206,7 @@ static Input make_input(const ChunkDev& c)
     Input in;
     in.words = c.words;
     in.offs = c.offs;
+    in.tfr = c.tfr;
     in.n_reads = c.n_reads;
     in.hashes = nullptr;
     in.n_pos = c.n_pos;
@@ -212,6 +217,7 @@ static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
     Input in;
     in.words = nullptr;
     in.offs = nullptr;
+    in.tfr = nullptr;
     in.n_reads = 0;
     in.hashes = d_hashes;
     in.n_pos = n;
@@ -251,6 +257,30 @@ static void launch_ingest(int src, const SketchDev& S, const SketchDev& M, HashC
     if (S.kind == BYTE) launch_ingest_kind<BYTE>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
     else if (S.kind == NIBBLE) launch_ingest_kind<NIBBLE>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
     else launch_ingest_kind<BIT>(H.kind, src, S, M, H, P, pred, in, flags, ctrl, st);
+}
+
+template <int KIND>
+static void launch_pass_kind(int hk, int src, const SketchDev& S, int table, uint64_t lo, uint64_t hi, int first, const SketchDev& M,
+                             HashCfg H, const Pred& P, bool pred, const Input& in, uint32_t* flags, Ctrl* ctrl, cudaStream_t st)
+{
+    unsigned g = n_tiles(in.n_pos);
+#define LP(HK, SRC)                                                                                                       \
+    do {                                                                                                                  \
+        if (pred) k_ingest_pass<KIND, HK, SRC, true><<<g, THREADS, 0, st>>>(S, table, lo, hi, first, M, H, P, in, flags, ctrl);  \
+        else k_ingest_pass<KIND, HK, SRC, false><<<g, THREADS, 0, st>>>(S, table, lo, hi, first, M, H, P, in, flags, ctrl);      \
+    } while (0)
+    if (src == 1) LP(TWOBIT, 1);
+    else if (hk == TWOBIT) LP(TWOBIT, 0);
+    else LP(MURMUR, 0);
+#undef LP
+}
+
+static void launch_pass(int src, const SketchDev& S, int table, uint64_t lo, uint64_t hi, int first, const SketchDev& M, HashCfg H,
+                        const Pred& P, bool pred, const Input& in, uint32_t* flags, Ctrl* ctrl, cudaStream_t st)
+{
+    if (S.kind == BYTE) launch_pass_kind<BYTE>(H.kind, src, S, table, lo, hi, first, M, H, P, pred, in, flags, ctrl, st);
+    else if (S.kind == NIBBLE) launch_pass_kind<NIBBLE>(H.kind, src, S, table, lo, hi, first, M, H, P, pred, in, flags, ctrl, st);
+    else launch_pass_kind<BIT>(H.kind, src, S, table, lo, hi, first, M, H, P, pred, in, flags, ctrl, st);
 }
 
 #define DISPATCH_HK_SRC(KERNEL, hk, src, grid, st, ...)                                        \
@@ -375,7 +405,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     kmgpu_ipc_detach(h);
     for (int i = 0; i < h->nt; i++)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
-    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_flags.release(); h->d_newbits.release();
+    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_tfr.release(); h->d_flags.release(); h->d_newbits.release(); h->d_filter.release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
     h->d_hashin.release(); h->d_stat_med.release(); h->d_stat_f.release(); h->d_stat_n.release(); h->d_stat_b.release();
     h->d_hist.release(); h->big_keys.release(); h->big_vals.release();
@@ -616,8 +646,15 @@ static int resolve_new(kmgpu_sketch* h, int src, const SketchDev& S, HashCfg H, 
     CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
     CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
     unsigned g = n_tiles(in.n_pos);
-    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 0, h->d_htkeys.p, slots - 1);
-    DISPATCH_HK_SRC(k_replay, H.kind, src, g, st, S, H, in, h->d_flags.p, h->d_htkeys.p, h->d_htvals.p, slots - 1);
+    // bitmap prefilter of the registered bins; pointless once it would be mostly ones
+    uint32_t* filter = nullptr;
+    if (n_keys < (uint64_t)S.n_tables * FILTER_BITS / 4) {
+        CKR(h->d_filter.ensure((size_t)S.n_tables * FILTER_WORDS));
+        CK(cudaMemsetAsync(h->d_filter.p, 0, (size_t)S.n_tables * FILTER_WORDS * 4, st));
+        filter = h->d_filter.p;
+    }
+    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 0, h->d_htkeys.p, slots - 1, filter);
+    DISPATCH_HK_SRC(k_replay, H.kind, src, g, st, S, H, in, h->d_flags.p, h->d_htkeys.p, h->d_htvals.p, slots - 1, filter);
     unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
     k_mark<<<gm, 256, 0, st>>>(h->d_htkeys.p, h->d_htvals.p, slots, h->d_newbits.p, h->d_ctrl);
     h->all_launches += 3;
@@ -657,7 +694,7 @@ static int resolve_bigcount(kmgpu_sketch* h, int src, HashCfg H, const Input& in
     uint64_t slots = pow2_at_least(2 * n_cross);
     CKR(h->d_htkeys.ensure(slots));
     CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
-    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 20, h->d_htkeys.p, slots - 1);
+    DISPATCH_HK_SRC(k_register, H.kind, src, g, st, S, H, in, h->d_flags.p, 20, h->d_htkeys.p, slots - 1, (uint32_t*)nullptr);
     uint64_t cap = in.n_pos;
     CKR(h->d_events.ensure(cap));
     CKR(h->h_events.ensure(cap));
@@ -716,6 +753,38 @@ static int resolve_bigcount(kmgpu_sketch* h, int src, HashCfg H, const Input& in
     return KMGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// L2-blocked passes.  A sketch that is neither small enough to sit in L2 as a whole nor hopelessly larger
+// than L2 is ingested one table (or one address range of a table) at a time, so that each pass's counters
+// stay L2-resident (profiles/r1_atomic_ceiling.txt: random updates run 2-5x faster at <= ~100 MB).
+// ------------------------------------------------------------------------------------------------------
+struct PassPlan {
+    int table;
+    uint64_t lo, hi;  // bins
+};
+
+static uint64_t l2_block_bytes()
+{
+    uint64_t b = env_u64("KMGPU_L2_BLOCK_BYTES", ~0ull);  // test hook: force passes on tiny tables
+    return b != ~0ull ? b : env_u64("KMGPU_L2_BLOCK_MB", 104) * 1000000ull;
+}
+
+static void plan_passes(const kmgpu_sketch* h, std::vector<PassPlan>& out)
+{
+    out.clear();
+    const uint64_t block = l2_block_bytes();
+    const uint64_t max_passes = env_u64("KMGPU_MAX_PASSES", 16);
+    uint64_t total = 0;
+    for (int i = 0; i < h->nt; i++) total += h->nbytes[i];
+    if (block == 0 || total <= block) return;  // single pass: everything is L2-resident anyway
+    for (int i = 0; i < h->nt; i++) {
+        uint64_t r = (h->nbytes[i] + block - 1) / block;
+        uint64_t per = (h->sizes[i] + r - 1) / r;
+        for (uint64_t j = 0; j < r; j++) out.push_back(PassPlan{i, j * per, std::min(h->sizes[i], (j + 1) * per)});
+    }
+    if (out.size() > max_passes) out.clear();  // far larger than L2: one pass, HBM-bound either way
+}
+
 struct ChunkResult {
     uint64_t n_kmers = 0, n_new = 0;
     bool have_newbits = false;
@@ -729,16 +798,31 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
     cudaStream_t st = h->stream;
     CKR(h->d_flags.ensure(in.n_pos));
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    std::vector<PassPlan> passes;
+    plan_passes(h, passes);
     CK(cudaEventRecord(h->ev0, st));
-    launch_ingest(src, h->dev, M ? *M : h->dev, H, P, pred, in, h->d_flags.p, h->d_ctrl, st);
+    if (passes.empty()) {
+        launch_ingest(src, h->dev, M ? *M : h->dev, H, P, pred, in, h->d_flags.p, h->d_ctrl, st);
+    } else {
+        for (size_t pi = 0; pi < passes.size(); pi++)
+            launch_pass(src, h->dev, passes[pi].table, passes[pi].lo, passes[pi].hi, pi == 0, M ? *M : h->dev, H, P, pred, in,
+                        h->d_flags.p, h->d_ctrl, st);
+    }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->ingest_ms += ms;
-    h->ingest_launches += 1;
-    h->all_launches += 1;
+    size_t nl = passes.empty() ? 1 : passes.size();
+    h->ingest_launches += nl;
+    h->all_launches += nl;
+    if (!passes.empty() && h->kind == BYTE && h->use_bigcount && h->h_ctrl->n_sat) {
+        k_count_allsat<<<148 * 8, 256, 0, st>>>(h->d_flags.p, in.n_pos, (1u << h->nt) - 1, h->d_ctrl);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        CKR(read_ctrl(h));
+    }
     Ctrl c = *h->h_ctrl;
     res->n_kmers += c.n_kmers;
     h->n_occupied += c.n_z0;
@@ -817,7 +901,9 @@ static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, ui
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
     k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(h->d_ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, h->d_words.p,
                                                              (uint32_t)n_words, h->d_ctrl);
-    h->all_launches += 1;
+    CKR(h->d_tfr.ensure(n_tiles(n_pos) + 1));
+    k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(h->d_offs.p, n_reads, n_tiles(n_pos), h->d_tfr.p);
+    h->all_launches += 2;
     CK(cudaGetLastError());
     if (need_acgt_check) {
         CKR(read_ctrl(h));
@@ -827,6 +913,7 @@ static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, ui
     }
     out->words = h->d_words.p;
     out->offs = h->d_offs.p;
+    out->tfr = h->d_tfr.p;
     out->n_reads = n_reads;
     out->n_pos = n_pos;
     return KMGPU_OK;
@@ -928,6 +1015,10 @@ static int for_each_packed_chunk(kmgpu_sketch* h, const uint64_t* words, uint64_
         cd.offs = h->d_offs.p;
         cd.n_reads = (uint32_t)offs.size() - 1;
         cd.n_pos = n_pos;
+        CKR(h->d_tfr.ensure(n_tiles(n_pos) + 1));
+        k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(h->d_offs.p, cd.n_reads, n_tiles(n_pos), h->d_tfr.p);
+        h->all_launches += 1;
+        cd.tfr = h->d_tfr.p;
         CKR(fn(cd));
     }
     return KMGPU_OK;
@@ -994,15 +1085,17 @@ extern "C" int kmgpu_batch_create(int device, const char* seqs, const uint64_t* 
             if ((e = cudaMalloc(&d_ascii, n_pos)) != cudaSuccess) { bail(e); break; }
             ascii_cap = n_pos;
         }
-        kmgpu_batch::Piece p{nullptr, nullptr, nr, n_pos};
+        kmgpu_batch::Piece p{nullptr, nullptr, nullptr, nr, n_pos};
         if ((e = cudaMalloc(&p.words, nw * 8)) != cudaSuccess) { bail(e); break; }
         if ((e = cudaMalloc(&p.offs, (nr + 1) * 4)) != cudaSuccess) { cudaFree(p.words); bail(e); break; }
+        if ((e = cudaMalloc(&p.tfr, (n_tiles(n_pos) + 1) * 4)) != cudaSuccess) { cudaFree(p.words); cudaFree(p.offs); bail(e); break; }
         b->pieces.push_back(p);
-        b->bytes += nw * 8 + (nr + 1) * 4;
+        b->bytes += nw * 8 + (nr + 1) * 4 + (n_tiles(n_pos) + 1) * 4;
         if (n_pos && (e = cudaMemcpy(d_ascii, seqs + c.base0, n_pos, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e); break; }
         if ((e = cudaMemcpy(p.offs, c.offs.data(), (nr + 1) * 4, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e); break; }
         cudaMemset(d_ctrl, 0, sizeof(Ctrl));
         k_pack<<<(unsigned)((nw + 255) / 256), 256>>>(d_ascii, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, p.words, (uint32_t)nw, d_ctrl);
+        k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256>>>(p.offs, nr, n_tiles(n_pos), p.tfr);
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e); break; }
     }
     if (d_ascii) cudaFree(d_ascii);
@@ -1022,6 +1115,7 @@ extern "C" int kmgpu_batch_destroy(kmgpu_batch_t* b)
     for (auto& p : b->pieces) {
         if (p.words) cudaFree(p.words);
         if (p.offs) cudaFree(p.offs);
+        if (p.tfr) cudaFree(p.tfr);
     }
     delete b;
     return KMGPU_OK;
@@ -1055,6 +1149,7 @@ extern "C" int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmg
         ChunkDev cd;
         cd.words = p.words;
         cd.offs = p.offs;
+        cd.tfr = p.tfr;
         cd.n_reads = p.n_reads;
         cd.n_pos = p.n_pos;
         CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));

@@ -269,6 +269,85 @@ __device__ __forceinline__ uint32_t counter_cap()
 }
 
 // ------------------------------------------------------------------------------------------------
+// U independent updates issued together: all loads first, then all compare-and-swaps, then the (rare)
+// retries.  Each update is two dependent L2 round trips; interleaving U of them per thread is what keeps
+// the L2 atomic units busy (profiles/r1_atomic_ceiling.txt: one-at-a-time ld+CAS reaches a third of the
+// L2-resident atomic rate).  Semantics per update are exactly update_counter<KIND>.
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int U>
+__device__ __forceinline__ void multi_update(uint8_t* const* tab, const uint64_t* bin, const bool* act, uint32_t* old)
+{
+    uint32_t* word[U];
+    uint32_t sh[U], cur[U];
+    bool pend[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        pend[u] = false;
+        old[u] = 1u;  // inactive slots report "occupied, not saturated"
+        if (!act[u]) continue;
+        if (KIND == BYTE) {
+            word[u] = reinterpret_cast<uint32_t*>(tab[u] + (bin[u] & ~3ull));
+            sh[u] = (uint32_t)(bin[u] & 3) * 8;
+        } else if (KIND == NIBBLE) {
+            uint64_t byte = bin[u] >> 1;
+            word[u] = reinterpret_cast<uint32_t*>(tab[u] + (byte & ~3ull));
+            sh[u] = (uint32_t)(byte & 3) * 8 + ((bin[u] & 1) ? 0 : 4);
+        } else {
+            word[u] = reinterpret_cast<uint32_t*>(tab[u]) + (bin[u] >> 5);
+            sh[u] = (uint32_t)(bin[u] & 31);
+        }
+        cur[u] = ld_cg_u32(word[u]);
+    }
+    constexpr uint32_t CAP = KIND == BYTE ? 255u : KIND == NIBBLE ? 15u : 1u;
+    // issue every atomic before looking at any result, so the U round trips overlap
+    uint32_t seen[U];
+    bool tried[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        uint32_t b = (cur[u] >> sh[u]) & CAP;
+        tried[u] = act[u] && b != CAP;
+        seen[u] = cur[u];
+        if (tried[u]) {
+            if (KIND == BIT) seen[u] = atomicOr(word[u], 1u << sh[u]);
+            else seen[u] = atomicCAS(word[u], cur[u], cur[u] + (1u << sh[u]));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (!act[u]) continue;
+        uint32_t b = (cur[u] >> sh[u]) & CAP;
+        if (!tried[u]) {
+            old[u] = CAP;
+        } else if (KIND == BIT) {
+            old[u] = (seen[u] >> sh[u]) & 1u;
+        } else if (seen[u] == cur[u]) {
+            old[u] = b;
+        } else {
+            cur[u] = seen[u];
+            pend[u] = true;
+        }
+    }
+    if (KIND != BIT) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            while (pend[u]) {
+                uint32_t b = (cur[u] >> sh[u]) & CAP;
+                if (b == CAP) {
+                    old[u] = CAP;
+                    pend[u] = false;
+                } else {
+                    uint32_t seen = atomicCAS(word[u], cur[u], cur[u] + (1u << sh[u]));
+                    if (seen == cur[u]) {
+                        old[u] = b;
+                        pend[u] = false;
+                    } else cur[u] = seen;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // open-addressing table keyed by (bin, table) used by the exact "first toucher" resolution
 // ------------------------------------------------------------------------------------------------
 constexpr uint64_t HT_EMPTY = ~0ull;

@@ -12,6 +12,7 @@ struct Ctrl {
     unsigned long long n_z0;      // updates that occupied a bin of table 0      -> n_occupied
     unsigned long long n_zbits;   // updates that occupied a bin of any table    -> #keys for resolution
     unsigned long long n_allsat;  // k-mers that saw every table saturated (bigcount candidates)
+    unsigned long long n_sat;     // updates that found their byte saturated (multi-pass mode)
     unsigned long long n_cross;   // updates that moved a byte 254 -> 255 in this chunk
     unsigned long long n_unique;  // result of the first-toucher resolution
     unsigned long long n_events;  // records appended by k_events / k_cross_replay
@@ -21,10 +22,13 @@ struct Ctrl {
 // flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
 constexpr uint32_t F_CONSUMED = 1u << 31;
 constexpr int F_MAXT = 10;
+constexpr uint64_t FILTER_BITS = 1ull << 23;  // per table
+constexpr uint64_t FILTER_WORDS = FILTER_BITS / 32;
 
 struct Input {
     const uint64_t* words;   // SRC 0: packed stream of the chunk (+ TILE_PAD_WORDS zero words)
     const uint32_t* offs;    //        read offsets (n_reads + 1), chunk relative
+    const uint32_t* tfr;     //        per tile: last read with offs[r] <= tile start (n_tiles + 1 entries)
     uint32_t n_reads;
     const uint64_t* hashes;  // SRC 1: hash array
     uint32_t n_pos;          // stream positions (bases) or number of hashes
@@ -61,24 +65,13 @@ __device__ __forceinline__ void tile_begin(const Input& in, int k, uint32_t t0, 
     if (HK == MURMUR) fill_lut4(sm.lut, tid, THREADS);
     const uint64_t* src = in.words + (t0 >> 5);
     for (int i = tid; i < TILE / 32 + TILE_PAD_WORDS; i += THREADS) sm.words[i] = __ldg(src + i);
-    if (tid == 0) {
-        // r_lo = last read with offs[r] <= t0 ; r_hi = first read with offs[r] >= t0 + TILE
-        uint32_t lo = 0, hi = in.n_reads;  // search in offs[0..n_reads]
-        while (lo < hi) {
-            uint32_t mid = (lo + hi + 1) >> 1;
-            if (in.offs[mid] <= t0) lo = mid; else hi = mid - 1;
-        }
-        sm.r_lo = lo;
-        uint32_t end = t0 + TILE;
-        uint32_t a = lo, b = in.n_reads;
-        while (a < b) {
-            uint32_t mid = (a + b) >> 1;
-            if (in.offs[mid] >= end) b = mid; else a = mid + 1;
-        }
-        sm.r_hi = a;
-    }
     __syncthreads();
-    for (uint32_t r = sm.r_lo + tid; r < sm.r_hi; r += THREADS) {
+    // reads overlapping the tile come from the per-tile index k_tile_index built for the chunk (a serial
+    // binary search here cost more than the tile's useful work)
+    const uint32_t r_lo = in.tfr[blockIdx.x];
+    uint32_t r_hi = in.tfr[blockIdx.x + 1] + 1;
+    if (r_hi > in.n_reads) r_hi = in.n_reads;
+    for (uint32_t r = r_lo + tid; r < r_hi; r += THREADS) {
         uint32_t s = in.offs[r], e = in.offs[r + 1];
         if (e - s < (uint32_t)k) continue;
         uint32_t first = s > t0 ? s : t0;
@@ -139,11 +132,32 @@ __device__ __forceinline__ bool pred_pass(const Pred& P, const SketchDev& M, uin
     return true;
 }
 
+// tfr[t] = last read r (0 <= r < n_reads) with offs[r] <= t * TILE, for t = 0..n_tiles (inclusive)
+__global__ void k_tile_index(const uint32_t* __restrict__ offs, uint32_t n_reads, uint32_t n_tiles, uint32_t* __restrict__ tfr)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    uint64_t start = (uint64_t)t * TILE;
+    uint32_t lo = 0, hi = n_reads ? n_reads - 1 : 0;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if ((uint64_t)offs[mid] <= start) lo = mid; else hi = mid - 1;
+    }
+    tfr[t] = lo;
+}
+
 // ---- ingest --------------------------------------------------------------------------------------
-// The hot kernel.  For every k-mer of the tile: hash, N x (mod, saturating update).  Per position it
-// leaves a flags word (which tables it saw empty / saturated / about to saturate) used by the exact
+// The hot kernels.  For every k-mer of the tile: hash, N x (mod, saturating update).  Per position they
+// leave a flags word (which tables it saw empty / saturated / about to saturate) used by the exact
 // resolutions that follow only when needed.  Replaces consume_string + Storage::add
 // (src/oxli/hashtable.cc:280-294, include/oxli/storage.hh:571-624).
+//
+// k_ingest      : all N tables in one pass — used when the whole sketch fits the L2 block (every update
+//                 hits L2 anyway) or is far larger than L2 (every update goes to HBM anyway).
+// k_ingest_pass : one table (or one address range of it) per pass, U positions per thread in flight.  The
+//                 range is chosen <= the L2 block so that after the first touches the pass's counters are
+//                 L2-resident and the random read-modify-writes stop going to HBM; the 2-bit stream is
+//                 re-hashed per pass, which costs far less than a DRAM row miss per update.
 template <int KIND, int HK, int SRC, int NT, bool PRED>
 __global__ void __launch_bounds__(THREADS)
 k_ingest(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __restrict__ flags, Ctrl* ctrl)
@@ -163,16 +177,24 @@ k_ingest(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __rest
             if (!PRED || pred_pass(P, M, h)) {
                 uint32_t z = 0, s = 0, c = 0;
                 if (NT > 0) {
-                    uint64_t bins[NT > 0 ? NT : 1];
+                    constexpr int NN = NT > 0 ? NT : 1;
+                    uint64_t bins[NN];
+                    uint8_t* tabs[NN];
+                    bool act[NN];
+                    uint32_t old[NN];
 #pragma unroll
-                    for (int i = 0; i < NT; i++) bins[i] = mod_magic(h, S.sizes[i], S.magic[i]);
+                    for (int i = 0; i < NN; i++) {
+                        bins[i] = mod_magic(h, S.sizes[i], S.magic[i]);
+                        tabs[i] = S.tables[i];
+                        act[i] = true;
+                    }
+                    multi_update<KIND, NN>(tabs, bins, act, old);
 #pragma unroll
-                    for (int i = 0; i < NT; i++) {
-                        uint32_t old = update_counter<KIND>(S.tables[i], bins[i]);
-                        z |= (old == 0) << i;
+                    for (int i = 0; i < NN; i++) {
+                        z |= (old[i] == 0) << i;
                         if (KIND == BYTE) {
-                            s |= (old == 255u) << i;
-                            c |= (old == 254u) << i;
+                            s |= (old[i] == 255u) << i;
+                            c |= (old[i] == 254u) << i;
                         }
                     }
                 } else {
@@ -211,6 +233,89 @@ k_ingest(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __rest
     }
 }
 
+constexpr int PASS_U = 4;  // positions in flight per thread in k_ingest_pass
+
+template <int KIND, int HK, int SRC, bool PRED>
+__global__ void __launch_bounds__(THREADS)
+k_ingest_pass(SketchDev S, int table, uint64_t bin_lo, uint64_t bin_hi, int first_pass, SketchDev M, HashCfg H, Pred P,
+              Input in, uint32_t* __restrict__ flags, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    unsigned n_k = 0, n_z = 0, n_s = 0, n_c = 0;
+    uint8_t* const tab = S.tables[table];
+    const uint64_t size = S.sizes[table], magic = S.magic[table];
+    const bool whole = bin_lo == 0 && bin_hi >= size;
+#pragma unroll 1
+    for (uint32_t lp0 = threadIdx.x; lp0 < TILE; lp0 += THREADS * PASS_U) {
+        uint64_t bins[PASS_U];
+        uint8_t* tabs[PASS_U];
+        bool act[PASS_U], consumed[PASS_U];
+        uint32_t old[PASS_U];
+#pragma unroll
+        for (int u = 0; u < PASS_U; u++) {
+            uint32_t lp = lp0 + u * THREADS;
+            tabs[u] = tab;
+            bins[u] = 0;
+            consumed[u] = false;
+            if (lp < TILE && t0 + lp < in.n_pos && tile_valid<HK, SRC>(sm, lp)) {
+                uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+                if (!PRED || pred_pass(P, M, h)) {
+                    consumed[u] = true;
+                    bins[u] = mod_magic(h, size, magic);
+                }
+            }
+            act[u] = consumed[u] && (whole || (bins[u] >= bin_lo && bins[u] < bin_hi));
+        }
+        multi_update<KIND, PASS_U>(tabs, bins, act, old);
+#pragma unroll
+        for (int u = 0; u < PASS_U; u++) {
+            uint32_t lp = lp0 + u * THREADS;
+            if (!(lp < TILE && t0 + lp < in.n_pos)) continue;
+            uint32_t bits = 0;
+            if (act[u]) {
+                bits = (uint32_t)(old[u] == 0) << table;
+                n_z += old[u] == 0;
+                if (KIND == BYTE) {
+                    bits |= ((uint32_t)(old[u] == 255u) << (10 + table)) | ((uint32_t)(old[u] == 254u) << (20 + table));
+                    n_s += old[u] == 255u;
+                    n_c += old[u] == 254u;
+                }
+            }
+            if (first_pass) {
+                __stcs(&flags[t0 + lp], bits | (consumed[u] ? F_CONSUMED : 0u));
+                n_k += consumed[u];
+            } else if (bits) {
+                atomicOr(&flags[t0 + lp], bits);
+            }
+        }
+    }
+    tile_accumulate(sm, 0, n_k);
+    tile_accumulate(sm, 1, table == 0 ? n_z : 0);
+    tile_accumulate(sm, 2, n_z);
+    tile_accumulate(sm, 3, n_s);
+    tile_accumulate(sm, 4, n_c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sm.acc[0]) atomicAdd(&ctrl->n_kmers, sm.acc[0]);
+        if (sm.acc[1]) atomicAdd(&ctrl->n_z0, sm.acc[1]);
+        if (sm.acc[2]) atomicAdd(&ctrl->n_zbits, sm.acc[2]);
+        if (sm.acc[3]) atomicAdd(&ctrl->n_sat, sm.acc[3]);
+        if (sm.acc[4]) atomicAdd(&ctrl->n_cross, sm.acc[4]);
+    }
+}
+
+// multi-pass mode: number of k-mers whose flags show every table saturated
+__global__ void k_count_allsat(const uint32_t* __restrict__ flags, uint32_t n_pos, uint32_t allmask, Ctrl* ctrl)
+{
+    unsigned cnt = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x)
+        cnt += ((flags[p] >> 10) & 0x3ffu) == allmask && (flags[p] & F_CONSUMED);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_allsat, (unsigned long long)cnt);
+}
+
 // ---- exact "is new" resolution ----------------------------------------------------------------------
 // Storage::add reports a k-mer as new iff one of its bins was empty when it arrived IN STREAM ORDER
 // (storage.hh:581-591,619-621; bits: :185-195).  Atomics give arrival in memory order instead, so the
@@ -220,7 +325,8 @@ k_ingest(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __rest
 //   which = 0: register bins flagged "saw 0" (shift 0) ; which = 2: bins flagged "saw 254" (shift 20)
 template <int HK, int SRC>
 __global__ void __launch_bounds__(THREADS)
-k_register(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, int shift, uint64_t* keys, uint64_t mask)
+k_register(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, int shift, uint64_t* keys, uint64_t mask,
+           uint32_t* filter)
 {
     __shared__ TileSmem sm;
     const uint32_t t0 = blockIdx.x * TILE;
@@ -242,7 +348,9 @@ k_register(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags,
         while (m) {
             int i = __ffs(m) - 1;
             m &= m - 1;
-            ht_insert(keys, mask, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+            uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+            ht_insert(keys, mask, ht_key(bin, i));
+            if (filter) atomicOr(&filter[i * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)], 1u << (bin & 31));
         }
     }
 }
@@ -250,7 +358,7 @@ k_register(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags,
 template <int HK, int SRC>
 __global__ void __launch_bounds__(THREADS)
 k_replay(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, const uint64_t* __restrict__ keys,
-         uint32_t* __restrict__ stamps, uint64_t mask)
+         uint32_t* __restrict__ stamps, uint64_t mask, const uint32_t* __restrict__ filter)
 {
     __shared__ TileSmem sm;
     const uint32_t t0 = blockIdx.x * TILE;
@@ -259,7 +367,11 @@ k_replay(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ flags, c
         if (!(flags[t0 + lp] & F_CONSUMED)) continue;
         uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
         for (int i = 0; i < S.n_tables; i++) {
-            uint64_t s = ht_find(keys, mask, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+            uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+            // 1 MB-per-table bitmap of the registered bins (L1/L2 resident): rejects almost every probe once
+            // few bins are new, which is the steady state
+            if (filter && !((__ldg(&filter[i * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)]) >> (bin & 31)) & 1u)) continue;
+            uint64_t s = ht_find(keys, mask, ht_key(bin, i));
             if (s != ~0ull) atomicMin(&stamps[s], t0 + lp);
         }
     }
