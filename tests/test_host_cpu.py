@@ -1,0 +1,98 @@
+"""Host layer pieces that need no GPU: hash helpers, prime finder, the FASTA/FASTQ reader — against the
+reference's known answers and the parser goldens recorded from the compiled reference."""
+import hashlib
+import os
+
+import pytest
+
+import khmer_b200 as kh
+
+
+def test_hash_known_answers():
+    # tests/test_functions.py:51-99,148-171
+    assert kh.forward_hash("AAAA", 4) == 0 and kh.forward_hash("TTTT", 4) == 0
+    assert kh.forward_hash("CCCC", 4) == 170 and kh.forward_hash("GGGG", 4) == 170
+    assert [kh.forward_hash_no_rc(s, 4) for s in ("AAAA", "TTTT", "CCCC", "GGGG")] == [0, 85, 170, 255]
+    assert [kh.reverse_hash(h, 4) for h in (0, 85, 170, 255)] == ["AAAA", "TTTT", "CCCC", "GGGG"]
+    assert kh.forward_hash("GGTTGACGGGGCTCAGGGGGCGGCTGACTCCG", 32) == 13607885392109549066
+    with pytest.raises(ValueError):
+        kh.forward_hash("A" * 33, 33)
+    assert kh.hash_murmur3("AAAA") == 526240128537019279 == kh.hash_murmur3("TTTT")
+    assert kh.hash_murmur3("CCCC") == 14391997331386449225 == kh.hash_murmur3("GGGG")
+    assert kh.hash_no_rc_murmur3("AAAA") == 5231866503566620412
+    assert kh.hash_no_rc_murmur3("TTTT") == 5753003579327329651
+    assert kh.hash_no_rc_murmur3("CCCC") == 3789793362494378039
+    assert kh.hash_no_rc_murmur3("GGGG") == 17519752047064575358
+    assert kh.reverse_complement("AAAC") == "GTTT"
+
+
+def test_hashes_against_reference_golden(golden):
+    for s, c, f, r in golden["hash_twobit"]:
+        assert kh.forward_hash(s, len(s)) == c and kh.forward_hash_no_rc(s, len(s)) == f
+    for s, c, f, r in golden["hash_murmur"]:
+        assert kh.hash_murmur3(s) == c and kh.hash_no_rc_murmur3(s) == f
+
+
+def test_primes(golden):
+    for key, want in golden["primes"].items():
+        n, x = map(int, key.split(","))
+        assert kh.get_n_primes_near_x(n, x) == want
+
+
+def test_band_interval():
+    assert kh.compute_band_interval(4, 0) == (0, (2 ** 64 - 1) // 4)
+    with pytest.raises(ValueError):
+        kh.compute_band_interval(4, 5)
+
+
+def test_reader_matches_reference_parser(golden, datadir):
+    for fn, want in golden["parse"].items():
+        p = os.path.join(datadir, fn)
+        if "error" in want:
+            with pytest.raises(OSError):
+                list(kh.ReadParser(p))
+            continue
+        parser = kh.ReadParser(p)
+        seqs = [r.cleaned_seq for r in parser]
+        assert len(seqs) == want["n"] == parser.num_reads, fn
+        assert hashlib.md5("\n".join(seqs).encode()).hexdigest() == want["md5"], fn
+
+
+def test_reader_errors(tmp_path, datadir):
+    with pytest.raises(OSError):
+        kh.ReadParser(str(tmp_path / "nope.fa"))
+    with pytest.raises(OSError) as e:
+        kh.ReadParser(os.path.join(datadir, "test-empty.fa"))
+    assert "does not contain any sequences" in str(e.value)
+    bad = tmp_path / "bad.fa"
+    bad.write_text("this is not\nfasta\n")
+    with pytest.raises(OSError):
+        kh.ReadParser(str(bad))
+    empty_seq = tmp_path / "e.fa"
+    empty_seq.write_text(">a\nACGT\n>b\n>c\nAC\n")
+    p = kh.ReadParser(str(empty_seq))
+    assert next(p).sequence == "ACGT"
+    with pytest.raises(ValueError):          # InvalidRead: "Sequence is empty" (read_parsers.cc:347-349)
+        next(p)
+    fq = tmp_path / "q.fq"
+    fq.write_text("@a\nACGT\n+\nIII\n")
+    with pytest.raises(ValueError):          # "Sequence and quality lengths differ"
+        list(kh.ReadParser(str(fq)))
+    multi = tmp_path / "m.fa"
+    multi.write_text(">a desc\nACGT\nTTGA\n\n>b\r\nAC\r\nGT")
+    assert [r.sequence for r in kh.ReadParser(str(multi))] == ["ACGTTTGA", "ACGT"]
+
+
+def test_api_surface():
+    """Every method of khmer/_oxli/graphs.pyx the four scripts and the table tests use exists."""
+    import khmer_b200._oxli as ox
+    want = ["ksize", "hash", "reverse_hash", "add", "count", "get", "consume", "get_kmers", "get_kmer_hashes",
+            "get_kmer_counts", "get_min_count", "get_max_count", "get_median_count", "median_at_least",
+            "n_unique_kmers", "n_occupied", "n_tables", "hashsizes", "set_use_bigcount", "get_use_bigcount", "save",
+            "load", "consume_seqfile", "consume_seqfile_with_mask", "consume_seqfile_banding",
+            "consume_seqfile_banding_with_mask", "abundance_distribution", "trim_on_abundance",
+            "trim_below_abundance", "find_spectral_error_positions", "get_raw_tables"]
+    for cls in ("Countgraph", "SmallCountgraph", "Nodegraph", "Counttable", "SmallCounttable", "Nodetable"):
+        for m in want:
+            assert hasattr(getattr(ox, cls), m), (cls, m)
+    assert hasattr(ox.Nodegraph, "update")
