@@ -5,9 +5,24 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include "oxli_b200.hh"
 
 namespace py = pybind11;
+
+// KMGPU_DEBUG_SEGV=1: print a native backtrace on SIGSEGV (debugging aid, off by default)
+static void segv_backtrace(int sig)
+{
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+
 using namespace oxli_b200;
 using namespace oxli_b200::read_parsers;
 
@@ -90,6 +105,7 @@ void bind_table(py::module_& m, const char* name, py::class_<Hashtable, std::sha
 
 PYBIND11_MODULE(_oxli, m)
 {
+    if (getenv("KMGPU_DEBUG_SEGV")) signal(SIGSEGV, segv_backtrace);
     m.doc() = "khmer_b200 host layer: liboxli-compatible classes backed by the kmgpu C ABI (tables in GPU memory)";
 
     // exception mapping — khmer/_oxli/oxli_exception_convert.cc:9-31

@@ -127,7 +127,7 @@ def test_reference_fixture_files(datadir, tmp_path):
     for fn, cls in (("badversion-k12.ct", kh.Countgraph), ("badversion-k12.ht", kh.Nodegraph)):
         with pytest.raises(OSError) as e:
             cls.load(os.path.join(datadir, fn))
-        assert "Incorrect file format version" in str(e.value)
+        assert "Does not start with signature for a oxli file" in str(e.value)   # pre-OXLI files, as the reference reports them
     with pytest.raises(OSError):
         kh.Countgraph.load(str(tmp_path / "missing.ct"))
     t = kh.Countgraph(5, 1, 1, primes=[11, 13])
@@ -165,10 +165,13 @@ def test_single_kmer_api_like_reference_tests():
     GG = "G" * 12
     t = kh.Countgraph(12, 1, 1, primes=[1000003, 1009837])
     assert t.hash(GG) == 11184810 and t.hash("AAACGTATGACT") == 184777
+    # hash(GG) % 1000003 == hash(collision_1), hash(GG) % 1009837 == hash(collision_2): test_collision_1/2/3
+    o = ol.Oracle("Countgraph", 12, [1000003, 1009837])
     for kmer in ("AAACGTATGACT", "AAATACCGAGCG", "AAACGTATCGAG"):
         t.count(kmer)
-    assert t.get("AAACGTATGACT") == 1 and t.get(GG) == 0
-    assert t.add(GG) is True and t.add(GG) is False
+        o.add(kmer)
+    assert t.get("AAACGTATGACT") == 1 and t.get(GG) == o.get(GG) == 1      # both of GG's bins are taken
+    assert t.add(GG) is o.add(GG) is False and t.add("ACGTACGTTTTT") is True
     assert t.get(t.hash(GG)) == 2 and t.reverse_hash(t.hash(GG)) == "C" * 12
     with pytest.raises(ValueError):
         t.get("ACGT")                      # wrong length
@@ -292,12 +295,36 @@ def test_banding_and_mask_against_live_reference(datadir, tmp_path):
         assert [bytes(v) for v in g.get_raw_tables()] == [r.table(i).tobytes() for i in range(3)]
 
 
-def test_trim_functions_against_live_reference(datadir):
+def _trim_expected(counts, k, seqlen, keep):
+    """Hashtable::trim_on_abundance / trim_below_abundance (src/oxli/hashtable.cc:504-560) over a count vector."""
+    if len(counts) == 0:
+        return 0
+    if len(counts) == 1 or not keep(counts[0]):
+        return 0
+    i = k
+    for c in counts[1:]:
+        if not keep(c):
+            return i
+        i += 1
+    return seqlen
+
+
+def test_trim_functions_against_oracle_counts():
     kh = _kh()
+    rng = np.random.default_rng(17)
     g = kh.Countgraph(8, 1e5, 3)
-    g.consume("ACGTACGTAAGGTTCCACGTACGTAAGGTTCC")
-    g.consume("ACGTACGTAAGGTTCC")
+    o = ol.Oracle("Countgraph", 8, g.hashsizes())
+    for s in ("ACGTACGTAAGGTTCCACGTACGTAAGGTTCC", "ACGTACGTAAGGTTCC", "GGATTACAGGATTACATTT"):
+        g.consume(s)
+        o.consume(s)
+    queries = ["ACGTACGTAAGGTTCCTTTTTTTTTTTTACGTACGT", "TTTTTTTTTTTTACGTACGTAAGG", "GGATTACAGGATTACATTTACGTACGTAAGGTTCC",
+               "ACGTACGT", "ACGTACGTA"] + ["".join("ACGT"[i] for i in rng.integers(0, 4, 40)) for _ in range(5)]
+    for q in queries:
+        c = o.kmer_counts(q).tolist()
+        for thr in (1, 2, 3):
+            pos = _trim_expected(c, 8, len(q), lambda v: v >= thr)
+            assert g.trim_on_abundance(q, thr) == (q[:pos], pos)
+            pos = _trim_expected(c, 8, len(q), lambda v: v <= thr)
+            assert g.trim_below_abundance(q, thr) == (q[:pos], pos)
     seq = "ACGTACGTAAGGTTCCTTTTTTTTTTTTACGTACGT"
-    assert g.trim_on_abundance(seq, 2) == (seq[:16], 16)
-    assert g.trim_below_abundance("TTTTTTTTTTTTACGTACGTAAGG", 1)[1] == 19
-    assert g.find_spectral_error_positions(seq, 1) == [16]
+    assert g.find_spectral_error_positions(seq, 1) == [16]      # hashtable.cc:565-612 walked by hand
