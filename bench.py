@@ -225,7 +225,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -279,19 +279,12 @@ def run_ours(args):
         host.append((buf, off, keep))
         dev.append(cabi.Batch((buf, off), K, clean=True, device=local_rank))
 
-    if world > 1:
-        handles = torch.from_numpy(sk.ipc_export()).cuda()
-        allh = [torch.empty_like(handles) for _ in range(world)]
-        dist.all_gather(allh, handles)
-        sk.ipc_attach(rank, world, torch.cat(allh).cpu().numpy())
+    from khmer_b200.multigpu import ReplicaGroup
+    group = ReplicaGroup(sk, dist if world > 1 else None, device=torch.device("cuda", local_rank))
+    group.attach()
 
     def merge_replicas():
-        if world == 1:
-            return
-        sk.reduce_scatter_peers()
-        barrier()
-        sk.all_gather_peers()
-        barrier()
+        group.merge()
 
     def job_boundary(step):
         """after every P steps: fold the replicas (N > 1), then start a new job on empty tables"""
@@ -318,12 +311,12 @@ def run_ours(args):
         # start the timed region on a job boundary so every timed step sees the same table states
         first = ((args.warmup + P - 1) // P) * P
         run_steps(first - args.warmup, leg, args.warmup)
-        barrier()
-        sk.profile_reset()
         sampler = ClockSampler(local_rank) if leg == "hbm" and rank == 0 else None
         if sampler:
             sampler.start()
             time.sleep(0.25)
+        barrier()                      # all ranks enter the timed region together
+        sk.profile_reset()
         t0 = time.time()
         sk.timer_start()
         kmers = run_steps(args.steps, leg, first)
@@ -335,6 +328,8 @@ def run_ours(args):
         if sampler:
             clocks = sampler.stop(t0, t1)
         kern_ms, kern_launches, all_launches = sk.profile_get()
+        print("[bench rank %d] leg=%s device_ms=%.2f wall_ms=%.2f ingest_kernel_ms=%.2f launches=%d" % (
+            rank, leg, ms, 1e3 * (t1 - t0), kern_ms, all_launches), file=sys.stderr, flush=True)
         results[leg] = {"ms": max_over_ranks(ms), "kmers": sum_over_ranks(kmers), "kern_ms": kern_ms,
                         "kern_launches": kern_launches, "launches": all_launches, "local_kmers": kmers,
                         "wall_ms": 1e3 * (t1 - t0)}
@@ -380,12 +375,29 @@ def run_ours(args):
                     "d2h_bytes_per_step": 64 * ((bases + (32 << 20) - 1) // (32 << 20)), "ms_per_step": e2e["ms"] / args.steps},
             "gpu_launches": int(hbm["launches"]), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL banners ...) was
+    diverted to stderr by divert_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def divert_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    divert_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

@@ -193,6 +193,9 @@ int kmgpu_all_gather_peers(kmgpu_t* h);
 /* single-process variant: fold sketches living on different GPUs of this process into replicas[0..n)
  * (peer access enabled internally). */
 int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
+/* the 32-bit-word range [*w0, *w1) of a table of n_words words that rank `rank` of `world` owns in the
+ * reduce-scatter / all-gather above (pure arithmetic, no device needed) */
+int kmgpu_slice_range(uint64_t n_words, int world, int rank, uint64_t* w0, uint64_t* w1);
 
 /* ---- measurement -----------------------------------------------------------------------
  * Device time (ms) and launch count of the ingest kernel accumulated since the last reset, measured

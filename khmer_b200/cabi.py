@@ -33,7 +33,7 @@ SYMBOLS = [
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
     "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
-    "kmgpu_timer_start", "kmgpu_timer_stop",
+    "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
         L.kmgpu_timer_start.argtypes = [C.c_void_p]
         L.kmgpu_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.kmgpu_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.kmgpu_slice_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
         _lib = L
     return _lib
 
@@ -387,6 +388,12 @@ class Sketch:
         ms = C.c_double()
         check(lib().kmgpu_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+
+def slice_range(n_words, world, rank):
+    a, b = C.c_uint64(), C.c_uint64()
+    check(lib().kmgpu_slice_range(n_words, world, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def reduce_replicas(sketches):

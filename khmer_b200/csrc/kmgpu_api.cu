@@ -1539,6 +1539,13 @@ static void slice_words(uint64_t n_words, int world, int r, uint64_t* w0, uint64
     *w1 = std::min<uint64_t>(n_words, per * (r + 1));
 }
 
+extern "C" int kmgpu_slice_range(uint64_t n_words, int world, int rank, uint64_t* w0, uint64_t* w1)
+{
+    if (world < 1 || rank < 0 || rank >= world || !w0 || !w1) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
+    slice_words(n_words, world, rank, w0, w1);
+    return KMGPU_OK;
+}
+
 // rank r folds word slice r of every peer's tables into its own copy
 static int reduce_scatter_locked(kmgpu_sketch* h)
 {
