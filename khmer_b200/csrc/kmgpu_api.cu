@@ -170,6 +170,10 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_flags;
     DevBuf<uint32_t> d_newbits;
     DevBuf<uint32_t> d_filter;
+    DevBuf<uint32_t> d_bins;
+    DevBuf<uint16_t> d_delta;
+    size_t delta_zeroed = 0;
+    DevBuf<uint64_t> d_binlist;
     DevBuf<uint64_t> d_htkeys;
     DevBuf<uint32_t> d_htvals;
     DevBuf<Event> d_events;
@@ -405,7 +409,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     kmgpu_ipc_detach(h);
     for (int i = 0; i < h->nt; i++)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
-    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_tfr.release(); h->d_flags.release(); h->d_newbits.release(); h->d_filter.release();
+    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_tfr.release(); h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
     h->d_hashin.release(); h->d_stat_med.release(); h->d_stat_f.release(); h->d_stat_n.release(); h->d_stat_b.release();
     h->d_hist.release(); h->big_keys.release(); h->big_vals.release();
@@ -790,11 +794,214 @@ struct ChunkResult {
     bool have_newbits = false;
 };
 
+// ------------------------------------------------------------------------------------------------------
+// delta + fold ingestion (see kmgpu_kernels.cuh): byte / nibble storages with every table <= 2^32 - 2 bins
+// ------------------------------------------------------------------------------------------------------
+struct DeltaPass {
+    int table;
+    uint32_t lo, hi;
+};
+
+static uint64_t delta_block_bins()
+{
+    uint64_t b = env_u64("KMGPU_DELTA_BLOCK_BINS", 0);  // test hook
+    if (!b) b = env_u64("KMGPU_DELTA_BLOCK_MB", 50) * 1000000ull / 2;
+    b &= ~7ull;
+    return b < 8 ? 8 : b;
+}
+
+static bool plan_delta(const kmgpu_sketch* h, std::vector<DeltaPass>& out)
+{
+    out.clear();
+    if (!env_u64("KMGPU_DELTA", 1)) return false;
+    if (h->kind != BYTE && h->kind != NIBBLE) return false;
+    const uint64_t block = delta_block_bins();
+    for (int i = 0; i < h->nt; i++) {
+        if (h->sizes[i] > 0xFFFFFFFEull) return false;
+        uint64_t r = (h->sizes[i] + block - 1) / block;
+        uint64_t per = ((h->sizes[i] + r - 1) / r + 7) & ~7ull;
+        for (uint64_t j = 0; j * per < h->sizes[i]; j++)
+            out.push_back(DeltaPass{i, (uint32_t)(j * per), (uint32_t)std::min<uint64_t>(h->sizes[i], (j + 1) * per)});
+    }
+    if (out.size() > env_u64("KMGPU_DELTA_MAX_PASSES", 64)) {
+        out.clear();
+        return false;
+    }
+    return true;
+}
+
+template <int HK, int SRC>
+static void launch_hashbins(bool pred, unsigned g, cudaStream_t st, const SketchDev& S, const SketchDev& M, HashCfg H, const Pred& P,
+                            const Input& in, uint32_t* bins, uint64_t stride, Ctrl* ctrl)
+{
+    if (pred) k_hashbins<HK, SRC, true><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
+    else k_hashbins<HK, SRC, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
+}
+
+static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Input& in, uint64_t stride, uint64_t n_list, uint64_t n_cross)
+{
+    cudaStream_t st = h->stream;
+    const SketchDev& S = h->dev;
+    unsigned g = n_tiles(in.n_pos);
+    uint64_t slots = 1024;
+    std::unordered_map<uint64_t, uint32_t> before;  // crossing bin (bin << 8 | table) -> value before the chunk
+    if (n_cross) {
+        slots = pow2_at_least(2 * n_cross);
+        CKR(h->d_htkeys.ensure(slots));
+        CKR(h->d_htvals.ensure(slots));
+        CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
+        unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
+        k_list_register<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, BL_CROSS, h->d_htkeys.p, h->d_htvals.p, slots - 1, nullptr, 1);
+        h->all_launches += 1;
+    }
+    uint64_t cap = in.n_pos;
+    CKR(h->d_events.ensure(cap));
+    CKR(h->h_events.ensure(cap));
+    CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+    DISPATCH_HK_SRC(k_bigscan, H.kind, src, g, st, S, H, in, h->d_bins.p, stride, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0, h->d_events.p,
+                    (unsigned long long)cap, h->d_ctrl);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    uint64_t n_rec = h->h_ctrl->n_events;
+    if (n_rec > cap) return fail(KMGPU_ECUDA, "internal: bigcount scan overflow");
+    if (n_rec) CK(cudaMemcpyAsync(h->h_events.p, h->d_events.p, n_rec * sizeof(Event), cudaMemcpyDeviceToHost, st));
+    std::vector<uint64_t> hk;
+    std::vector<uint32_t> hv;
+    if (n_cross) {
+        hk.resize(slots);
+        hv.resize(slots);
+        CK(cudaMemcpyAsync(hk.data(), h->d_htkeys.p, slots * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hv.data(), h->d_htvals.p, slots * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < hk.size(); i++)
+        if (hk[i] != HT_EMPTY) before[hk[i]] = hv[i];
+    std::vector<Event> recs(h->h_events.p, h->h_events.p + n_rec);
+    std::sort(recs.begin(), recs.end(), [](const Event& a, const Event& b) { return a.pos < b.pos; });
+    // stream position T at which each crossing bin reached 255: its (255 - before)-th touch of the chunk
+    std::unordered_map<uint64_t, std::vector<uint32_t>> touches;
+    for (const Event& e : recs) {
+        uint32_t cross = e.info & 0x3ff;
+        for (int i = 0; i < h->nt && cross; i++)
+            if (cross >> i & 1) touches[((e.hash % h->sizes[i]) << 8) | (uint64_t)i].push_back(e.pos);
+    }
+    std::unordered_map<uint64_t, uint32_t> T;
+    for (auto& kv : touches) {
+        auto it = before.find(kv.first);
+        if (it == before.end()) return fail(KMGPU_ECUDA, "internal: crossing bin without a recorded value");
+        size_t need = 255 - it->second;  // >= 1
+        if (kv.second.size() < need) return fail(KMGPU_ECUDA, "internal: inconsistent saturation record");
+        T[kv.first] = kv.second[need - 1];
+    }
+    for (const Event& e : recs) {
+        if (!(e.info >> 30 & 1)) continue;  // some byte of this k-mer is still below 255
+        bool after_all = true;
+        uint32_t cross = e.info & 0x3ff;
+        for (int i = 0; i < h->nt && after_all; i++) {
+            if (!(cross >> i & 1)) continue;
+            if (!(e.pos > T[((e.hash % h->sizes[i]) << 8) | (uint64_t)i])) after_all = false;
+        }
+        if (after_all) big_event(h, e.hash);
+    }
+    return KMGPU_OK;
+}
+
+static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& passes, int src, HashCfg H, const Input& in, const Pred& P,
+                              bool pred, const SketchDev* M, ChunkResult* res)
+{
+    cudaStream_t st = h->stream;
+    const uint64_t stride = ((uint64_t)in.n_pos + 7) & ~7ull;
+    CKR(h->d_bins.ensure((size_t)h->nt * stride));
+    uint64_t total_bins = 0, max_span = 0;
+    for (int i = 0; i < h->nt; i++) total_bins += h->sizes[i];
+    for (const DeltaPass& p : passes) max_span = std::max<uint64_t>(max_span, p.hi - p.lo);
+    const uint64_t list_cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nt * in.n_pos, total_bins));
+    CKR(h->d_binlist.ensure(list_cap));
+    size_t need_lanes = ((max_span + 7) & ~7ull) + 8;
+    if (h->d_delta.cap < need_lanes) h->delta_zeroed = 0;
+    CKR(h->d_delta.ensure(need_lanes));
+    if (h->delta_zeroed < h->d_delta.cap) {  // the fold keeps the block zeroed from then on
+        CK(cudaMemsetAsync(h->d_delta.p, 0, h->d_delta.cap * 2, st));
+        h->delta_zeroed = h->d_delta.cap;
+    }
+    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    CK(cudaEventRecord(h->ev0, st));
+    {
+        unsigned g = n_tiles(in.n_pos);
+        const SketchDev& MS = M ? *M : h->dev;
+        if (src == 1) launch_hashbins<TWOBIT, 1>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
+        else if (H.kind == TWOBIT) launch_hashbins<TWOBIT, 0>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
+        else launch_hashbins<MURMUR, 0>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
+    }
+    const int want_cross = h->kind == BYTE && h->use_bigcount;
+    const unsigned gs = (in.n_pos + 2047) / 2048;
+    for (const DeltaPass& p : passes) {
+        k_scatter<<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
+        unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
+        if (h->kind == BYTE)
+            k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross);
+        else
+            k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0);
+    }
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ingest_ms += ms;
+    h->ingest_launches += 1 + 2 * passes.size();
+    h->all_launches += 1 + 2 * passes.size();
+    Ctrl c = *h->h_ctrl;
+    if (c.n_events > list_cap) return fail(KMGPU_ECUDA, "internal: bin list overflow");
+    res->n_kmers += c.n_kmers;
+    h->n_occupied += c.n_z0;
+    const uint64_t n_list = c.n_events;
+    if (c.n_zbits) {
+        // first-toucher stamps, one table at a time (packed 8-byte slots, bitmap prefilter)
+        size_t nb_words = (in.n_pos + 31) / 32;
+        CKR(h->d_newbits.ensure(nb_words));
+        CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
+        CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+        unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
+        for (int i = 0; i < h->nt; i++) {
+            uint64_t n_new_i = c.n_new_t[i];
+            if (!n_new_i) continue;
+            uint64_t slots = pow2_at_least(2 * n_new_i);
+            CKR(h->d_htkeys.ensure(slots));
+            CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
+            uint32_t* filter = nullptr;
+            if (n_new_i < FILTER_BITS / 4) {
+                CKR(h->d_filter.ensure(FILTER_WORDS));
+                CK(cudaMemsetAsync(h->d_filter.p, 0, FILTER_WORDS * 4, st));
+                filter = h->d_filter.p;
+            }
+            unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
+            k_pk_register<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, i, sl, slots - 1, filter);
+            k_pk_replay<<<(in.n_pos + 255) / 256, 256, 0, st>>>(h->d_bins.p + (size_t)i * stride, in.n_pos, sl, slots - 1, filter);
+            unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
+            k_pk_mark<<<gm, 256, 0, st>>>(sl, slots, h->d_newbits.p, h->d_ctrl);
+            h->all_launches += 3;
+        }
+        CK(cudaGetLastError());
+        CKR(read_ctrl(h));
+        h->n_unique += h->h_ctrl->n_unique;
+        res->n_new += h->h_ctrl->n_unique;
+        res->have_newbits = true;
+    }
+    if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, in, stride, n_list, c.n_cross));
+    return KMGPU_OK;
+}
+
 // ingest one staged chunk into sketch `h` (hash config may come from another sketch: abundance tracking)
 static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, const Pred& P, bool pred, const SketchDev* M,
                         ChunkResult* res)
 {
     if (in.n_pos == 0) return KMGPU_OK;
+    {
+        std::vector<DeltaPass> dp;
+        if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, in, P, pred, M, res);
+    }
     cudaStream_t st = h->stream;
     CKR(h->d_flags.ensure(in.n_pos));
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));

@@ -2,6 +2,7 @@
 // arbitrary table size, and the three saturating counter updates.  sm_100a only.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace kmgpu {

@@ -17,6 +17,7 @@ struct Ctrl {
     unsigned long long n_unique;  // result of the first-toucher resolution
     unsigned long long n_events;  // records appended by k_events / k_cross_replay
     unsigned long long non_acgt;  // pack kernel: bytes outside ACGT seen in raw mode
+    unsigned long long n_new_t[10];  // delta path: newly occupied bins per table
 };
 
 // flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
@@ -687,6 +688,301 @@ __global__ void k_count_occupied(int kind, const uint32_t* __restrict__ t, uint6
     }
     cnt = __reduce_add_sync(0xffffffffu, (unsigned)cnt);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+
+// =====================================================================================================
+// Delta + fold ingestion (byte and nibble storages, tables up to 2^32 bins).
+//
+// Instead of one compare-and-swap round trip per counter update, the chunk's updates of one table block are
+// accumulated with return-less `red.global.add.noftz.f16x2` into a block of half-precision lanes that stays
+// L2-resident (2 bytes per bin; profiles/r1_red_ceiling.txt: ~200 G updates/s at <= 50 MB), then one streaming
+// kernel folds the block into the byte/nibble table: new = min(cap, old + touches).  A half lane counts
+// exactly up to 2048 and then sticks there (2048 + 1 rounds back to 2048), so a lane can neither wrap nor
+// carry into its neighbour however hot the bin is, and any touch count >= cap saturates the counter anyway.
+// The fold sees, per BIN, the value before the chunk and the number of touches — everything the exactness
+// resolutions need (newly occupied bins, bins that saturate inside the chunk) without per-update return values.
+// =====================================================================================================
+constexpr uint32_t BIN_NONE = 0xFFFFFFFFu;   // position not consumed
+constexpr uint64_t BL_NEW = 1ull << 56;      // bin list entry flags: bin went 0 -> occupied in this chunk
+constexpr uint64_t BL_CROSS = 1ull << 57;    //                       bin reached the cap in this chunk (bits 48..55: value before)
+
+__device__ __forceinline__ void red_add_half_lane(uint16_t* lanes, uint32_t idx)
+{
+    // lanes is 4-byte aligned; lane idx&1 of word idx>>1 gets +1.0h
+    uint32_t* word = reinterpret_cast<uint32_t*>(lanes) + (idx >> 1);
+    uint32_t v = (idx & 1) ? 0x3C000000u : 0x00003C00u;
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(word), "r"(v) : "memory");
+}
+
+// 1. hash every k-mer once and keep its bin in each table: bins[i * stride + pos] (BIN_NONE if not consumed)
+template <int HK, int SRC, bool PRED>
+__global__ void __launch_bounds__(THREADS)
+k_hashbins(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __restrict__ bins, uint64_t stride, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    unsigned n_k = 0;
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        bool consumed = false;
+        uint64_t h = 0;
+        if (tile_valid<HK, SRC>(sm, lp)) {
+            h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+            consumed = !PRED || pred_pass(P, M, h);
+        }
+        n_k += consumed;
+        for (int i = 0; i < S.n_tables; i++) {
+            uint32_t b = consumed ? (uint32_t)mod_magic(h, S.sizes[i], S.magic[i]) : BIN_NONE;
+            __stcs(&bins[i * stride + t0 + lp], b);
+        }
+    }
+    tile_accumulate(sm, 0, n_k);
+    __syncthreads();
+    if (threadIdx.x == 0 && sm.acc[0]) atomicAdd(&ctrl->n_kmers, sm.acc[0]);
+}
+
+// 2. touches of one table block: bins of this table in [lo, hi) -> +1 on their half lane
+__global__ void __launch_bounds__(256)
+k_scatter(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta)
+{
+    const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 8u;
+    if (i0 >= n_pos) return;
+    uint32_t v[8];
+    if (i0 + 8 <= n_pos) {
+        uint4 a = __ldcs(reinterpret_cast<const uint4*>(bins + i0));
+        uint4 b = __ldcs(reinterpret_cast<const uint4*>(bins + i0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = i0 + j < n_pos ? __ldcs(bins + i0 + j) : BIN_NONE;
+    }
+    const uint32_t span = hi - lo;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t d = v[j] - lo;           // BIN_NONE and bins below lo wrap far above span
+        if (d < span) red_add_half_lane(delta, d);
+    }
+}
+
+// 3. fold the block into the table, 8 bins per thread; zeroes the lanes it consumed.
+//    byte: ByteStorage::add's `+1 while < 255` applied `touches` times (storage.hh:599-603);
+//    nibble: NibbleStorage::add (storage.hh:345-351), even bin -> high nibble.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta, uint64_t* __restrict__ binlist,
+       unsigned long long list_cap, Ctrl* ctrl, int want_cross)
+{
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;  // group of 8 bins
+    const uint32_t span = hi - lo;
+    unsigned n_new = 0, n_sat = 0, n_cross = 0, n_ent = 0;
+    uint64_t ent[8];
+    if (g * 8u < span) {
+        uint4 d4 = *reinterpret_cast<const uint4*>(delta + (size_t)g * 8);
+        if (d4.x | d4.y | d4.z | d4.w) {
+            *reinterpret_cast<uint4*>(delta + (size_t)g * 8) = make_uint4(0, 0, 0, 0);
+            const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w};
+            constexpr uint32_t CAP = KIND == BYTE ? 255u : 15u;
+            const uint32_t b0 = lo + g * 8u;
+            uint64_t old64 = 0;
+            uint32_t old32 = 0;
+            if (KIND == BYTE) old64 = *reinterpret_cast<const uint64_t*>(table + b0);
+            else old32 = *reinterpret_cast<const uint32_t*>(table + (b0 >> 1));
+            uint64_t new64 = old64;
+            uint32_t new32 = old32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t hbits = (dw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (!hbits) continue;
+                uint32_t m = (uint32_t)__half2float(__ushort_as_half((unsigned short)hbits));
+                uint32_t s, sh;
+                if (KIND == BYTE) {
+                    sh = j * 8;
+                    s = (uint32_t)(old64 >> sh) & 255u;
+                } else {
+                    sh = (j >> 1) * 8 + ((j & 1) ? 0 : 4);   // bin b0+j: byte j/2, even bin -> high nibble
+                    s = (old32 >> sh) & 15u;
+                }
+                uint32_t t = s + m;
+                uint32_t nv = t > CAP ? CAP : t;
+                if (KIND == BYTE) new64 = (new64 & ~(255ull << sh)) | ((uint64_t)nv << sh);
+                else new32 = (new32 & ~(15u << sh)) | (nv << sh);
+                uint64_t entry = 0;
+                if (s == 0) {
+                    entry |= BL_NEW;
+                    n_new++;
+                }
+                if (KIND == BYTE && t >= CAP) {
+                    if (t > CAP) n_sat++;   // at least one touch of this chunk found the byte already saturated
+                    if (s < CAP) {          // the byte reached 255 inside this chunk
+                        n_cross++;
+                        if (want_cross) entry |= BL_CROSS | ((uint64_t)s << 48);
+                    }
+                }
+                if (entry) {
+                    ent[n_ent++] = entry | ht_key((uint64_t)(b0 + j), table_idx);
+                }
+            }
+            if (KIND == BYTE) *reinterpret_cast<uint64_t*>(table + b0) = new64;
+            else *reinterpret_cast<uint32_t*>(table + (b0 >> 1)) = new32;
+        }
+    }
+    // one list reservation per warp: exclusive scan of the per-thread entry counts
+    {
+        const unsigned lane = threadIdx.x & 31;
+        unsigned incl = n_ent;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += v;
+        }
+        unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(&ctrl->n_events, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long at = base + (incl - n_ent);
+            for (unsigned e = 0; e < n_ent; e++)
+                if (at + e < list_cap) binlist[at + e] = ent[e];
+        }
+    }
+    n_new = __reduce_add_sync(0xffffffffu, n_new);
+    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_new) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)n_new);
+            atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)n_new);
+            if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)n_new);
+        }
+        if (n_sat) atomicAdd(&ctrl->n_sat, (unsigned long long)n_sat);
+        if (n_cross) atomicAdd(&ctrl->n_cross, (unsigned long long)n_cross);
+    }
+}
+
+// 4a. hash table of the listed bins carrying `flag` (+ bitmap prefilter); cross entries keep "value before" in vals
+__global__ void k_list_register(const uint64_t* __restrict__ binlist, uint64_t n, uint64_t flag, uint64_t* keys, uint32_t* vals,
+                                uint64_t mask, uint32_t* filter, int store_before)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = binlist[i];
+        if (!(e & flag)) continue;
+        uint64_t key = e & 0xFFFFFFFFFFFFull;
+        uint64_t s = ht_insert(keys, mask, key);
+        if (store_before) vals[s] = (uint32_t)((e >> 48) & 255u);
+        if (filter) {
+            uint64_t bin = key >> 8;
+            int t = (int)(key & 255u);
+            atomicOr(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)], 1u << (bin & 31));
+        }
+    }
+}
+
+// 4b. first-toucher stamps straight from the stored bins (no re-hash)
+__global__ void __launch_bounds__(256)
+k_replay_bins(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables, uint32_t n_pos, const uint64_t* __restrict__ keys,
+              uint32_t* __restrict__ stamps, uint64_t mask, const uint32_t* __restrict__ filter)
+{
+    uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= n_pos) return;
+    for (int i = 0; i < n_tables; i++) {
+        uint32_t bin = __ldcs(&bins[i * stride + p]);
+        if (bin == BIN_NONE) return;
+        if (filter && !((__ldg(&filter[i * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)]) >> (bin & 31)) & 1u)) continue;
+        uint64_t s = ht_find(keys, mask, ht_key(bin, i));
+        if (s != ~0ull) atomicMin(&stamps[s], p);
+    }
+}
+
+// 4c. per-table stamp tables with packed 8-byte slots (bin << 32 | stamp): one 8-byte load per probe, the stamp
+//     lowered with a 64-bit atomicMin (the key half of a slot never changes once claimed).  One table at a
+//     time keeps the structure small enough to stay in L2 unless almost every bin of the chunk is new.
+constexpr unsigned long long PK_EMPTY = ~0ull;
+__device__ __forceinline__ uint64_t pk_slot0(uint32_t bin, uint64_t mask) { return fmix64((uint64_t)bin) & mask; }
+
+__global__ void k_pk_register(const uint64_t* __restrict__ binlist, uint64_t n, int table, unsigned long long* slots, uint64_t mask,
+                              uint32_t* filter)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = binlist[i];
+        if (!(e & BL_NEW) || (int)(e & 255u) != table) continue;
+        uint32_t bin = (uint32_t)((e & 0xFFFFFFFFFFFFull) >> 8);
+        unsigned long long fresh = ((unsigned long long)bin << 32) | 0xFFFFFFFFull;
+        uint64_t s = pk_slot0(bin, mask);
+        while (true) {
+            unsigned long long prev = atomicCAS(&slots[s], PK_EMPTY, fresh);
+            if (prev == PK_EMPTY || (uint32_t)(prev >> 32) == bin) break;
+            s = (s + 1) & mask;
+        }
+        if (filter) atomicOr(&filter[(bin & (FILTER_BITS - 1)) >> 5], 1u << (bin & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pk_replay(const uint32_t* __restrict__ bins, uint32_t n_pos, unsigned long long* slots, uint64_t mask, const uint32_t* __restrict__ filter)
+{
+    uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= n_pos) return;
+    uint32_t bin = __ldcs(&bins[p]);
+    if (bin == BIN_NONE) return;
+    if (filter && !((__ldg(&filter[(bin & (FILTER_BITS - 1)) >> 5]) >> (bin & 31)) & 1u)) return;
+    uint64_t s = pk_slot0(bin, mask);
+    while (true) {
+        unsigned long long v = __ldcg(&slots[s]);
+        if (v == PK_EMPTY) return;
+        if ((uint32_t)(v >> 32) == bin) {
+            if ((uint32_t)v > p) atomicMin(&slots[s], ((unsigned long long)bin << 32) | p);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void k_pk_mark(const unsigned long long* __restrict__ slots, uint64_t n_slots, uint32_t* newbits, Ctrl* ctrl)
+{
+    unsigned cnt = 0;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long v = slots[s];
+        if (v == PK_EMPTY) continue;
+        uint32_t p = (uint32_t)v;
+        if (p == 0xFFFFFFFFu) continue;  // registered but never stamped: cannot happen for a touched bin
+        uint32_t bit = 1u << (p & 31);
+        uint32_t old = atomicOr(&newbits[p >> 5], bit);
+        cnt += !(old & bit);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_unique, (unsigned long long)cnt);
+}
+
+// 5. bigcount scan after the fold: k-mers whose N bytes are all 255 now, and every k-mer touching a bin that
+//    reached 255 inside this chunk (so the host can find the stream position at which it did).
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_bigscan(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ bins, uint64_t stride, const uint64_t* __restrict__ keys,
+          uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
+        const uint32_t p = t0 + lp;
+        if (bins[p] == BIN_NONE) continue;
+        uint32_t cross = 0, allsat = 1;
+        for (int i = 0; i < S.n_tables; i++) {
+            uint32_t bin = bins[i * stride + p];
+            if (have_cross && ht_find(keys, mask, ht_key(bin, i)) != ~0ull) cross |= 1u << i;
+            else if (read_byte(S.tables[i], bin) != 255u) allsat = 0;
+        }
+        if (!cross && !allsat) continue;
+        Event e;
+        e.hash = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        e.pos = p;
+        e.info = cross | (allsat << 30);
+        unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+        if (at < cap) out[at] = e;
+    }
 }
 
 }  // namespace kmgpu

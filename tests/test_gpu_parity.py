@@ -33,7 +33,25 @@ def test_gpu_matches_reference_golden(golden, name):
 def test_gpu_golden_cases_in_pass_mode():
     """All reference goldens again with the L2-blocked pass kernel forced (block of 3 kB, small chunks)."""
     import subprocess, sys
-    env = dict(os.environ, KMGPU_L2_BLOCK_BYTES="3000", KMGPU_MAX_PASSES="100000", KMGPU_CHUNK_BASES="65536")
+    env = dict(os.environ, KMGPU_DELTA="0", KMGPU_L2_BLOCK_BYTES="3000", KMGPU_MAX_PASSES="100000", KMGPU_CHUNK_BASES="65536")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_gpu_matches_reference_golden and not C1 and not 25k"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_gpu_golden_cases_cas_single_pass():
+    """All reference goldens through the compare-and-swap kernel (the path huge tables take)."""
+    import subprocess, sys
+    env = dict(os.environ, KMGPU_DELTA="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_gpu_matches_reference_golden and not C1 and not 25k"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_gpu_golden_cases_delta_many_blocks():
+    """All reference goldens through the delta+fold path with ~2k-bin blocks (many blocks per table)."""
+    import subprocess, sys
+    env = dict(os.environ, KMGPU_DELTA_BLOCK_BINS="2048", KMGPU_DELTA_MAX_PASSES="1000000", KMGPU_CHUNK_BASES="65536")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
                         "test_gpu_matches_reference_golden and not C1 and not 25k"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -46,15 +64,19 @@ def _same_state(g, o, n_tables):
 
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
-@pytest.mark.parametrize("chunk", [None, 4096, 8192, "passes"])
+@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
     if chunk is not None:
         import subprocess, sys
         env = dict(os.environ, KMGPU_TEST_CLS=cls)
-        if chunk == "passes":   # L2-blocked multi-pass mode forced on tiny tables, several ranges per table
-            env.update(KMGPU_L2_BLOCK_BYTES="1500", KMGPU_MAX_PASSES="64", KMGPU_CHUNK_BASES="16384")
+        if chunk == "passes":   # compare-and-swap path, L2-blocked multi-pass mode forced on tiny tables
+            env.update(KMGPU_DELTA="0", KMGPU_L2_BLOCK_BYTES="1500", KMGPU_MAX_PASSES="64", KMGPU_CHUNK_BASES="16384")
+        elif chunk == "cas-8192":   # compare-and-swap path, all tables in one pass
+            env.update(KMGPU_DELTA="0", KMGPU_CHUNK_BASES="8192")
+        elif chunk == "delta-blocks":   # delta+fold path with many blocks per table
+            env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384")
         else:
             env.update(KMGPU_CHUNK_BASES=str(chunk))
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
