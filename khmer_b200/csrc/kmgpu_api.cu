@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -162,11 +163,20 @@ struct kmgpu_sketch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     std::mutex mu;
 
+    // staging of read chunks: two slots so that the upload + packing of chunk i+1 (copy stream) overlaps the
+    // ingestion of chunk i (main stream)
+    struct Stage {
+        DevBuf<uint8_t> ascii;
+        DevBuf<uint64_t> words;
+        DevBuf<uint32_t> offs;
+        DevBuf<uint32_t> tfr;
+        PinBuf<uint32_t> h_offs;
+        cudaEvent_t ready = nullptr;
+    } stage[2];
+    cudaStream_t copy_stream = nullptr;
+    Ctrl* d_ctrl_copy = nullptr;
+    Ctrl* h_ctrl_copy = nullptr;  // pinned
     // workspace
-    DevBuf<uint8_t> d_ascii;
-    DevBuf<uint64_t> d_words;
-    DevBuf<uint32_t> d_offs;
-    DevBuf<uint32_t> d_tfr;
     DevBuf<uint32_t> d_flags;
     DevBuf<uint32_t> d_newbits;
     DevBuf<uint32_t> d_filter;
@@ -187,7 +197,6 @@ struct kmgpu_sketch {
     DevBuf<unsigned long long> d_hist;
     Ctrl* d_ctrl = nullptr;
     Ctrl* h_ctrl = nullptr;  // pinned
-    PinBuf<uint32_t> h_offs;
     PinBuf<Event> h_events;
 
     // profile
@@ -391,6 +400,10 @@ extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, cons
     if (e == cudaSuccess) e = cudaEventCreate(&h->tev1);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl_copy, sizeof(Ctrl));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl_copy, sizeof(Ctrl));
+    for (int sl = 0; sl < 2 && e == cudaSuccess; sl++) e = cudaEventCreateWithFlags(&h->stage[sl].ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         kmgpu_destroy(h);
         return fail(KMGPU_ECUDA, "handle setup: %s", cudaGetErrorString(e));
@@ -409,11 +422,20 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     kmgpu_ipc_detach(h);
     for (int i = 0; i < h->nt; i++)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
-    h->d_ascii.release(); h->d_words.release(); h->d_offs.release(); h->d_tfr.release(); h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release();
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (int sl = 0; sl < 2; sl++) {
+        h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].tfr.release();
+        h->stage[sl].h_offs.release();
+        if (h->stage[sl].ready) cudaEventDestroy(h->stage[sl].ready);
+    }
+    if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
+    if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
     h->d_hashin.release(); h->d_stat_med.release(); h->d_stat_f.release(); h->d_stat_n.release(); h->d_stat_b.release();
     h->d_hist.release(); h->big_keys.release(); h->big_vals.release();
-    h->h_offs.release(); h->h_events.release();
+    h->h_events.release();
     if (h->d_ctrl) cudaFree(h->d_ctrl);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -907,8 +929,12 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
     return KMGPU_OK;
 }
 
+// `between` (optional) runs on the host after the chunk's kernels have been queued and before the host waits for
+// them: the caller uses it to prepare and upload the next chunk while this one is being ingested.
+typedef std::function<int()> Between;
+
 static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& passes, int src, HashCfg H, const Input& in, const Pred& P,
-                              bool pred, const SketchDev* M, ChunkResult* res)
+                              bool pred, const SketchDev* M, ChunkResult* res, const Between& between)
 {
     cudaStream_t st = h->stream;
     const uint64_t stride = ((uint64_t)in.n_pos + 7) & ~7ull;
@@ -946,6 +972,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
+    if (between) CKR(between());
     CKR(read_ctrl(h));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -995,12 +1022,12 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
 
 // ingest one staged chunk into sketch `h` (hash config may come from another sketch: abundance tracking)
 static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, const Pred& P, bool pred, const SketchDev* M,
-                        ChunkResult* res)
+                        ChunkResult* res, const Between& between = Between())
 {
-    if (in.n_pos == 0) return KMGPU_OK;
+    if (in.n_pos == 0) return between ? between() : KMGPU_OK;
     {
         std::vector<DeltaPass> dp;
-        if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, in, P, pred, M, res);
+        if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, in, P, pred, M, res, between);
     }
     cudaStream_t st = h->stream;
     CKR(h->d_flags.ensure(in.n_pos));
@@ -1017,6 +1044,7 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
     }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
+    if (between) CKR(between());
     CKR(read_ctrl(h));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1091,36 +1119,39 @@ static void plan_chunks(const uint64_t* offsets, uint64_t n_reads, int k, uint64
     }
 }
 
-// upload chunk (ASCII -> device -> 2-bit)
-static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, uint32_t flags, ChunkDev* out, bool need_acgt_check)
+// upload chunk (ASCII -> device -> 2-bit) into staging slot `slot` on stream `st`
+static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, uint32_t flags, ChunkDev* out, bool need_acgt_check,
+                       int slot = 0, cudaStream_t st = nullptr)
 {
-    cudaStream_t st = h->stream;
+    if (!st) st = h->stream;
+    kmgpu_sketch::Stage& S = h->stage[slot];
     uint32_t n_pos = (uint32_t)(c.base1 - c.base0);
     uint32_t n_reads = (uint32_t)c.offs.size() - 1;
     size_t n_words = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
-    CKR(h->d_ascii.ensure(std::max<size_t>(n_pos, 1)));
-    CKR(h->d_words.ensure(n_words));
-    CKR(h->d_offs.ensure(n_reads + 1));
-    CKR(h->h_offs.ensure(n_reads + 1));
-    memcpy(h->h_offs.p, c.offs.data(), (n_reads + 1) * sizeof(uint32_t));
-    if (n_pos) CK(cudaMemcpyAsync(h->d_ascii.p, seqs + c.base0, n_pos, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_offs.p, h->h_offs.p, (n_reads + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
-    k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(h->d_ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, h->d_words.p,
-                                                             (uint32_t)n_words, h->d_ctrl);
-    CKR(h->d_tfr.ensure(n_tiles(n_pos) + 1));
-    k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(h->d_offs.p, n_reads, n_tiles(n_pos), h->d_tfr.p);
+    CKR(S.ascii.ensure(std::max<size_t>(n_pos, 1)));
+    CKR(S.words.ensure(n_words));
+    CKR(S.offs.ensure(n_reads + 1));
+    CKR(S.h_offs.ensure(n_reads + 1));
+    memcpy(S.h_offs.p, c.offs.data(), (n_reads + 1) * sizeof(uint32_t));
+    if (n_pos) CK(cudaMemcpyAsync(S.ascii.p, seqs + c.base0, n_pos, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.offs.p, S.h_offs.p, (n_reads + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (need_acgt_check) CK(cudaMemsetAsync(h->d_ctrl_copy, 0, sizeof(Ctrl), st));
+    k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(S.ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, S.words.p,
+                                                             (uint32_t)n_words, h->d_ctrl_copy);
+    CKR(S.tfr.ensure(n_tiles(n_pos) + 1));
+    k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(S.offs.p, n_reads, n_tiles(n_pos), S.tfr.p);
     h->all_launches += 2;
     CK(cudaGetLastError());
     if (need_acgt_check) {
-        CKR(read_ctrl(h));
-        if (h->h_ctrl->non_acgt)
+        CK(cudaMemcpyAsync(h->h_ctrl_copy, h->d_ctrl_copy, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h->h_ctrl_copy->non_acgt)
             return fail(KMGPU_ENONACGT, "sequence holds %llu bytes outside ACGT; the Murmur hash of uncleaned sequences is not computed on the device",
-                        (unsigned long long)h->h_ctrl->non_acgt);
+                        (unsigned long long)h->h_ctrl_copy->non_acgt);
     }
-    out->words = h->d_words.p;
-    out->offs = h->d_offs.p;
-    out->tfr = h->d_tfr.p;
+    out->words = S.words.p;
+    out->offs = S.offs.p;
+    out->tfr = S.tfr.p;
     out->n_reads = n_reads;
     out->n_pos = n_pos;
     return KMGPU_OK;
@@ -1168,10 +1199,23 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
     HashCfg H{h->hash, h->k};
     ChunkResult res;
-    for (const ChunkPlan& c : plan) {
-        ChunkDev cd;
-        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
-        CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));
+    // chunk i+1 is uploaded and packed on the copy stream while chunk i is ingested on the main stream
+    const bool chk = needs_acgt_check(h, flags);
+    ChunkDev cd[2];
+    if (!plan.empty()) {
+        CKR(stage_chunk(h, seqs, plan[0], flags, &cd[0], chk, 0, h->copy_stream));
+        CK(cudaEventRecord(h->stage[0].ready, h->copy_stream));
+    }
+    for (size_t i = 0; i < plan.size(); i++) {
+        CK(cudaStreamWaitEvent(h->stream, h->stage[i & 1].ready, 0));
+        CKR(ingest_chunk(h, 0, H, make_input(cd[i & 1]), P, pred, M, &res, [&]() -> int {
+            if (i + 1 < plan.size()) {
+                int ns = (int)((i + 1) & 1);
+                CKR(stage_chunk(h, seqs, plan[i + 1], flags, &cd[ns], chk, ns, h->copy_stream));
+                CK(cudaEventRecord(h->stage[ns].ready, h->copy_stream));
+            }
+            return KMGPU_OK;
+        }));
     }
     if (n_kmers_out) *n_kmers_out = res.n_kmers;
     return KMGPU_OK;
@@ -1210,22 +1254,23 @@ static int for_each_packed_chunk(kmgpu_sketch* h, const uint64_t* words, uint64_
         uint32_t n_pos = (uint32_t)(b1 - b0);
         size_t nw = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
         uint64_t w0 = b0 / 32, w1 = std::min<uint64_t>(n_words, w0 + nw);
-        CKR(h->d_words.ensure(nw));
-        if (w1 - w0 < nw) CK(cudaMemsetAsync(h->d_words.p + (w1 - w0), 0, (nw - (w1 - w0)) * 8, st));
-        CK(cudaMemcpyAsync(h->d_words.p, words + w0, (w1 - w0) * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        CKR(h->d_offs.ensure(offs.size()));
-        CKR(h->h_offs.ensure(offs.size()));
-        memcpy(h->h_offs.p, offs.data(), offs.size() * 4);
-        CK(cudaMemcpyAsync(h->d_offs.p, h->h_offs.p, offs.size() * 4, cudaMemcpyHostToDevice, st));
+        kmgpu_sketch::Stage& SG = h->stage[0];
+        CKR(SG.words.ensure(nw));
+        if (w1 - w0 < nw) CK(cudaMemsetAsync(SG.words.p + (w1 - w0), 0, (nw - (w1 - w0)) * 8, st));
+        CK(cudaMemcpyAsync(SG.words.p, words + w0, (w1 - w0) * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        CKR(SG.offs.ensure(offs.size()));
+        CKR(SG.h_offs.ensure(offs.size()));
+        memcpy(SG.h_offs.p, offs.data(), offs.size() * 4);
+        CK(cudaMemcpyAsync(SG.offs.p, SG.h_offs.p, offs.size() * 4, cudaMemcpyHostToDevice, st));
         ChunkDev cd;
-        cd.words = h->d_words.p;
-        cd.offs = h->d_offs.p;
+        cd.words = SG.words.p;
+        cd.offs = SG.offs.p;
         cd.n_reads = (uint32_t)offs.size() - 1;
         cd.n_pos = n_pos;
-        CKR(h->d_tfr.ensure(n_tiles(n_pos) + 1));
-        k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(h->d_offs.p, cd.n_reads, n_tiles(n_pos), h->d_tfr.p);
+        CKR(SG.tfr.ensure(n_tiles(n_pos) + 1));
+        k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(SG.offs.p, cd.n_reads, n_tiles(n_pos), SG.tfr.p);
         h->all_launches += 1;
-        cd.tfr = h->d_tfr.p;
+        cd.tfr = SG.tfr.p;
         CKR(fn(cd));
     }
     return KMGPU_OK;

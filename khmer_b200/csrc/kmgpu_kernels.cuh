@@ -829,36 +829,48 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
             else *reinterpret_cast<uint32_t*>(table + (b0 >> 1)) = new32;
         }
     }
-    // one list reservation per warp: exclusive scan of the per-thread entry counts
+    // one list reservation and one set of counter updates per CTA (same-address atomics from every warp of a
+    // cold chunk were costing more than the fold itself)
     {
-        const unsigned lane = threadIdx.x & 31;
+        __shared__ unsigned s_cnt[8][4];   // per warp: entries, new, sat, cross
+        __shared__ unsigned long long s_base;
+        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         unsigned incl = n_ent;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (unsigned)o) incl += v;
         }
-        unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
-            unsigned long long base = 0;
-            if (lane == 31) base = atomicAdd(&ctrl->n_events, (unsigned long long)total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            unsigned long long at = base + (incl - n_ent);
+        unsigned w_new = __reduce_add_sync(0xffffffffu, n_new);
+        unsigned w_sat = __reduce_add_sync(0xffffffffu, n_sat);
+        unsigned w_cross = __reduce_add_sync(0xffffffffu, n_cross);
+        if (lane == 31) {
+            s_cnt[wid][0] = incl;
+            s_cnt[wid][1] = w_new;
+            s_cnt[wid][2] = w_sat;
+            s_cnt[wid][3] = w_cross;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot[4] = {0, 0, 0, 0};
+            for (int w = 0; w < 8; w++)
+                for (int q = 0; q < 4; q++) tot[q] += s_cnt[w][q];
+            s_base = tot[0] ? atomicAdd(&ctrl->n_events, (unsigned long long)tot[0]) : 0ull;
+            if (tot[1]) {
+                atomicAdd(&ctrl->n_zbits, (unsigned long long)tot[1]);
+                atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)tot[1]);
+                if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)tot[1]);
+            }
+            if (tot[2]) atomicAdd(&ctrl->n_sat, (unsigned long long)tot[2]);
+            if (tot[3]) atomicAdd(&ctrl->n_cross, (unsigned long long)tot[3]);
+        }
+        __syncthreads();
+        if (n_ent) {
+            unsigned long long at = s_base + (incl - n_ent);
+            for (unsigned w = 0; w < wid; w++) at += s_cnt[w][0];
             for (unsigned e = 0; e < n_ent; e++)
                 if (at + e < list_cap) binlist[at + e] = ent[e];
         }
-    }
-    n_new = __reduce_add_sync(0xffffffffu, n_new);
-    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
-    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
-    if ((threadIdx.x & 31) == 0) {
-        if (n_new) {
-            atomicAdd(&ctrl->n_zbits, (unsigned long long)n_new);
-            atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)n_new);
-            if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)n_new);
-        }
-        if (n_sat) atomicAdd(&ctrl->n_sat, (unsigned long long)n_sat);
-        if (n_cross) atomicAdd(&ctrl->n_cross, (unsigned long long)n_cross);
     }
 }
 
