@@ -169,6 +169,7 @@ struct kmgpu_sketch {
         DevBuf<uint8_t> ascii;
         DevBuf<uint64_t> words;
         DevBuf<uint32_t> offs;
+        DevBuf<uint64_t> offs64;
         DevBuf<uint32_t> tfr;
         PinBuf<uint32_t> h_offs;
         cudaEvent_t ready = nullptr;
@@ -424,7 +425,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (int sl = 0; sl < 2; sl++) {
-        h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].tfr.release();
+        h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].offs64.release(); h->stage[sl].tfr.release();
         h->stage[sl].h_offs.release();
         if (h->stage[sl].ready) cudaEventDestroy(h->stage[sl].ready);
     }
@@ -985,31 +986,35 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     h->n_occupied += c.n_z0;
     const uint64_t n_list = c.n_events;
     if (c.n_zbits) {
-        // first-toucher stamps, one table at a time (packed 8-byte slots, bitmap prefilter)
+        // first-toucher stamps: per-table sub-tables of packed 8-byte slots in one buffer, bitmap prefilter
         size_t nb_words = (in.n_pos + 31) / 32;
         CKR(h->d_newbits.ensure(nb_words));
         CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
         CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
-        unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
+        PkLayout L;
+        memset(&L, 0, sizeof L);
+        uint64_t total_slots = 0;
         for (int i = 0; i < h->nt; i++) {
-            uint64_t n_new_i = c.n_new_t[i];
-            if (!n_new_i) continue;
-            uint64_t slots = pow2_at_least(2 * n_new_i);
-            CKR(h->d_htkeys.ensure(slots));
-            CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
-            uint32_t* filter = nullptr;
-            if (n_new_i < FILTER_BITS / 4) {
-                CKR(h->d_filter.ensure(FILTER_WORDS));
-                CK(cudaMemsetAsync(h->d_filter.p, 0, FILTER_WORDS * 4, st));
-                filter = h->d_filter.p;
-            }
-            unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
-            k_pk_register<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, i, sl, slots - 1, filter);
-            k_pk_replay<<<(in.n_pos + 255) / 256, 256, 0, st>>>(h->d_bins.p + (size_t)i * stride, in.n_pos, sl, slots - 1, filter);
-            unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
-            k_pk_mark<<<gm, 256, 0, st>>>(sl, slots, h->d_newbits.p, h->d_ctrl);
-            h->all_launches += 3;
+            if (!c.n_new_t[i]) continue;
+            uint64_t sl = pow2_at_least(2 * c.n_new_t[i]);
+            L.base[i] = total_slots;
+            L.mask[i] = sl - 1;
+            total_slots += sl;
         }
+        L.use_filter = c.n_zbits < (uint64_t)h->nt * FILTER_BITS / 4;
+        CKR(h->d_htkeys.ensure(total_slots));
+        CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, total_slots * 8, st));
+        if (L.use_filter) {
+            CKR(h->d_filter.ensure((size_t)h->nt * FILTER_WORDS));
+            CK(cudaMemsetAsync(h->d_filter.p, 0, (size_t)h->nt * FILTER_WORDS * 4, st));
+        }
+        unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
+        unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
+        k_pk_register_all<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, L, sl, h->d_filter.p);
+        k_pk_replay_all<<<(in.n_pos + 255) / 256, 256, 0, st>>>(h->d_bins.p, stride, h->nt, in.n_pos, L, sl, h->d_filter.p);
+        unsigned gm = (unsigned)std::min<uint64_t>((total_slots + 255) / 256, 148 * 8);
+        k_pk_mark<<<gm, 256, 0, st>>>(sl, total_slots, h->d_newbits.p, h->d_ctrl);
+        h->all_launches += 3;
         CK(cudaGetLastError());
         CKR(read_ctrl(h));
         h->n_unique += h->h_ctrl->n_unique;
@@ -1182,6 +1187,51 @@ static int make_pred(kmgpu_sketch* h, const kmgpu_band_t* band, const kmgpu_mask
 
 static bool needs_acgt_check(const kmgpu_sketch* h, uint32_t flags) { return h->hash == KMGPU_MURMUR && !(flags & KMGPU_CLEAN); }
 
+// upload the base range [b0, b1) of the caller's buffer with the reads overlapping it; offsets are clipped and
+// rebased on the device, so the host does O(log n_reads) work per chunk
+static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint64_t b0, uint64_t b1,
+                       uint32_t flags, ChunkDev* out, bool need_acgt_check, int slot, cudaStream_t st)
+{
+    kmgpu_sketch::Stage& S = h->stage[slot];
+    // r_lo = last read starting at or before b0; r_hi = first index whose offset is >= b1
+    uint64_t r_lo = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, b0) - offsets);
+    r_lo = r_lo ? r_lo - 1 : 0;
+    if (r_lo >= n_reads) r_lo = n_reads - 1;
+    uint64_t r_hi = (uint64_t)(std::lower_bound(offsets + r_lo, offsets + n_reads + 1, b1) - offsets);
+    if (r_hi > n_reads) r_hi = n_reads;
+    if (r_hi <= r_lo) r_hi = r_lo + 1;
+    uint32_t n_pos = (uint32_t)(b1 - b0);
+    uint32_t nr = (uint32_t)(r_hi - r_lo);
+    size_t n_words = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
+    CKR(S.ascii.ensure(std::max<size_t>(n_pos, 1)));
+    CKR(S.words.ensure(n_words));
+    CKR(S.offs.ensure(nr + 1));
+    CKR(S.offs64.ensure(nr + 1));
+    CKR(S.tfr.ensure(n_tiles(n_pos) + 1));
+    if (n_pos) CK(cudaMemcpyAsync(S.ascii.p, seqs + b0, n_pos, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.offs64.p, offsets + r_lo, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_clip_offsets<<<(nr + 1 + 255) / 256, 256, 0, st>>>(S.offs64.p, nr + 1, b0, b1, S.offs.p);
+    if (need_acgt_check) CK(cudaMemsetAsync(h->d_ctrl_copy, 0, sizeof(Ctrl), st));
+    k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(S.ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, S.words.p,
+                                                             (uint32_t)n_words, h->d_ctrl_copy);
+    k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(S.offs.p, nr, n_tiles(n_pos), S.tfr.p);
+    h->all_launches += 3;
+    CK(cudaGetLastError());
+    if (need_acgt_check) {
+        CK(cudaMemcpyAsync(h->h_ctrl_copy, h->d_ctrl_copy, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h->h_ctrl_copy->non_acgt)
+            return fail(KMGPU_ENONACGT, "sequence holds %llu bytes outside ACGT; the Murmur hash of uncleaned sequences is not computed on the device",
+                        (unsigned long long)h->h_ctrl_copy->non_acgt);
+    }
+    out->words = S.words.p;
+    out->offs = S.offs.p;
+    out->tfr = S.tfr.p;
+    out->n_reads = nr;
+    out->n_pos = n_pos;
+    return KMGPU_OK;
+}
+
 extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                                    const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out)
 {
@@ -1195,23 +1245,33 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     bool pred;
     const SketchDev* M;
     CKR(make_pred(h, band, mask, &P, &pred, &M));
-    std::vector<ChunkPlan> plan;
-    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
     HashCfg H{h->hash, h->k};
     ChunkResult res;
-    // chunk i+1 is uploaded and packed on the copy stream while chunk i is ingested on the main stream
+    // Chunk i covers bases [first + i*cap, first + i*cap + cap + k-1) of the caller's buffer with the reads clipped to
+    // it: a clipped piece inside the k-1 overlap is shorter than k and yields nothing, the piece that continues past it
+    // starts exactly at the first k-mer the previous chunk could not hold — the k-mer stream is unchanged.
+    // Chunk i+1 is uploaded and packed on the copy stream while chunk i is ingested on the main stream.
+    const uint64_t first = offsets[0], last = offsets[n_reads], cap = chunk_bases();
     const bool chk = needs_acgt_check(h, flags);
+    if (last <= first) return KMGPU_OK;
+    const uint64_t n_chunks = (last - first + cap - 1) / cap;
+    auto range = [&](uint64_t i, uint64_t* b0, uint64_t* b1) {
+        *b0 = first + i * cap;
+        *b1 = std::min(last, *b0 + cap + (uint64_t)(h->k - 1));
+    };
     ChunkDev cd[2];
-    if (!plan.empty()) {
-        CKR(stage_chunk(h, seqs, plan[0], flags, &cd[0], chk, 0, h->copy_stream));
-        CK(cudaEventRecord(h->stage[0].ready, h->copy_stream));
-    }
-    for (size_t i = 0; i < plan.size(); i++) {
+    uint64_t b0, b1;
+    range(0, &b0, &b1);
+    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd[0], chk, 0, h->copy_stream));
+    CK(cudaEventRecord(h->stage[0].ready, h->copy_stream));
+    for (uint64_t i = 0; i < n_chunks; i++) {
         CK(cudaStreamWaitEvent(h->stream, h->stage[i & 1].ready, 0));
         CKR(ingest_chunk(h, 0, H, make_input(cd[i & 1]), P, pred, M, &res, [&]() -> int {
-            if (i + 1 < plan.size()) {
+            if (i + 1 < n_chunks) {
                 int ns = (int)((i + 1) & 1);
-                CKR(stage_chunk(h, seqs, plan[i + 1], flags, &cd[ns], chk, ns, h->copy_stream));
+                uint64_t c0, c1;
+                range(i + 1, &c0, &c1);
+                CKR(stage_range(h, seqs, offsets, n_reads, c0, c1, flags, &cd[ns], chk, ns, h->copy_stream));
                 CK(cudaEventRecord(h->stage[ns].ready, h->copy_stream));
             }
             return KMGPU_OK;

@@ -968,6 +968,67 @@ __global__ void k_pk_mark(const unsigned long long* __restrict__ slots, uint64_t
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_unique, (unsigned long long)cnt);
 }
 
+// fused forms over all tables: table i owns slots [base[i], base[i] + mask[i] + 1) of one buffer
+struct PkLayout {
+    uint64_t base[F_MAXT];
+    uint64_t mask[F_MAXT];   // 0 => table has no new bin in this chunk
+    int use_filter;
+};
+
+__global__ void k_pk_register_all(const uint64_t* __restrict__ binlist, uint64_t n, PkLayout L, unsigned long long* slots, uint32_t* filter)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = binlist[i];
+        if (!(e & BL_NEW)) continue;
+        int t = (int)(e & 255u);
+        uint32_t bin = (uint32_t)((e & 0xFFFFFFFFFFFFull) >> 8);
+        unsigned long long fresh = ((unsigned long long)bin << 32) | 0xFFFFFFFFull;
+        unsigned long long* tb = slots + L.base[t];
+        uint64_t s = pk_slot0(bin, L.mask[t]);
+        while (true) {
+            unsigned long long prev = atomicCAS(&tb[s], PK_EMPTY, fresh);
+            if (prev == PK_EMPTY || (uint32_t)(prev >> 32) == bin) break;
+            s = (s + 1) & L.mask[t];
+        }
+        if (L.use_filter) atomicOr(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)], 1u << (bin & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pk_replay_all(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables, uint32_t n_pos, PkLayout L, unsigned long long* slots,
+                const uint32_t* __restrict__ filter)
+{
+    uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= n_pos) return;
+    for (int t = 0; t < n_tables; t++) {
+        uint32_t bin = __ldcs(&bins[t * stride + p]);
+        if (bin == BIN_NONE) return;
+        if (!L.mask[t]) continue;
+        if (L.use_filter && !((__ldg(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)]) >> (bin & 31)) & 1u)) continue;
+        unsigned long long* tb = slots + L.base[t];
+        uint64_t s = pk_slot0(bin, L.mask[t]);
+        while (true) {
+            unsigned long long v = __ldcg(&tb[s]);
+            if (v == PK_EMPTY) break;
+            if ((uint32_t)(v >> 32) == bin) {
+                if ((uint32_t)v > p) atomicMin(&tb[s], ((unsigned long long)bin << 32) | p);
+                break;
+            }
+            s = (s + 1) & L.mask[t];
+        }
+    }
+}
+
+// chunk-relative 32-bit read offsets from the caller's 64-bit ones, clipped to the chunk [b0, b1)
+__global__ void k_clip_offsets(const uint64_t* __restrict__ off64, uint32_t n, uint64_t b0, uint64_t b1, uint32_t* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = off64[i];
+    v = v < b0 ? b0 : (v > b1 ? b1 : v);
+    out[i] = (uint32_t)(v - b0);
+}
+
 // 5. bigcount scan after the fold: k-mers whose N bytes are all 255 now, and every k-mer touching a bin that
 //    reached 255 inside this chunk (so the host can find the stream position at which it did).
 template <int HK, int SRC>
