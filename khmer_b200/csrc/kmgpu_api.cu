@@ -64,7 +64,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt)
 static uint64_t chunk_bases()
 {
     static uint64_t c = [] {
-        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 32ull << 20);
+        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 64ull << 20);
         v = std::max<uint64_t>(TILE, std::min<uint64_t>(v, 1ull << 31));
         return (v / TILE) * TILE;
     }();
@@ -970,6 +970,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
             k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross);
         else
             k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0);
+        if (passes.size() <= 64) k_pass_snapshot<<<1, 1, 0, st>>>(h->d_ctrl, (int)(&p - passes.data()));
     }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
@@ -991,6 +992,31 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         CKR(h->d_newbits.ensure(nb_words));
         CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
         CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+        const uint64_t cold_min = env_u64("KMGPU_COLD_MIN_NEW", 8ull << 20);
+        if (passes.size() <= 64 && c.n_zbits >= cold_min) {
+            // cold chunk (most bins new): resolve one (table, block) at a time, so that the block's stamp table
+            // (a few tens of MB) stays in L2 while every position of the chunk probes it
+            unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
+            uint64_t seg0 = 0;
+            for (size_t pi = 0; pi < passes.size(); pi++) {
+                uint64_t seg1 = c.pass_list_end[pi];
+                if (seg1 > seg0) {
+                    const DeltaPass& p = passes[pi];
+                    uint64_t slots = pow2_at_least(2 * (seg1 - seg0));
+                    CKR(h->d_htkeys.ensure(slots));
+                    sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
+                    CK(cudaMemsetAsync(sl, 0xFF, slots * 8, st));
+                    unsigned gl = (unsigned)std::min<uint64_t>((seg1 - seg0 + 255) / 256, 148 * 8);
+                    k_pk_register<<<gl, 256, 0, st>>>(h->d_binlist.p + seg0, seg1 - seg0, p.table, sl, slots - 1, nullptr);
+                    k_pk_replay<<<(in.n_pos + 1023) / 1024, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, sl,
+                                                                    slots - 1, nullptr);
+                    unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
+                    k_pk_mark<<<gm, 256, 0, st>>>(sl, slots, h->d_newbits.p, h->d_ctrl);
+                    h->all_launches += 3;
+                }
+                seg0 = seg1;
+            }
+        } else {
         PkLayout L;
         memset(&L, 0, sizeof L);
         uint64_t total_slots = 0;
@@ -1002,11 +1028,18 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
             total_slots += sl;
         }
         L.use_filter = c.n_zbits < (uint64_t)h->nt * FILTER_BITS / 4;
+        {   // bitmap of ~32 bits per new bin, between 32 Kbit (4 KB, L1-resident) and FILTER_BITS per table
+            uint64_t mx = 0;
+            for (int i = 0; i < h->nt; i++) mx = std::max<uint64_t>(mx, c.n_new_t[i]);
+            uint64_t fb = 1u << 15;
+            while (fb < 32 * mx && fb < FILTER_BITS) fb <<= 1;
+            L.filter_bits = (uint32_t)fb;
+        }
         CKR(h->d_htkeys.ensure(total_slots));
         CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, total_slots * 8, st));
         if (L.use_filter) {
             CKR(h->d_filter.ensure((size_t)h->nt * FILTER_WORDS));
-            CK(cudaMemsetAsync(h->d_filter.p, 0, (size_t)h->nt * FILTER_WORDS * 4, st));
+            CK(cudaMemsetAsync(h->d_filter.p, 0, (size_t)h->nt * (L.filter_bits >> 5) * 4, st));
         }
         unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
         unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
@@ -1015,6 +1048,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         unsigned gm = (unsigned)std::min<uint64_t>((total_slots + 255) / 256, 148 * 8);
         k_pk_mark<<<gm, 256, 0, st>>>(sl, total_slots, h->d_newbits.p, h->d_ctrl);
         h->all_launches += 3;
+        }
         CK(cudaGetLastError());
         CKR(read_ctrl(h));
         h->n_unique += h->h_ctrl->n_unique;

@@ -18,6 +18,7 @@ struct Ctrl {
     unsigned long long n_events;  // records appended by k_events / k_cross_replay
     unsigned long long non_acgt;  // pack kernel: bytes outside ACGT seen in raw mode
     unsigned long long n_new_t[10];  // delta path: newly occupied bins per table
+    unsigned long long pass_list_end[64];  // delta path: bin list length after each (table, block) pass
 };
 
 // flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
@@ -932,24 +933,52 @@ __global__ void k_pk_register(const uint64_t* __restrict__ binlist, uint64_t n, 
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_pk_replay(const uint32_t* __restrict__ bins, uint32_t n_pos, unsigned long long* slots, uint64_t mask, const uint32_t* __restrict__ filter)
+__global__ void k_pass_snapshot(Ctrl* ctrl, int pass) { ctrl->pass_list_end[pass] = ctrl->n_events; }
+
+// finish one probe whose first slot value `v` has already been loaded
+__device__ __forceinline__ void pk_finish(unsigned long long* tb, uint64_t mask, uint64_t s, unsigned long long v, uint32_t bin, uint32_t p)
 {
-    uint32_t p = blockIdx.x * 256u + threadIdx.x;
-    if (p >= n_pos) return;
-    uint32_t bin = __ldcs(&bins[p]);
-    if (bin == BIN_NONE) return;
-    if (filter && !((__ldg(&filter[(bin & (FILTER_BITS - 1)) >> 5]) >> (bin & 31)) & 1u)) return;
-    uint64_t s = pk_slot0(bin, mask);
     while (true) {
-        unsigned long long v = __ldcg(&slots[s]);
         if (v == PK_EMPTY) return;
         if ((uint32_t)(v >> 32) == bin) {
-            if ((uint32_t)v > p) atomicMin(&slots[s], ((unsigned long long)bin << 32) | p);
+            if ((uint32_t)v > p) atomicMin(&tb[s], ((unsigned long long)bin << 32) | p);
             return;
         }
         s = (s + 1) & mask;
+        v = __ldcg(&tb[s]);
     }
+}
+
+// 4 consecutive positions per thread, their first probes issued together (the kernel is latency-bound otherwise)
+__global__ void __launch_bounds__(256)
+k_pk_replay(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32_t hi, unsigned long long* slots, uint64_t mask,
+            const uint32_t* __restrict__ filter)
+{
+    const uint32_t p0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    if (p0 >= n_pos) return;
+    uint32_t b[4];
+    if (p0 + 4 <= n_pos) {
+        uint4 q = __ldcs(reinterpret_cast<const uint4*>(bins + p0));
+        b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = p0 + j < n_pos ? __ldcs(bins + p0 + j) : BIN_NONE;
+    }
+    const uint32_t span = hi - lo;
+    bool act[4];
+    uint64_t s[4];
+    unsigned long long v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        act[j] = b[j] - lo < span;   // BIN_NONE and bins of other blocks fall out
+        if (act[j] && filter) act[j] = (__ldg(&filter[(b[j] & (FILTER_BITS - 1)) >> 5]) >> (b[j] & 31)) & 1u;
+        s[j] = act[j] ? pk_slot0(b[j], mask) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = act[j] ? __ldcg(&slots[s[j]]) : PK_EMPTY;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (act[j]) pk_finish(slots, mask, s[j], v[j], b[j], p0 + j);
 }
 
 __global__ void k_pk_mark(const unsigned long long* __restrict__ slots, uint64_t n_slots, uint32_t* newbits, Ctrl* ctrl)
@@ -973,6 +1002,7 @@ struct PkLayout {
     uint64_t base[F_MAXT];
     uint64_t mask[F_MAXT];   // 0 => table has no new bin in this chunk
     int use_filter;
+    uint32_t filter_bits;    // per table, power of two: small enough to sit in L1 when few bins are new
 };
 
 __global__ void k_pk_register_all(const uint64_t* __restrict__ binlist, uint64_t n, PkLayout L, unsigned long long* slots, uint32_t* filter)
@@ -990,7 +1020,7 @@ __global__ void k_pk_register_all(const uint64_t* __restrict__ binlist, uint64_t
             if (prev == PK_EMPTY || (uint32_t)(prev >> 32) == bin) break;
             s = (s + 1) & L.mask[t];
         }
-        if (L.use_filter) atomicOr(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)], 1u << (bin & 31));
+        if (L.use_filter) atomicOr(&filter[t * (L.filter_bits >> 5) + ((bin & (L.filter_bits - 1)) >> 5)], 1u << (bin & 31));
     }
 }
 
@@ -1000,22 +1030,21 @@ k_pk_replay_all(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables
 {
     uint32_t p = blockIdx.x * 256u + threadIdx.x;
     if (p >= n_pos) return;
+    uint32_t b[F_MAXT];
+    bool act[F_MAXT];
+    // bins of all tables, then all filter words, then all first probes: three rounds of independent loads
+    for (int t = 0; t < n_tables; t++) b[t] = __ldcs(&bins[t * stride + p]);
+    if (b[0] == BIN_NONE) return;
+    const uint32_t fmask = L.filter_bits - 1, fwords = L.filter_bits >> 5;
     for (int t = 0; t < n_tables; t++) {
-        uint32_t bin = __ldcs(&bins[t * stride + p]);
-        if (bin == BIN_NONE) return;
-        if (!L.mask[t]) continue;
-        if (L.use_filter && !((__ldg(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)]) >> (bin & 31)) & 1u)) continue;
+        act[t] = L.mask[t] != 0;
+        if (act[t] && L.use_filter) act[t] = (__ldg(&filter[t * fwords + ((b[t] & fmask) >> 5)]) >> (b[t] & 31)) & 1u;
+    }
+    for (int t = 0; t < n_tables; t++) {
+        if (!act[t]) continue;
         unsigned long long* tb = slots + L.base[t];
-        uint64_t s = pk_slot0(bin, L.mask[t]);
-        while (true) {
-            unsigned long long v = __ldcg(&tb[s]);
-            if (v == PK_EMPTY) break;
-            if ((uint32_t)(v >> 32) == bin) {
-                if ((uint32_t)v > p) atomicMin(&tb[s], ((unsigned long long)bin << 32) | p);
-                break;
-            }
-            s = (s + 1) & L.mask[t];
-        }
+        uint64_t s = pk_slot0(b[t], L.mask[t]);
+        pk_finish(tb, L.mask[t], s, __ldcg(&tb[s]), b[t], p);
     }
 }
 

@@ -51,7 +51,8 @@ def test_gpu_golden_cases_cas_single_pass():
 def test_gpu_golden_cases_delta_many_blocks():
     """All reference goldens through the delta+fold path with ~2k-bin blocks (many blocks per table)."""
     import subprocess, sys
-    env = dict(os.environ, KMGPU_DELTA_BLOCK_BINS="2048", KMGPU_DELTA_MAX_PASSES="1000000", KMGPU_CHUNK_BASES="65536")
+    env = dict(os.environ, KMGPU_DELTA_BLOCK_BINS="2048", KMGPU_DELTA_MAX_PASSES="1000000", KMGPU_CHUNK_BASES="65536",
+               KMGPU_COLD_MIN_NEW="64")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
                         "test_gpu_matches_reference_golden and not C1 and not 25k"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -64,7 +65,7 @@ def _same_state(g, o, n_tables):
 
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
-@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks"])
+@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
@@ -75,6 +76,8 @@ def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
             env.update(KMGPU_DELTA="0", KMGPU_L2_BLOCK_BYTES="1500", KMGPU_MAX_PASSES="64", KMGPU_CHUNK_BASES="16384")
         elif chunk == "cas-8192":   # compare-and-swap path, all tables in one pass
             env.update(KMGPU_DELTA="0", KMGPU_CHUNK_BASES="8192")
+        elif chunk == "delta-cold":   # delta+fold path, per-block ("cold chunk") stamp resolution forced
+            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768")
         elif chunk == "delta-blocks":   # delta+fold path with many blocks per table
             env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384")
         else:
