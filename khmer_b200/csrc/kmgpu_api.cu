@@ -825,24 +825,29 @@ struct DeltaPass {
     uint32_t lo, hi;
 };
 
-static uint64_t delta_block_bins()
+// bins per delta block: 2 bytes per bin for the counting storages (half lanes), 1 bit per bin for BitStorage
+static uint64_t delta_block_bins(int kind)
 {
     uint64_t b = env_u64("KMGPU_DELTA_BLOCK_BINS", 0);  // test hook
-    if (!b) b = env_u64("KMGPU_DELTA_BLOCK_MB", 50) * 1000000ull / 2;
-    b &= ~7ull;
-    return b < 8 ? 8 : b;
+    if (!b) {
+        uint64_t bytes = env_u64("KMGPU_DELTA_BLOCK_MB", 50) * 1000000ull;
+        b = kind == BIT ? bytes * 8 : bytes / 2;
+    }
+    const uint64_t gran = kind == BIT ? 128 : 8;
+    b = (b / gran) * gran;
+    return b < gran ? gran : b;
 }
 
 static bool plan_delta(const kmgpu_sketch* h, std::vector<DeltaPass>& out)
 {
     out.clear();
     if (!env_u64("KMGPU_DELTA", 1)) return false;
-    if (h->kind != BYTE && h->kind != NIBBLE) return false;
-    const uint64_t block = delta_block_bins();
+    const uint64_t block = delta_block_bins(h->kind);
+    const uint64_t gran = h->kind == BIT ? 128 : 8;
     for (int i = 0; i < h->nt; i++) {
-        if (h->sizes[i] > 0xFFFFFFFEull) return false;
+        if (h->sizes[i] > 0xFFFFFFFEull - 128) return false;
         uint64_t r = (h->sizes[i] + block - 1) / block;
-        uint64_t per = ((h->sizes[i] + r - 1) / r + 7) & ~7ull;
+        uint64_t per = (((h->sizes[i] + r - 1) / r + gran - 1) / gran) * gran;
         for (uint64_t j = 0; j * per < h->sizes[i]; j++)
             out.push_back(DeltaPass{i, (uint32_t)(j * per), (uint32_t)std::min<uint64_t>(h->sizes[i], (j + 1) * per)});
     }
@@ -945,7 +950,8 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     for (const DeltaPass& p : passes) max_span = std::max<uint64_t>(max_span, p.hi - p.lo);
     const uint64_t list_cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nt * in.n_pos, total_bins));
     CKR(h->d_binlist.ensure(list_cap));
-    size_t need_lanes = ((max_span + 7) & ~7ull) + 8;
+    // block storage in 2-byte units: one half lane per bin, or one bit per bin for BitStorage
+    size_t need_lanes = h->kind == BIT ? ((max_span + 127) / 128) * 8 + 8 : ((max_span + 7) & ~7ull) + 8;
     if (h->d_delta.cap < need_lanes) h->delta_zeroed = 0;
     CKR(h->d_delta.ensure(need_lanes));
     if (h->delta_zeroed < h->d_delta.cap) {  // the fold keeps the block zeroed from then on
@@ -964,7 +970,14 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     const int want_cross = h->kind == BYTE && h->use_bigcount;
     const unsigned gs = (in.n_pos + 2047) / 2048;
     for (const DeltaPass& p : passes) {
-        k_scatter<<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
+        if (h->kind == BIT) {
+            k_scatter<true><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
+            unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
+            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl);
+            if (passes.size() <= 64) k_pass_snapshot<<<1, 1, 0, st>>>(h->d_ctrl, (int)(&p - passes.data()));
+            continue;
+        }
+        k_scatter<false><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
         unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
         if (h->kind == BYTE)
             k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross);

@@ -745,7 +745,9 @@ k_hashbins(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __re
     if (threadIdx.x == 0 && sm.acc[0]) atomicAdd(&ctrl->n_kmers, sm.acc[0]);
 }
 
-// 2. touches of one table block: bins of this table in [lo, hi) -> +1 on their half lane
+// 2. touches of one table block: bins of this table in [lo, hi) -> +1 on their half lane (counting storages)
+//    or their bit set in the block's bitmap (BitStorage: OR is idempotent, so a return-less red.or is exact)
+template <bool BITS>
 __global__ void __launch_bounds__(256)
 k_scatter(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta)
 {
@@ -764,7 +766,77 @@ k_scatter(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint32_t d = v[j] - lo;           // BIN_NONE and bins below lo wrap far above span
-        if (d < span) red_add_half_lane(delta, d);
+        if (d >= span) continue;
+        if (BITS) {
+            uint32_t* word = reinterpret_cast<uint32_t*>(delta) + (d >> 5);
+            asm volatile("red.global.or.b32 [%0], %1;" ::"l"(word), "r"(1u << (d & 31)) : "memory");
+        } else {
+            red_add_half_lane(delta, d);
+        }
+    }
+}
+
+// 3b. BitStorage fold: 128 bins (4 words) per thread.  new bits = block & ~table (BitStorage::test_and_set_bits,
+//     storage.hh:176-195: a k-mer is new iff one of its bits was clear); table |= block; block re-zeroed.
+__global__ void __launch_bounds__(256)
+k_fold_bits(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta, uint64_t* __restrict__ binlist,
+            unsigned long long list_cap, Ctrl* ctrl)
+{
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;   // group of 128 bins
+    const uint32_t span = hi - lo;
+    unsigned n_new = 0;
+    uint4 fresh = make_uint4(0, 0, 0, 0);
+    if ((uint64_t)g * 128u < span) {
+        uint4* dp = reinterpret_cast<uint4*>(delta) + g;
+        uint4 d = *dp;
+        if (d.x | d.y | d.z | d.w) {
+            *dp = make_uint4(0, 0, 0, 0);
+            uint4* tp = reinterpret_cast<uint4*>(table + (lo >> 3)) + g;
+            uint4 t = *tp;
+            fresh = make_uint4(d.x & ~t.x, d.y & ~t.y, d.z & ~t.z, d.w & ~t.w);
+            if (fresh.x | fresh.y | fresh.z | fresh.w) {
+                *tp = make_uint4(t.x | d.x, t.y | d.y, t.z | d.z, t.w | d.w);
+                n_new = __popc(fresh.x) + __popc(fresh.y) + __popc(fresh.z) + __popc(fresh.w);
+            }
+        }
+    }
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned incl = n_new;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    if (lane == 31) s_cnt[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; w++) tot += s_cnt[w];
+        s_base = tot ? atomicAdd(&ctrl->n_events, (unsigned long long)tot) : 0ull;
+        if (tot) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)tot);
+            atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)tot);
+            if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)tot);
+        }
+    }
+    __syncthreads();
+    if (n_new) {
+        unsigned long long at = s_base + (incl - n_new);
+        for (unsigned w = 0; w < wid; w++) at += s_cnt[w];
+        const uint32_t fw[4] = {fresh.x, fresh.y, fresh.z, fresh.w};
+        const uint32_t b0 = lo + g * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t m = fw[q];
+            while (m) {
+                int bit = __ffs(m) - 1;
+                m &= m - 1;
+                if (at < list_cap) binlist[at] = BL_NEW | ht_key((uint64_t)(b0 + q * 32 + bit), table_idx);
+                at++;
+            }
+        }
     }
 }
 
