@@ -185,6 +185,14 @@ struct kmgpu_sketch {
     DevBuf<uint16_t> d_delta;
     size_t delta_zeroed = 0;
     DevBuf<uint64_t> d_binlist;
+    DevBuf<uint32_t> d_sel;      // radix-select state (need / prefix / cnt per crossing-bin slot) + record slots
+    DevBuf<uint32_t> d_recslot;
+    DevBuf<unsigned long long> d_evkeys;
+    DevBuf<uint32_t> d_evvals;
+    DevBuf<EvOut> d_evout;
+    PinBuf<EvOut> h_evout;
+    DevBuf<uint8_t> d_satbits[MAX_TABLES];   // delta path + bigcount: bitmap of saturated bytes per table
+    bool satbits_valid = false;
     DevBuf<uint64_t> d_htkeys;
     DevBuf<uint32_t> d_htvals;
     DevBuf<Event> d_events;
@@ -432,7 +440,9 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
+    for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
     h->d_hashin.release(); h->d_stat_med.release(); h->d_stat_f.release(); h->d_stat_n.release(); h->d_stat_b.release();
     h->d_hist.release(); h->big_keys.release(); h->big_vals.release();
@@ -454,6 +464,7 @@ extern "C" int kmgpu_set_use_bigcount(kmgpu_t* h, int on)
     if (h->kind != KMGPU_BYTE) return fail(KMGPU_EUNSUPPORTED, "bigcount is not supported for this storage.");  // storage.cc:52-54
     std::lock_guard<std::mutex> g(h->mu);
     h->use_bigcount = on != 0;
+    h->satbits_valid = false;
     return KMGPU_OK;
 }
 extern "C" int kmgpu_get_use_bigcount(kmgpu_t* h, int* on)
@@ -522,6 +533,7 @@ extern "C" int kmgpu_upload_table(kmgpu_t* h, int table, const uint8_t* src, uin
     CKR(set_device(h->device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(h->dev.tables[table] + offset, src, nbytes, cudaMemcpyHostToDevice));
+    h->satbits_valid = false;
     return KMGPU_OK;
 }
 
@@ -542,6 +554,7 @@ extern "C" int kmgpu_reset(kmgpu_t* h)
     h->n_unique = 0;
     h->big.clear();
     h->big_dirty = true;
+    h->satbits_valid = false;
     return KMGPU_OK;
 }
 extern "C" int kmgpu_timer_start(kmgpu_t* h)
@@ -866,13 +879,20 @@ static void launch_hashbins(bool pred, unsigned g, cudaStream_t st, const Sketch
     else k_hashbins<HK, SRC, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
 }
 
+// ByteStorage::add tail (storage.hh:606-617) applied `count` times to one k-mer
+static inline void big_events(kmgpu_sketch* h, uint64_t hash, uint32_t count)
+{
+    uint16_t& v = h->big[hash];
+    uint32_t base = v == 0 ? 255u : v;
+    uint32_t nv = base + count;
+    v = (uint16_t)(nv > 65535u ? 65535u : nv);
+    h->big_dirty = true;
+}
+
 static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Input& in, uint64_t stride, uint64_t n_list, uint64_t n_cross)
 {
     cudaStream_t st = h->stream;
-    const SketchDev& S = h->dev;
-    unsigned g = n_tiles(in.n_pos);
     uint64_t slots = 1024;
-    std::unordered_map<uint64_t, uint32_t> before;  // crossing bin (bin << 8 | table) -> value before the chunk
     if (n_cross) {
         slots = pow2_at_least(2 * n_cross);
         CKR(h->d_htkeys.ensure(slots));
@@ -882,56 +902,73 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
         k_list_register<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, BL_CROSS, h->d_htkeys.p, h->d_htvals.p, slots - 1, nullptr, 1);
         h->all_launches += 1;
     }
+    // 1. candidates and touches of crossing bins
     uint64_t cap = in.n_pos;
     CKR(h->d_events.ensure(cap));
-    CKR(h->h_events.ensure(cap));
     CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
-    DISPATCH_HK_SRC(k_bigscan, H.kind, src, g, st, S, H, in, h->d_bins.p, stride, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0, h->d_events.p,
-                    (unsigned long long)cap, h->d_ctrl);
+    SatBits sb;
+    for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
+    {
+        unsigned gb = (in.n_pos + 255) / 256;
+        if (src == 1) k_bigscan<TWOBIT, 1><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
+                                                                h->d_events.p, (unsigned long long)cap, h->d_ctrl);
+        else if (H.kind == TWOBIT) k_bigscan<TWOBIT, 0><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1,
+                                                                            n_cross ? 1 : 0, h->d_events.p, (unsigned long long)cap, h->d_ctrl);
+        else k_bigscan<MURMUR, 0><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
+                                                      h->d_events.p, (unsigned long long)cap, h->d_ctrl);
+    }
     h->all_launches += 1;
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
-    uint64_t n_rec = h->h_ctrl->n_events;
+    const uint64_t n_rec = h->h_ctrl->n_events;
     if (n_rec > cap) return fail(KMGPU_ECUDA, "internal: bigcount scan overflow");
-    if (n_rec) CK(cudaMemcpyAsync(h->h_events.p, h->d_events.p, n_rec * sizeof(Event), cudaMemcpyDeviceToHost, st));
-    std::vector<uint64_t> hk;
-    std::vector<uint32_t> hv;
+    if (n_rec == 0) return KMGPU_OK;
+    const unsigned gr = (unsigned)((n_rec + 255) / 256);
+    // 2. stream position of the saturating touch of every crossing bin (radix select over the reported touches)
+    uint32_t* Tarr = nullptr;
     if (n_cross) {
-        hk.resize(slots);
-        hv.resize(slots);
-        CK(cudaMemcpyAsync(hk.data(), h->d_htkeys.p, slots * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hv.data(), h->d_htvals.p, slots * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    for (uint64_t i = 0; i < hk.size(); i++)
-        if (hk[i] != HT_EMPTY) before[hk[i]] = hv[i];
-    std::vector<Event> recs(h->h_events.p, h->h_events.p + n_rec);
-    std::sort(recs.begin(), recs.end(), [](const Event& a, const Event& b) { return a.pos < b.pos; });
-    // stream position T at which each crossing bin reached 255: its (255 - before)-th touch of the chunk
-    std::unordered_map<uint64_t, std::vector<uint32_t>> touches;
-    for (const Event& e : recs) {
-        uint32_t cross = e.info & 0x3ff;
-        for (int i = 0; i < h->nt && cross; i++)
-            if (cross >> i & 1) touches[((e.hash % h->sizes[i]) << 8) | (uint64_t)i].push_back(e.pos);
-    }
-    std::unordered_map<uint64_t, uint32_t> T;
-    for (auto& kv : touches) {
-        auto it = before.find(kv.first);
-        if (it == before.end()) return fail(KMGPU_ECUDA, "internal: crossing bin without a recorded value");
-        size_t need = 255 - it->second;  // >= 1
-        if (kv.second.size() < need) return fail(KMGPU_ECUDA, "internal: inconsistent saturation record");
-        T[kv.first] = kv.second[need - 1];
-    }
-    for (const Event& e : recs) {
-        if (!(e.info >> 30 & 1)) continue;  // some byte of this k-mer is still below 255
-        bool after_all = true;
-        uint32_t cross = e.info & 0x3ff;
-        for (int i = 0; i < h->nt && after_all; i++) {
-            if (!(cross >> i & 1)) continue;
-            if (!(e.pos > T[((e.hash % h->sizes[i]) << 8) | (uint64_t)i])) after_all = false;
+        CKR(h->d_sel.ensure(3 * slots));
+        CKR(h->d_recslot.ensure(n_rec * F_MAXT));
+        SelState ss{h->d_sel.p, h->d_sel.p + slots, h->d_sel.p + 2 * slots};
+        const unsigned gsl = (unsigned)((slots + 255) / 256);
+        k_sel_slots<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->dev, h->d_htkeys.p, slots - 1, h->d_recslot.p);
+        k_sel_init<<<gsl, 256, 0, st>>>(h->d_htkeys.p, h->d_htvals.p, slots, ss);
+        int top = 0;
+        while (top < 31 && (1ull << (top + 1)) <= (uint64_t)in.n_pos) top++;
+        for (int bit = top; bit >= 0; bit--) {
+            k_sel_count<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->nt, h->d_recslot.p, bit, ss);
+            k_sel_update<<<gsl, 256, 0, st>>>(slots, bit, ss);
         }
-        if (after_all) big_event(h, e.hash);
+        h->all_launches += 2 + 2 * (top + 1);
+        Tarr = ss.prefix;
     }
+    // 3. decide and aggregate per k-mer
+    uint64_t evslots = pow2_at_least(2 * n_rec);
+    CKR(h->d_evkeys.ensure(evslots));
+    CKR(h->d_evvals.ensure(2 * evslots));
+    CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, evslots * 8, st));
+    CK(cudaMemsetAsync(h->d_evvals.p, 0, evslots * 4, st));
+    CK(cudaMemsetAsync(h->d_evvals.p + evslots, 0xFF, evslots * 4, st));
+    CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+    EvTable ev{h->d_evkeys.p, h->d_evvals.p, h->d_evvals.p + evslots, evslots - 1};
+    k_ev_decide<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->nt, h->d_recslot.p, Tarr, n_cross ? 1 : 0, ev, h->d_ctrl);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    const uint64_t n_distinct = h->h_ctrl->n_unique;
+    if (n_distinct == 0) return KMGPU_OK;
+    CKR(h->d_evout.ensure(n_distinct));
+    CKR(h->h_evout.ensure(n_distinct));
+    k_ev_compact<<<(unsigned)((evslots + 255) / 256), 256, 0, st>>>(ev, h->d_evout.p, h->d_ctrl);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_evout.p, h->d_evout.p, n_distinct * sizeof(EvOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // 4. one map update per distinct k-mer, new keys inserted in the order of their first event (stream order)
+    std::vector<EvOut> evs(h->h_evout.p, h->h_evout.p + n_distinct);
+    std::sort(evs.begin(), evs.end(), [](const EvOut& a, const EvOut& b) { return a.first < b.first; });
+    for (const EvOut& e : evs) big_events(h, e.hash, e.count);
     return KMGPU_OK;
 }
 
@@ -968,6 +1005,15 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         else launch_hashbins<MURMUR, 0>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
     }
     const int want_cross = h->kind == BYTE && h->use_bigcount;
+    if (want_cross && !h->satbits_valid) {
+        for (int i = 0; i < h->nt; i++) {
+            uint64_t groups = (h->sizes[i] + 7) / 8;
+            CKR(h->d_satbits[i].ensure(groups));
+            k_build_satbits<<<(unsigned)std::min<uint64_t>((groups + 255) / 256, 148 * 16), 256, 0, st>>>(h->dev.tables[i], groups, h->d_satbits[i].p);
+            h->all_launches += 1;
+        }
+        h->satbits_valid = true;
+    }
     const unsigned gs = (in.n_pos + 2047) / 2048;
     for (const DeltaPass& p : passes) {
         if (h->kind == BIT) {
@@ -980,9 +1026,10 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         k_scatter<false><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
         unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
         if (h->kind == BYTE)
-            k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross);
+            k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross,
+                                             want_cross ? h->d_satbits[p.table].p : nullptr);
         else
-            k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0);
+            k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, nullptr);
         if (passes.size() <= 64) k_pass_snapshot<<<1, 1, 0, st>>>(h->d_ctrl, (int)(&p - passes.data()));
     }
     CK(cudaEventRecord(h->ev1, st));
@@ -1767,6 +1814,7 @@ extern "C" int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, 
 // ------------------------------------------------------------------------------------------------------
 static int recount_occupied_locked(kmgpu_sketch* h)
 {
+    h->satbits_valid = false;  // callers have just rewritten table words (merge / reduce / gather)
     cudaStream_t st = h->stream;
     CK(cudaMemsetAsync(&h->d_ctrl->n_z0, 0, sizeof(unsigned long long), st));
     uint64_t nw = h->alloc_bytes[0] / 4;

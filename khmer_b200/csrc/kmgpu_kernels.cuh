@@ -846,7 +846,7 @@ k_fold_bits(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi
 template <int KIND>
 __global__ void __launch_bounds__(256)
 k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta, uint64_t* __restrict__ binlist,
-       unsigned long long list_cap, Ctrl* ctrl, int want_cross)
+       unsigned long long list_cap, Ctrl* ctrl, int want_cross, uint8_t* __restrict__ satbits)
 {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;  // group of 8 bins
     const uint32_t span = hi - lo;
@@ -898,8 +898,17 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
                     ent[n_ent++] = entry | ht_key((uint64_t)(b0 + j), table_idx);
                 }
             }
-            if (KIND == BYTE) *reinterpret_cast<uint64_t*>(table + b0) = new64;
-            else *reinterpret_cast<uint32_t*>(table + (b0 >> 1)) = new32;
+            if (KIND == BYTE) {
+                *reinterpret_cast<uint64_t*>(table + b0) = new64;
+                if (satbits) {   // one bit per bin "byte is 255": this thread owns the whole byte of the bitmap
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) m |= (uint32_t)(((new64 >> (8 * j)) & 255u) == 255u) << j;
+                    satbits[b0 >> 3] = (uint8_t)m;
+                }
+            } else {
+                *reinterpret_cast<uint32_t*>(table + (b0 >> 1)) = new32;
+            }
         }
     }
     // one list reservation and one set of counter updates per CTA (same-address atomics from every warp of a
@@ -1130,33 +1139,222 @@ __global__ void k_clip_offsets(const uint64_t* __restrict__ off64, uint32_t n, u
     out[i] = (uint32_t)(v - b0);
 }
 
-// 5. bigcount scan after the fold: k-mers whose N bytes are all 255 now, and every k-mer touching a bin that
-//    reached 255 inside this chunk (so the host can find the stream position at which it did).
-template <int HK, int SRC>
-__global__ void __launch_bounds__(THREADS)
-k_bigscan(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ bins, uint64_t stride, const uint64_t* __restrict__ keys,
-          uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl)
+// 5. bigcount scan after the fold.  satbits[t] holds one bit per bin of table t, set iff the byte is 255 (kept by
+//    k_fold, rebuilt by k_build_satbits after uploads/merges), 12.5 MB per 1e8-bin table: L2-resident, so nearly
+//    every k-mer is dismissed after one cached load.  Reported: k-mers whose N bytes are all 255 now, and — when
+//    bins reached 255 inside this chunk — every k-mer touching such a bin (the host needs all their positions).
+struct SatBits {
+    const uint8_t* t[F_MAXT];
+};
+
+__global__ void k_build_satbits(const uint8_t* __restrict__ table, uint64_t n_groups, uint8_t* __restrict__ satbits)
 {
-    __shared__ TileSmem sm;
-    const uint32_t t0 = blockIdx.x * TILE;
-    tile_begin<HK, SRC>(in, H.k, t0, sm);
-    for (uint32_t lp = threadIdx.x; lp < TILE && t0 + lp < in.n_pos; lp += THREADS) {
-        const uint32_t p = t0 + lp;
-        if (bins[p] == BIN_NONE) continue;
-        uint32_t cross = 0, allsat = 1;
-        for (int i = 0; i < S.n_tables; i++) {
-            uint32_t bin = bins[i * stride + p];
-            if (have_cross && ht_find(keys, mask, ht_key(bin, i)) != ~0ull) cross |= 1u << i;
-            else if (read_byte(S.tables[i], bin) != 255u) allsat = 0;
-        }
-        if (!cross && !allsat) continue;
-        Event e;
-        e.hash = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
-        e.pos = p;
-        e.info = cross | (allsat << 30);
-        unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
-        if (at < cap) out[at] = e;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t v = *reinterpret_cast<const uint64_t*>(table + g * 8);
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) m |= (uint32_t)(((v >> (8 * j)) & 255u) == 255u) << j;
+        satbits[g] = (uint8_t)m;
     }
+}
+
+// hash of the k-mer at stream position p straight from global memory (rare path: candidates only)
+template <int HK, int SRC>
+__device__ __forceinline__ uint64_t hash_at(const Input& in, int k, uint32_t p)
+{
+    if (SRC == 1) return in.hashes[p];
+    if (HK == TWOBIT) return hash_twobit(in.words, p, k);
+    // Murmur without the shared-memory LUT: rebuild the four-letter words arithmetically
+    Murmur F, R;
+    F.init();
+    R.init();
+    bool same = true;
+    auto expand = [](uint32_t v, uint64_t& k1, uint64_t& k2) {
+        uint64_t w[2] = {0, 0};
+        for (int j = 0; j < 16; j++) {
+            uint32_t c = (v >> (30 - 2 * j)) & 3u;
+            uint64_t ch = c == 0 ? 'A' : c == 1 ? 'T' : c == 2 ? 'C' : 'G';
+            w[j >> 3] |= ch << (8 * (j & 7));
+        }
+        k1 = w[0];
+        k2 = w[1];
+    };
+    int nfull = k >> 4, rem = k & 15;
+    for (int b = 0; b < nfull; b++) {
+        uint32_t fv = get16(in.words, p + 16 * b);
+        uint32_t rv = pair_reverse32(get16(in.words, p + k - 16 * b - 16)) ^ 0x55555555u;
+        same &= fv == rv;
+        uint64_t k1, k2;
+        expand(fv, k1, k2);
+        F.block(k1, k2);
+        expand(rv, k1, k2);
+        R.block(k1, k2);
+    }
+    if (rem) {
+        uint32_t keep = ~0u << (32 - 2 * rem);
+        uint32_t fv = get16(in.words, p + 16 * nfull) & keep;
+        uint32_t src = get16(in.words, p) >> (32 - 2 * rem);
+        uint32_t rv = ((pair_reverse32(src) >> (32 - 2 * rem)) ^ (0x55555555u >> (32 - 2 * rem))) << (32 - 2 * rem);
+        same &= fv == rv;
+        uint64_t m1 = rem >= 8 ? ~0ull : ((1ull << (8 * rem)) - 1);
+        uint64_t m2 = rem > 8 ? ((1ull << (8 * (rem - 8))) - 1) : 0;
+        uint64_t k1, k2;
+        expand(fv, k1, k2);
+        F.tail(k1 & m1, k2 & m2, rem);
+        expand(rv, k1, k2);
+        R.tail(k1 & m1, k2 & m2, rem);
+    }
+    uint64_t h = F.finish((uint64_t)k);
+    return same ? h : h ^ R.finish((uint64_t)k);
+}
+
+template <int HK, int SRC>
+__global__ void __launch_bounds__(256)
+k_bigscan(int n_tables, HashCfg H, Input in, const uint32_t* __restrict__ bins, uint64_t stride, SatBits sat,
+          const uint64_t* __restrict__ keys, uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl)
+{
+    const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= in.n_pos) return;
+    uint32_t b[F_MAXT];
+    for (int i = 0; i < n_tables; i++) b[i] = __ldcs(&bins[i * stride + p]);
+    if (b[0] == BIN_NONE) return;
+    uint32_t satmask = 0;
+    for (int i = 0; i < n_tables; i++) {
+        uint32_t bit = (__ldg(&sat.t[i][b[i] >> 3]) >> (b[i] & 7)) & 1u;
+        satmask |= bit << i;
+        if (!bit && !have_cross) return;   // a byte below 255 and no crossing bins to report: not a candidate
+    }
+    uint32_t cross = 0;
+    if (have_cross) {
+        for (int i = 0; i < n_tables; i++)
+            if ((satmask >> i & 1u) && ht_find(keys, mask, ht_key(b[i], i)) != ~0ull) cross |= 1u << i;
+    }
+    const uint32_t allsat = satmask == (1u << n_tables) - 1u;
+    if (!cross && !allsat) return;
+    Event e;
+    e.hash = hash_at<HK, SRC>(in, H.k, p);
+    e.pos = p;
+    e.info = cross | (allsat << 30);
+    unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+    if (at < cap) out[at] = e;
+}
+
+// 6. bigcount events resolved on the device (delta path).
+//    For a bin that reached 255 inside the chunk with value s before it, the saturating touch is its
+//    need = 255 - s -th touch in stream order; T = that touch's position is found for all such bins at once by a
+//    radix select over the positions of the reported touches (one counting pass per position bit).  A k-mer whose N
+//    bytes are all 255 after the chunk is a bigcount event iff it comes after T in every such bin it touches.  Events
+//    are aggregated per k-mer hash (count, first position) so the host applies one map update per distinct k-mer.
+struct SelState {          // per slot of the crossing-bin hash table
+    uint32_t* need;        // remaining rank to find (starts at 255 - before)
+    uint32_t* prefix;      // bits of T decided so far
+    uint32_t* cnt;         // scratch: touches matching the prefix with the current bit clear
+};
+
+// slot of every (record, crossing table) pair, computed once
+__global__ void k_sel_slots(const Event* __restrict__ recs, uint64_t n_rec, SketchDev S, const uint64_t* __restrict__ keys, uint64_t mask,
+                            uint32_t* __restrict__ rec_slot)
+{
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    Event e = recs[r];
+    uint32_t cross = e.info & 0x3ffu;
+    for (int i = 0; i < S.n_tables; i++) {
+        uint32_t sl = 0xFFFFFFFFu;
+        if (cross >> i & 1u) sl = (uint32_t)ht_find(keys, mask, ht_key(mod_magic(e.hash, S.sizes[i], S.magic[i]), i));
+        rec_slot[r * F_MAXT + i] = sl;
+    }
+}
+
+__global__ void k_sel_init(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ before, uint64_t n_slots, SelState st)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    st.need[s] = keys[s] == HT_EMPTY ? 0u : 255u - before[s];
+    st.prefix[s] = 0;
+    st.cnt[s] = 0;
+}
+
+__global__ void k_sel_count(const Event* __restrict__ recs, uint64_t n_rec, int n_tables, const uint32_t* __restrict__ rec_slot, int bit,
+                            SelState st)
+{
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    uint32_t pos = recs[r].pos;
+    if ((pos >> bit) & 1u) return;
+    for (int i = 0; i < n_tables; i++) {
+        uint32_t sl = rec_slot[r * F_MAXT + i];
+        if (sl == 0xFFFFFFFFu) continue;
+        // same bits above `bit` as the prefix decided so far
+        if (bit == 31 || (pos >> (bit + 1)) == (st.prefix[sl] >> (bit + 1))) atomicAdd(&st.cnt[sl], 1u);
+    }
+}
+
+__global__ void k_sel_update(uint64_t n_slots, int bit, SelState st)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    uint32_t need = st.need[s];
+    if (need) {
+        uint32_t c = st.cnt[s];
+        if (c < need) {            // the need-th smallest position has this bit set
+            st.need[s] = need - c;
+            st.prefix[s] |= 1u << bit;
+        }
+    }
+    st.cnt[s] = 0;
+}
+
+// events hash table keyed by k-mer hash: count of events, first position
+struct EvTable {
+    unsigned long long* keys;   // HT_EMPTY = free
+    uint32_t* count;
+    uint32_t* first;
+    uint64_t mask;
+};
+
+__global__ void k_ev_decide(const Event* __restrict__ recs, uint64_t n_rec, int n_tables, const uint32_t* __restrict__ rec_slot,
+                            const uint32_t* __restrict__ T, int have_cross, EvTable ev, Ctrl* ctrl)
+{
+    uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    Event e = recs[r];
+    if (!(e.info >> 30 & 1u)) return;   // some byte of this k-mer is still below 255
+    if (have_cross) {
+        for (int i = 0; i < n_tables; i++) {
+            uint32_t sl = rec_slot[r * F_MAXT + i];
+            if (sl != 0xFFFFFFFFu && !(e.pos > T[sl])) return;   // arrived before (or as) the saturating touch
+        }
+    }
+    uint64_t s = fmix64(e.hash) & ev.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&ev.keys[s], (unsigned long long)HT_EMPTY, (unsigned long long)e.hash);
+        if (prev == HT_EMPTY) atomicAdd(&ctrl->n_unique, 1ull);   // distinct k-mers with events (n_unique is free here)
+        if (prev == HT_EMPTY || prev == e.hash) break;
+        s = (s + 1) & ev.mask;
+    }
+    atomicAdd(&ev.count[s], 1u);
+    atomicMin(&ev.first[s], e.pos);
+}
+
+struct EvOut {
+    uint64_t hash;
+    uint32_t count;
+    uint32_t first;
+};
+
+__global__ void k_ev_compact(EvTable ev, EvOut* out, Ctrl* ctrl)
+{
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s > ev.mask) return;
+    unsigned long long k = ev.keys[s];
+    if (k == HT_EMPTY) return;
+    unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+    EvOut o;
+    o.hash = k;
+    o.count = ev.count[s];
+    o.first = ev.first[s];
+    out[at] = o;
 }
 
 }  // namespace kmgpu
