@@ -78,6 +78,9 @@ typedef struct {
 const char* kmgpu_last_error(void);
 int kmgpu_abi_version(void);
 int kmgpu_device_count(int* n);
+/* page-locked host memory for read batches (uploads from it are asynchronous and run at PCIe speed) */
+int kmgpu_alloc_pinned(size_t nbytes, void** out);
+int kmgpu_free_pinned(void* p);
 
 /* ---- lifetime -------------------------------------------------------------------------
  * Replaces: ByteStorage/NibbleStorage/BitStorage constructors + _allocate_counters

@@ -33,7 +33,7 @@ SYMBOLS = [
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
     "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
-    "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range",
+    "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
 ]
 
 

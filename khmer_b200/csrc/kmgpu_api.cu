@@ -346,6 +346,21 @@ extern "C" int kmgpu_device_count(int* n)
     return KMGPU_OK;
 }
 
+extern "C" int kmgpu_alloc_pinned(size_t nbytes, void** out)
+{
+    if (!out) return fail(KMGPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(KMGPU_ENODEV, "no CUDA device");
+    CK(cudaMallocHost(out, nbytes ? nbytes : 1));
+    return KMGPU_OK;
+}
+extern "C" int kmgpu_free_pinned(void* p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return KMGPU_OK;
+}
+
 static uint64_t table_nbytes(int kind, uint64_t size)
 {
     // ByteStorage: size; NibbleStorage: size/2+1; BitStorage: size/8+1 (storage.hh:505-507, :290, :118)

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <limits>
 #include <sstream>
 
@@ -810,8 +811,6 @@ void Hashtable::bulk_consume(ReadParserPtr<SeqIO>& parser, const uint64_t* band,
     // Hashtable::consume_seqfile (hashtable.cc:126-150): reads are cleaned (on the device) and all their
     // k-mers counted.  Reads are pulled from the shared parser a batch at a time, so several host threads
     // may run this on one table as the reference's scripts do.
-    std::string seqs;
-    std::vector<uint64_t> offs;
     kmgpu_band_t b;
     kmgpu_mask_t m;
     if (band) {
@@ -823,15 +822,31 @@ void Hashtable::bulk_consume(ReadParserPtr<SeqIO>& parser, const uint64_t* band,
         m.threshold = threshold;
         m.consume_masked = consume_masked ? 1 : 0;
     }
-    while (true) {
-        seqs.clear();
-        offs.clear();
-        size_t got = parser->io().read_batch(feed_bases(), seqs, offs);
-        if (got == 0) break;
+    // two pinned batches: the next one is parsed (by the reader's threads) while the device ingests the current one
+    ReadBatch batch[2];
+    auto fetch = [&](int slot) -> size_t {
+        batch[slot].clear();
+        return parser->io().read_batch(feed_bases(), batch[slot]);
+    };
+    int cur = 0;
+    size_t got = fetch(cur);
+    while (got) {
+        std::future<size_t> next = std::async(std::launch::async, fetch, cur ^ 1);
         uint64_t n = 0;
-        check(kmgpu_consume_reads(store->handle(), seqs.data(), offs.data(), got, KMGPU_CLEAN, band ? &b : nullptr, mask ? &m : nullptr, &n));
+        int rc = kmgpu_consume_reads(store->handle(), batch[cur].seqs, batch[cur].offsets.data(), got, KMGPU_CLEAN, band ? &b : nullptr,
+                                     mask ? &m : nullptr, &n);
         __sync_add_and_fetch(&n_consumed, n);
         __sync_add_and_fetch(&total_reads, (unsigned int)got);
+        size_t got_next = 0;
+        try {
+            got_next = next.get();
+        } catch (...) {
+            check(rc);
+            throw;
+        }
+        check(rc);
+        got = got_next;
+        cur ^= 1;
     }
 }
 
@@ -897,15 +912,13 @@ uint64_t* Hashtable::abundance_distribution(ReadParserPtr<SeqIO>& parser, Hashta
 {
     uint64_t* dist = new uint64_t[MAX_BIGCOUNT + 1];
     for (uint64_t i = 0; i <= MAX_BIGCOUNT; i++) dist[i] = 0;
-    std::string seqs;
-    std::vector<uint64_t> offs;
+    ReadBatch batch;
     try {
         while (true) {
-            seqs.clear();
-            offs.clear();
-            size_t got = parser->io().read_batch(feed_bases(), seqs, offs);
+            batch.clear();
+            size_t got = parser->io().read_batch(feed_bases(), batch);
             if (got == 0) break;
-            check(kmgpu_abundance_distribution(store->handle(), tracking->store->handle(), seqs.data(), offs.data(), got, KMGPU_CLEAN, dist));
+            check(kmgpu_abundance_distribution(store->handle(), tracking->store->handle(), batch.seqs, batch.offsets.data(), got, KMGPU_CLEAN, dist));
         }
     } catch (...) {
         delete[] dist;

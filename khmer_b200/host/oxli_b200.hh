@@ -95,6 +95,27 @@ struct Read {
 };
 typedef std::pair<Read, Read> ReadPair;
 
+// A batch of raw (uncleaned) reads, concatenated, for the device feed.  The sequence buffer is page-locked host
+// memory obtained through the C ABI (kmgpu_alloc_pinned) so that uploads are asynchronous and run at PCIe speed;
+// it is reused from batch to batch.
+struct ReadBatch {
+    char* seqs = nullptr;
+    size_t n_bases = 0, cap = 0;
+    std::vector<uint64_t> offsets;   // n_reads + 1 entries once filled
+    bool pinned = false;
+    ReadBatch() {}
+    ~ReadBatch();
+    ReadBatch(const ReadBatch&) = delete;
+    ReadBatch& operator=(const ReadBatch&) = delete;
+    void clear()
+    {
+        n_bases = 0;
+        offsets.clear();
+    }
+    void reserve(size_t n);          // keeps the first n_bases bytes
+    size_t n_reads() const { return offsets.empty() ? 0 : offsets.size() - 1; }
+};
+
 // FASTA / FASTQ reader for plain, gzip and bzip2 files.  Thread-safe like the reference's (one lock around
 // the stream); additionally hands out whole batches of reads so that the device feed does not pay a lock per read.
 class FastxReader {
@@ -106,8 +127,9 @@ public:
     size_t get_num_reads();
     void close();
     // append reads until at least max_bases bases are buffered or the stream ends; raw (uncleaned) sequences,
-    // concatenated, offsets has one more entry than reads.  Returns the number of reads appended.
-    size_t read_batch(uint64_t max_bases, std::string& seqs, std::vector<uint64_t>& offsets);
+    // concatenated, offsets has one more entry than reads.  Returns the number of reads appended.  Plain files are
+    // memory-mapped and a batch is parsed by several threads (KMGPU_PARSE_THREADS).
+    size_t read_batch(uint64_t max_bases, ReadBatch& out);
 
 private:
     struct Impl;

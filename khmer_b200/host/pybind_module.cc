@@ -161,6 +161,18 @@ PYBIND11_MODULE(_oxli, m)
         .def_property_readonly("num_reads", [](PyParser& p) { return p.parser->get_num_reads(); })
         .def("is_complete", [](PyParser& p) { return p.parser->is_complete(); })
         .def("close", [](PyParser& p) { p.parser->close(); })
+        .def("read_batch", [](PyParser& p, uint64_t max_bases) {
+            // the device feed's view of the file: raw sequences of the next batch (several parser threads on plain files)
+            ReadBatch b;
+            size_t n;
+            {
+                py::gil_scoped_release nogil;
+                n = p.parser->io().read_batch(max_bases, b);
+            }
+            py::list out;
+            for (size_t i = 0; i < n; i++) out.append(py::bytes(b.seqs + b.offsets[i], b.offsets[i + 1] - b.offsets[i]));
+            return out;
+        }, py::arg("max_bases") = (uint64_t)(64u << 20))
         .def("__iter__", [](py::object self) { return self; })
         .def("__next__", [](PyParser& p) {
             try {

@@ -4,7 +4,13 @@
 // Plain and gzip input go through zlib's gz* API (it reads uncompressed files transparently); bzip2 input
 // through libbz2 loaded at run time.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <thread>
 
 #include <algorithm>
 #include <cstdio>
@@ -12,6 +18,7 @@
 #include <mutex>
 
 #include "oxli_b200.hh"
+#include "../../include/kmgpu.h"
 
 namespace oxli_b200 {
 namespace read_parsers {
@@ -40,6 +47,32 @@ void Read::set_clean_seq()
             c = 'A';
         }
     }
+}
+
+ReadBatch::~ReadBatch()
+{
+    if (seqs) {
+        if (pinned) kmgpu_free_pinned(seqs);
+        else free(seqs);
+    }
+}
+
+void ReadBatch::reserve(size_t n)
+{
+    if (n <= cap) return;
+    size_t want = std::max(n, cap + cap / 2);
+    void* np = nullptr;
+    bool np_pinned = kmgpu_alloc_pinned(want, &np) == 0 && np;   // no device: plain memory still parses
+    if (!np_pinned) np = malloc(want);
+    if (!np) throw std::bad_alloc();
+    if (n_bases) memcpy(np, seqs, n_bases);
+    if (seqs) {
+        if (pinned) kmgpu_free_pinned(seqs);
+        else free(seqs);
+    }
+    seqs = (char*)np;
+    cap = want;
+    pinned = np_pinned;
 }
 
 namespace {
@@ -73,13 +106,36 @@ Bz2& bz2()
 
 }  // namespace
 
+namespace {
+struct Seg {            // a piece of sequence inside the mapping
+    const char* p;
+    uint32_t n;
+    uint32_t last;       // 1: this piece ends a record
+};
+
+struct Slice {
+    const char* a;
+    const char* b;
+    std::vector<Seg> segs;
+    size_t bytes = 0, reads = 0;
+    bool ok = true;
+};
+
+}  // namespace
+
 struct FastxReader::Impl {
+    std::vector<Slice> slices;   // per-thread scratch of the parallel batch parser, reused
     std::string filename;
     gzFile gz = nullptr;
     void* bz = nullptr;
     std::vector<char> buf;
+    char* base = nullptr;      // parse window: buf.data() for compressed input, the mapping for plain files
     size_t pos = 0, end = 0;
     bool eof = false;
+    // plain files are memory-mapped: no copy, and whole batches can be parsed by several threads
+    void* map = nullptr;
+    size_t map_len = 0;
+    char kind = 0;             // '>' or '@' (first record marker), for the parallel path
     bool read_error = false;
     size_t num_reads = 0;
     bool have_qualities = false;
@@ -96,6 +152,7 @@ struct FastxReader::Impl {
         end -= pos;
         pos = 0;
         if (buf.size() - end < (1u << 16)) buf.resize(buf.size() * 2);
+        base = buf.data();
         int want = (int)std::min<size_t>(buf.size() - end, 1u << 30);
         int got;
         if (bz) {
@@ -124,9 +181,9 @@ struct FastxReader::Impl {
     bool get_line(const char*& s, size_t& n)
     {
         while (true) {
-            char* nl = (char*)memchr(buf.data() + pos, '\n', end - pos);
+            char* nl = (char*)memchr(base + pos, '\n', end - pos);
             if (nl) {
-                s = buf.data() + pos;
+                s = base + pos;
                 n = (size_t)(nl - s);
                 pos += n + 1;
                 if (n && s[n - 1] == '\r') n--;
@@ -134,7 +191,7 @@ struct FastxReader::Impl {
             }
             if (!fill()) {
                 if (pos < end) {  // last line without newline
-                    s = buf.data() + pos;
+                    s = base + pos;
                     n = end - pos;
                     pos = end;
                     if (n && s[n - 1] == '\r') n--;
@@ -149,7 +206,7 @@ struct FastxReader::Impl {
     {
         while (pos >= end)
             if (!fill()) return -1;
-        return (unsigned char)buf[pos];
+        return (unsigned char)base[pos];
     }
 
     void skip_blank()
@@ -226,10 +283,38 @@ FastxReader::FastxReader(const std::string& filename) : _impl(new Impl())
         if (!bz2().lib) throw InvalidStream("File " + filename + " is bzip2-compressed and libbz2 is not available.");
         m.bz = bz2().open(filename.c_str(), "rb");
         if (!m.bz) throw InvalidStream(bad);
-    } else {
+    } else if (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         m.gz = gzopen(filename.c_str(), "rb");
         if (!m.gz) throw InvalidStream(bad);
         gzbuffer(m.gz, 1u << 20);
+    } else {
+        // plain file: map it; the serial routines parse straight out of the mapping (no refills), and
+        // read_batch can hand slices of it to several threads
+        int fd = open(filename.c_str(), O_RDONLY);
+        if (fd < 0) throw InvalidStream(bad);
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+            ::close(fd);
+            m.gz = gzopen(filename.c_str(), "rb");   // pipes and the like: stream through zlib's transparent mode
+            if (!m.gz) throw InvalidStream(bad);
+        } else {
+            m.map_len = (size_t)sb.st_size;
+            if (m.map_len) {
+                m.map = mmap(nullptr, m.map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+                ::close(fd);
+                if (m.map == MAP_FAILED) {
+                    m.map = nullptr;
+                    throw InvalidStream(bad);
+                }
+                madvise(m.map, m.map_len, MADV_SEQUENTIAL);
+            } else {
+                ::close(fd);
+            }
+            m.base = (char*)m.map;
+            m.pos = 0;
+            m.end = m.map_len;
+            m.eof = true;   // nothing to refill
+        }
     }
     // same two checks as FastxReader::_init (read_parsers.cc:259-274)
     if (m.at_end()) {
@@ -238,6 +323,7 @@ FastxReader::FastxReader(const std::string& filename) : _impl(new Impl())
     }
     int c = m.peek();
     if (c != '>' && c != '@') throw InvalidStream(bad);
+    m.kind = (char)c;
 }
 
 FastxReader::~FastxReader() { close(); }
@@ -249,6 +335,9 @@ void FastxReader::close()
     if (m.bz) bz2().close(m.bz);
     m.gz = nullptr;
     m.bz = nullptr;
+    if (m.map) munmap(m.map, m.map_len);
+    m.map = nullptr;
+    m.base = m.buf.data();
     m.eof = true;
     m.pos = m.end = 0;
 }
@@ -290,7 +379,106 @@ Read FastxReader::get_next_read()
     return read;
 }
 
-size_t FastxReader::read_batch(uint64_t max_bases, std::string& seqs, std::vector<uint64_t>& offsets)
+namespace {
+
+unsigned parse_threads()
+{
+    static unsigned n = [] {
+        const char* e = getenv("KMGPU_PARSE_THREADS");
+        unsigned v = e && *e ? (unsigned)atoi(e) : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        return std::max(1u, std::min(v, 64u));
+    }();
+    return n;
+}
+
+// first record start at or after p in [p, e): a line beginning with `kind`; for FASTQ the line two below must begin
+// with '+' (a quality line may begin with '@', but then the line two below it is a sequence line)
+const char* find_record(const char* b, const char* p, const char* e, char kind)
+{
+    while (p < e) {
+        if (p != b) {   // move to the next line start unless we are at the very beginning of the data
+            const char* nl = (const char*)memchr(p - 1, '\n', (size_t)(e - p + 1));
+            if (!nl) return e;
+            p = nl + 1;
+            if (p >= e) return e;
+        }
+        if (*p == kind) {
+            if (kind == '>') return p;
+            const char* l2 = (const char*)memchr(p, '\n', (size_t)(e - p));
+            const char* l3 = l2 ? (const char*)memchr(l2 + 1, '\n', (size_t)(e - l2 - 1)) : nullptr;
+            if (!l3 || l3 + 1 >= e) return p;   // too close to the end to check: the caller only cuts far from it
+            if (l3[1] == '+') return p;
+        }
+        p++;
+    }
+    return e;
+}
+
+// all records of [a, b) (a is a record start, b the next slice's record start or the end of the data); sequences are
+// only located here, the copy into the batch happens once every slice's size is known
+void parse_slice(Slice& s, char kind)
+{
+    const char* p = s.a;
+    const char* e = s.b;
+    s.segs.clear();
+    s.bytes = s.reads = 0;
+    s.ok = true;
+    while (p < e) {
+        while (p < e && (*p == '\n' || *p == '\r')) p++;
+        if (p >= e) break;
+        if (*p != kind) { s.ok = false; return; }
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        if (!nl) { s.ok = false; return; }   // header without a sequence
+        p = nl + 1;
+        size_t len = 0;
+        if (kind == '>') {
+            size_t first = s.segs.size();
+            while (p < e && *p != '>') {
+                nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+                const char* le = nl ? nl : e;
+                size_t n = (size_t)(le - p);
+                if (n && p[n - 1] == '\r') n--;
+                if (n) {
+                    if (n > 0xFFFFFFFFull) { s.ok = false; return; }
+                    s.segs.push_back(Seg{p, (uint32_t)n, 0});
+                    len += n;
+                }
+                p = nl ? nl + 1 : e;
+            }
+            if (len == 0 || s.segs.size() == first) { s.ok = false; return; }
+            s.segs.back().last = 1;
+        } else {
+            // four-line FASTQ only; anything else is left to the serial parser
+            nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) { s.ok = false; return; }
+            size_t n = (size_t)(nl - p);
+            if (n && p[n - 1] == '\r') n--;
+            const char* sp = p;
+            p = nl + 1;
+            if (p >= e || *p != '+') { s.ok = false; return; }
+            nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) { s.ok = false; return; }
+            p = nl + 1;
+            nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+            const char* le = nl ? nl : e;
+            size_t q = (size_t)(le - p);
+            if (q && p[q - 1] == '\r') q--;
+            if (q != n || n == 0 || n > 0xFFFFFFFFull) { s.ok = false; return; }
+            p = nl ? nl + 1 : e;
+            s.segs.push_back(Seg{sp, (uint32_t)n, 1});
+            len = n;
+        }
+        s.bytes += len;
+        s.reads++;
+    }
+}
+
+}  // namespace
+
+// plain (memory-mapped) files: cut the next window of the mapping into slices at record boundaries and parse them
+// concurrently.  Any irregularity (empty sequence, quality length mismatch, multi-line FASTQ, stray bytes) makes the
+// whole window fall back to the serial parser, which then reports it exactly as the reference would.
+size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
 {
     Impl& m = *_impl;
     std::lock_guard<std::mutex> g(m.mu);
@@ -301,11 +489,79 @@ size_t FastxReader::read_batch(uint64_t max_bases, std::string& seqs, std::vecto
         if (k == 1) throw InvalidRead(msg);
         throw StreamReadError();
     }
-    if (offsets.empty()) offsets.push_back(seqs.size());
+    if (out.offsets.empty()) out.offsets.push_back(out.n_bases);
+    static const size_t par_min = [] {
+        const char* e = getenv("KMGPU_PARSE_MIN_BYTES");
+        return e && *e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(4u << 20);
+    }();
+    if (m.map && parse_threads() > 1 && m.end - m.pos > par_min) {
+        const unsigned T = parse_threads();
+        // window: enough bytes for ~max_bases bases (FASTQ spends about half its bytes on qualities)
+        uint64_t want = m.kind == '@' ? max_bases * 2 + max_bases / 4 : max_bases + max_bases / 8;
+        const char* b = m.base;
+        const char* w0 = b + m.pos;
+        const char* fe = b + m.end;
+        const char* w1 = (uint64_t)(fe - w0) <= want + (1u << 20) ? fe : find_record(b, w0 + want, fe, m.kind);
+        std::vector<Slice>& sl = m.slices;
+        sl.resize(T);
+        std::vector<const char*> cut(T + 1);
+        cut[0] = w0;
+        cut[T] = w1;
+        for (unsigned t = 1; t < T; t++) cut[t] = find_record(b, w0 + (uint64_t)(w1 - w0) * t / T, w1, m.kind);
+        for (unsigned t = 1; t <= T; t++)
+            if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) {
+            sl[t].a = cut[t];
+            sl[t].b = cut[t + 1];
+            th.emplace_back(parse_slice, std::ref(sl[t]), m.kind);
+        }
+        for (auto& x : th) x.join();
+        bool ok = true;
+        size_t total = 0, nreads = 0;
+        for (auto& x : sl) {
+            ok = ok && x.ok;
+            total += x.bytes;
+            nreads += x.reads;
+        }
+        if (ok && nreads) {
+            if (m.num_reads == 0 && m.kind == '@') m.have_qualities = true;
+            const size_t base0 = out.n_bases;
+            out.reserve(base0 + total);
+            const size_t o0 = out.offsets.size();
+            out.offsets.resize(o0 + nreads);
+            std::vector<size_t> sb(T), rb(T);
+            size_t accb = base0, accr = o0;
+            for (unsigned t = 0; t < T; t++) {
+                sb[t] = accb;
+                rb[t] = accr;
+                accb += sl[t].bytes;
+                accr += sl[t].reads;
+            }
+            char* dst = out.seqs;
+            uint64_t* offp = out.offsets.data();
+            th.clear();
+            for (unsigned t = 0; t < T; t++)
+                th.emplace_back([&, t]() {
+                    size_t o = sb[t], r = rb[t];
+                    for (const Seg& sg : sl[t].segs) {
+                        memcpy(dst + o, sg.p, sg.n);
+                        o += sg.n;
+                        if (sg.last) offp[r++] = o;
+                    }
+                });
+            for (auto& x : th) x.join();
+            out.n_bases = base0 + total;
+            m.pos = (size_t)(w1 - b);
+            m.num_reads += nreads;
+            return nreads;
+        }
+        // fall through: the serial parser handles this window
+    }
     size_t n = 0;
     std::string name, seq, qual;
-    const uint64_t start = seqs.size();
-    while (seqs.size() - start < max_bases) {
+    const uint64_t start = out.n_bases;
+    while (out.n_bases - start < max_bases) {
         int rc = m.next_record(name, seq, qual);
         const char* err = nullptr;
         int kind = 0;
@@ -329,8 +585,10 @@ size_t FastxReader::read_batch(uint64_t max_bases, std::string& seqs, std::vecto
             break;
         }
         m.num_reads++;
-        seqs += seq;
-        offsets.push_back(seqs.size());
+        out.reserve(out.n_bases + seq.size());
+        memcpy(out.seqs + out.n_bases, seq.data(), seq.size());
+        out.n_bases += seq.size();
+        out.offsets.push_back(out.n_bases);
         n++;
     }
     return n;

@@ -96,3 +96,73 @@ def test_api_surface():
         for m in want:
             assert hasattr(getattr(ox, cls), m), (cls, m)
     assert hasattr(ox.Nodegraph, "update")
+
+
+def test_parallel_batch_parser_equals_serial(tmp_path, datadir):
+    """read_batch on plain files cuts the mapping at record boundaries and parses slices concurrently; the result
+    must be the serial parser's, record for record (subprocesses: thread count and threshold are read once)."""
+    import subprocess
+    import sys
+    import numpy as np
+    rng = np.random.default_rng(3)
+    fa = tmp_path / "multi.fa"
+    with open(fa, "w") as fh:
+        for i in range(3000):
+            n = int(rng.integers(1, 400))
+            s = "".join("ACGTNacgt"[j] for j in rng.integers(0, 9, n))
+            fh.write(">r%d some description\n" % i)
+            for o in range(0, n, 70):                       # multi-line records, some blank lines, a CRLF here and there
+                fh.write(s[o:o + 70] + ("\r\n" if i % 97 == 0 else "\n"))
+            if i % 50 == 0:
+                fh.write("\n")
+    fq = tmp_path / "reads.fq"
+    with open(fq, "w") as fh:
+        for i in range(4000):
+            n = int(rng.integers(1, 200))
+            s = "".join("ACGTN"[j] for j in rng.integers(0, 5, n))
+            q = "".join(chr(int(c)) for c in rng.integers(33, 74, n))
+            if i % 7 == 0:
+                q = "@" + q[1:]                              # quality lines starting with '@' must not fool the cutter
+            fh.write("@read%d\n%s\n+\n%s\n" % (i, s, q))
+    code = ("import sys; sys.path.insert(0, %r); import khmer_b200 as kh, hashlib\n"
+            "p = kh.ReadParser(sys.argv[1]); out = []\n"
+            "while True:\n"
+            "    b = p.read_batch(int(sys.argv[2]))\n"
+            "    if not b: break\n"
+            "    out += b\n"
+            "print(len(out), p.num_reads, hashlib.md5(b'\\n'.join(out)).hexdigest())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in (str(fa), str(fq), os.path.join(datadir, "synth-2k-150.fa"), os.path.join(datadir, "random-20-a.fq")):
+        outs = set()
+        for threads, batch in (("1", "100000000"), ("4", "100000000"), ("7", "20000"), ("3", "5000")):
+            env = dict(os.environ, KMGPU_PARSE_THREADS=threads, KMGPU_PARSE_MIN_BYTES="1000")
+            r = subprocess.run([sys.executable, "-c", code, path, batch], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.add(r.stdout.strip())
+        assert len(outs) == 1, (path, outs)
+        want = [r.sequence for r in kh.ReadParser(path)]
+        n, nr, digest = next(iter(outs)).split()
+        assert int(n) == len(want) == int(nr)
+        assert digest == hashlib.md5("\n".join(want).encode()).hexdigest()
+
+
+def test_parallel_batch_parser_falls_back_on_irregular_input(tmp_path):
+    import subprocess
+    import sys
+    bad = tmp_path / "bad.fa"
+    with open(bad, "w") as fh:
+        for i in range(2000):
+            fh.write(">r%d\nACGTACGTAC\n" % i)
+        fh.write(">empty\n>after\nACGT\n")
+    code = ("import sys; sys.path.insert(0, %r); import khmer_b200 as kh\n"
+            "p = kh.ReadParser(sys.argv[1]); n = 0\n"
+            "try:\n"
+            "    while True:\n"
+            "        b = p.read_batch(1000000)\n"
+            "        if not b: break\n"
+            "        n += len(b)\n"
+            "except ValueError as e:\n"
+            "    print('ValueError', n, e)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KMGPU_PARSE_THREADS="4", KMGPU_PARSE_MIN_BYTES="1000")
+    r = subprocess.run([sys.executable, "-c", code, str(bad)], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip() == "ValueError 2000 Sequence is empty"      # the good reads first, then the reference's error
