@@ -853,16 +853,17 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
     unsigned n_new = 0, n_sat = 0, n_cross = 0, n_ent = 0;
     uint64_t ent[8];
     if (g * 8u < span) {
-        uint4 d4 = *reinterpret_cast<const uint4*>(delta + (size_t)g * 8);
+        // both loads are issued before either is looked at (the table slice streams from HBM, the lanes from L2)
+        const uint32_t b0 = lo + g * 8u;
+        uint4 d4 = __ldcg(reinterpret_cast<const uint4*>(delta + (size_t)g * 8));
+        uint64_t old64 = 0;
+        uint32_t old32 = 0;
+        if (KIND == BYTE) old64 = __ldcs(reinterpret_cast<const unsigned long long*>(table + b0));
+        else old32 = __ldcs(reinterpret_cast<const uint32_t*>(table + (b0 >> 1)));
         if (d4.x | d4.y | d4.z | d4.w) {
             *reinterpret_cast<uint4*>(delta + (size_t)g * 8) = make_uint4(0, 0, 0, 0);
             const uint32_t dw[4] = {d4.x, d4.y, d4.z, d4.w};
             constexpr uint32_t CAP = KIND == BYTE ? 255u : 15u;
-            const uint32_t b0 = lo + g * 8u;
-            uint64_t old64 = 0;
-            uint32_t old32 = 0;
-            if (KIND == BYTE) old64 = *reinterpret_cast<const uint64_t*>(table + b0);
-            else old32 = *reinterpret_cast<const uint32_t*>(table + (b0 >> 1));
             uint64_t new64 = old64;
             uint32_t new32 = old32;
 #pragma unroll
@@ -971,22 +972,6 @@ __global__ void k_list_register(const uint64_t* __restrict__ binlist, uint64_t n
             int t = (int)(key & 255u);
             atomicOr(&filter[t * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)], 1u << (bin & 31));
         }
-    }
-}
-
-// 4b. first-toucher stamps straight from the stored bins (no re-hash)
-__global__ void __launch_bounds__(256)
-k_replay_bins(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables, uint32_t n_pos, const uint64_t* __restrict__ keys,
-              uint32_t* __restrict__ stamps, uint64_t mask, const uint32_t* __restrict__ filter)
-{
-    uint32_t p = blockIdx.x * 256u + threadIdx.x;
-    if (p >= n_pos) return;
-    for (int i = 0; i < n_tables; i++) {
-        uint32_t bin = __ldcs(&bins[i * stride + p]);
-        if (bin == BIN_NONE) return;
-        if (filter && !((__ldg(&filter[i * FILTER_WORDS + ((bin & (FILTER_BITS - 1)) >> 5)]) >> (bin & 31)) & 1u)) continue;
-        uint64_t s = ht_find(keys, mask, ht_key(bin, i));
-        if (s != ~0ull) atomicMin(&stamps[s], p);
     }
 }
 
