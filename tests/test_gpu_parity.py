@@ -111,6 +111,8 @@ def _random_body(cls):
         for part in range(3):
             reads = synth_reads(1000 * trial + part, 400, int(rng.integers(k, 300)), 3000, err=0.02, with_n=True)
             reads += ["", "A", "ACGT" * 70, "N" * 50, "acgtn" * 30]
+            # a read far longer than the small device chunks of the subprocess variants: it continues across chunks
+            reads.insert(7, "".join("ACGT"[i] for i in rng.integers(0, 4, 21000)))
             assert g.consume_reads(reads, clean=True) == o.consume_reads(reads, clean=True)
             _same_state(g, o, nt)
         probe = synth_reads(7, 50, 120, 3000)
@@ -123,6 +125,16 @@ def _random_body(cls):
         if kind == ol.BYTE:
             gk, gv = g.bigcounts()
             assert dict(zip(gk.tolist(), gv.tolist())) == o.bigcounts()
+
+
+def test_offsets_need_not_start_at_zero():
+    """reads are seqs[offsets[r] .. offsets[r+1]): a window into a larger buffer works as is."""
+    from khmer_b200 import cabi
+    reads = synth_reads(77, 300, 90, 2000)
+    buf, off = cabi.as_reads(reads)
+    g, o = make_gpu("Countgraph", 19, [7919, 7927]), ol.Oracle("Countgraph", 19, [7919, 7927])
+    assert g.consume_reads((buf, off[100:201])) == o.consume_reads(reads[100:200])
+    _same_state(g, o, 2)
 
 
 def test_raw_mode_twobit_matches_consume_string():
