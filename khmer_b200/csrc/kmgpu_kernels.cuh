@@ -1098,15 +1098,19 @@ k_pk_replay_all(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables
     if (p >= n_pos) return;
     uint32_t b[F_MAXT];
     bool act[F_MAXT];
-    // bins of all tables, then all filter words, then all first probes: three rounds of independent loads
-    for (int t = 0; t < n_tables; t++) b[t] = __ldcs(&bins[t * stride + p]);
+    // bins of all tables, then all filter words, then all first probes: three rounds of independent loads.  The loops
+    // run over the compile-time bound with a guard so that the small arrays live in registers.
+#pragma unroll
+    for (int t = 0; t < F_MAXT; t++) b[t] = t < n_tables ? __ldcs(&bins[t * stride + p]) : BIN_NONE;
     if (b[0] == BIN_NONE) return;
     const uint32_t fmask = L.filter_bits - 1, fwords = L.filter_bits >> 5;
-    for (int t = 0; t < n_tables; t++) {
-        act[t] = L.mask[t] != 0;
+#pragma unroll
+    for (int t = 0; t < F_MAXT; t++) {
+        act[t] = t < n_tables && L.mask[t] != 0;
         if (act[t] && L.use_filter) act[t] = (__ldg(&filter[t * fwords + ((b[t] & fmask) >> 5)]) >> (b[t] & 31)) & 1u;
     }
-    for (int t = 0; t < n_tables; t++) {
+#pragma unroll
+    for (int t = 0; t < F_MAXT; t++) {
         if (!act[t]) continue;
         unsigned long long* tb = slots + L.base[t];
         uint64_t s = pk_slot0(b[t], L.mask[t]);
@@ -1201,18 +1205,22 @@ k_bigscan(int n_tables, HashCfg H, Input in, const uint32_t* __restrict__ bins, 
     const uint32_t p = blockIdx.x * 256u + threadIdx.x;
     if (p >= in.n_pos) return;
     uint32_t b[F_MAXT];
-    for (int i = 0; i < n_tables; i++) b[i] = __ldcs(&bins[i * stride + p]);
+#pragma unroll
+    for (int i = 0; i < F_MAXT; i++) b[i] = i < n_tables ? __ldcs(&bins[i * stride + p]) : BIN_NONE;
     if (b[0] == BIN_NONE) return;
     uint32_t satmask = 0;
-    for (int i = 0; i < n_tables; i++) {
+#pragma unroll
+    for (int i = 0; i < F_MAXT; i++) {
+        if (i >= n_tables) continue;
         uint32_t bit = (__ldg(&sat.t[i][b[i] >> 3]) >> (b[i] & 7)) & 1u;
         satmask |= bit << i;
-        if (!bit && !have_cross) return;   // a byte below 255 and no crossing bins to report: not a candidate
     }
+    if (!have_cross && satmask != (1u << n_tables) - 1u) return;   // a byte below 255 and no crossing bins to report
     uint32_t cross = 0;
     if (have_cross) {
-        for (int i = 0; i < n_tables; i++)
-            if ((satmask >> i & 1u) && ht_find(keys, mask, ht_key(b[i], i)) != ~0ull) cross |= 1u << i;
+#pragma unroll
+        for (int i = 0; i < F_MAXT; i++)
+            if (i < n_tables && (satmask >> i & 1u) && ht_find(keys, mask, ht_key(b[i], i)) != ~0ull) cross |= 1u << i;
     }
     const uint32_t allsat = satmask == (1u << n_tables) - 1u;
     if (!cross && !allsat) return;
