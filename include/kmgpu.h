@@ -200,6 +200,33 @@ int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
  * reduce-scatter / all-gather above (pure arithmetic, no device needed) */
 int kmgpu_slice_range(uint64_t n_words, int world, int rank, uint64_t* w0, uint64_t* w1);
 
+/* ---- multi-GPU, address-sharded sketches ---------------------------------
+ * For tables too large to replicate: bins [r*S_i, (r+1)*S_i) of table i live on rank r (S_i = slice length).
+ * Every rank hashes its own reads, then routes each counter update to the owner of its bin by writing the
+ * (slice-relative) bin straight into a receive queue in the owner's HBM over NVLink peer memory — the k-mer
+ * all-to-all — and every owner applies what it received to its slices with the same delta + fold kernels as
+ * the single-GPU path.  Collective protocol per batch of reads (the caller provides the barriers):
+ *     kmgpu_shard_route (all ranks)  ->  barrier  ->  kmgpu_shard_apply (all ranks)  ->  barrier
+ * Table bytes and n_occupied are exact (the sum of the ranks' slices / counters equals the single sketch);
+ * n_unique_kmers and bigcount need an order across ranks and are not maintained in this mode.
+ * The saved table is the concatenation of the ranks' slices in rank order (kmgpu_shard_slice + the local
+ * sketch's kmgpu_download_table). */
+typedef struct kmgpu_shard kmgpu_shard_t;
+int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables, const uint64_t* full_sizes, int device,
+                       int rank, int world, uint64_t max_positions_per_route, kmgpu_shard_t** out);
+int kmgpu_shard_destroy(kmgpu_shard_t* s);
+/* the local sketch holding this rank's slices (stats, downloads, merges work on it as on any sketch) */
+kmgpu_t* kmgpu_shard_local(kmgpu_shard_t* s);
+int kmgpu_shard_slice(kmgpu_shard_t* s, int table, uint64_t* lo, uint64_t* hi);
+/* peers: CUDA-IPC handles of the receive queues ((n_tables + 1) * 64 bytes per rank), or direct pointers when
+ * all ranks live in one process */
+int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles);
+int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all_handles);
+int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n);
+int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                      uint64_t* n_kmers_out);
+int kmgpu_shard_apply(kmgpu_shard_t* s);
+
 /* ---- measurement -----------------------------------------------------------------------
  * Device time (ms) and launch count of the ingest kernel accumulated since the last reset, measured
  * with CUDA events on the handle's own stream. */

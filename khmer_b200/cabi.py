@@ -34,6 +34,8 @@ SYMBOLS = [
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
     "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
     "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
+    "kmgpu_shard_create", "kmgpu_shard_destroy", "kmgpu_shard_local", "kmgpu_shard_slice", "kmgpu_shard_ipc_export",
+    "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_apply",
 ]
 
 
@@ -113,6 +115,17 @@ def lib():
         L.kmgpu_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.kmgpu_device_count.argtypes = [C.POINTER(C.c_int)]
         L.kmgpu_slice_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+        L.kmgpu_shard_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, u64p, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                         C.POINTER(C.c_void_p)]
+        L.kmgpu_shard_destroy.argtypes = [C.c_void_p]
+        L.kmgpu_shard_local.restype = C.c_void_p
+        L.kmgpu_shard_local.argtypes = [C.c_void_p]
+        L.kmgpu_shard_slice.argtypes = [C.c_void_p, C.c_int, u64p, u64p]
+        L.kmgpu_shard_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.kmgpu_shard_ipc_attach.argtypes = [C.c_void_p, C.c_void_p]
+        L.kmgpu_shard_attach_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.kmgpu_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]
+        L.kmgpu_shard_apply.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -388,6 +401,78 @@ class Sketch:
         ms = C.c_double()
         check(lib().kmgpu_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+
+class Shard:
+    """One rank's part of an address-sharded sketch (kmgpu_shard_*)."""
+
+    def __init__(self, storage, hashkind, ksize, full_sizes, rank, world, device=0, max_positions=8 << 20):
+        self.full_sizes = [int(x) for x in full_sizes]
+        arr = (C.c_uint64 * len(self.full_sizes))(*self.full_sizes)
+        self.h = C.c_void_p()
+        self.storage, self.rank, self.world, self.max_positions = storage, rank, world, max_positions
+        check(lib().kmgpu_shard_create(storage, hashkind, ksize, len(self.full_sizes), arr, device, rank, world, max_positions,
+                                       C.byref(self.h)))
+        # the local sketch is owned by the shard: wrap it without taking ownership
+        self.local = Sketch.__new__(Sketch)
+        self.local.h = C.c_void_p(lib().kmgpu_shard_local(self.h))
+        self.local.sizes = [max(hi - lo, 1) for lo, hi in (self.slice(i) for i in range(len(self.full_sizes)))]
+        self.local.storage, self.local.hashkind, self.local.ksize = storage, hashkind, ksize
+        self.local.close = lambda: None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.local.h = None
+            lib().kmgpu_shard_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def slice(self, table):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        check(lib().kmgpu_shard_slice(self.h, table, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def ipc_export(self):
+        out = np.zeros(64 * (len(self.full_sizes) + 1), dtype=np.uint8)
+        check(lib().kmgpu_shard_ipc_export(self.h, _ptr(out)))
+        return out
+
+    def ipc_attach(self, all_handles):
+        all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        check(lib().kmgpu_shard_ipc_attach(self.h, _ptr(all_handles)))
+
+    def route(self, reads, clean=True):
+        buf, off = as_reads(reads)
+        n = C.c_uint64()
+        check(lib().kmgpu_shard_route(self.h, _ptr(buf), _ptr(off), len(off) - 1, CLEAN if clean else 0, C.byref(n)))
+        return n.value
+
+    def apply(self):
+        check(lib().kmgpu_shard_apply(self.h))
+
+    def slice_bytes(self, table):
+        """This rank's part of the table image: concatenating the parts of all ranks in rank order gives the
+        table a single sketch would hold (slices start on a byte boundary of every storage kind)."""
+        lo, hi = self.slice(table)
+        if hi <= lo:
+            return np.zeros(0, dtype=np.uint8)
+        t = self.local.table(table)
+        last = hi == self.full_sizes[table]
+        if self.storage == BYTE:
+            return t[: hi - lo]
+        if self.storage == NIBBLE:
+            return t if last else t[: (hi - lo) // 2]
+        return t if last else t[: (hi - lo) // 8]
+
+
+def attach_local_shards(shards):
+    arr = (C.c_void_p * len(shards))(*[s.h for s in shards])
+    check(lib().kmgpu_shard_attach_local(arr, len(shards)))
 
 
 def slice_range(n_words, world, rank):

@@ -2070,3 +2070,257 @@ extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
     }
     return KMGPU_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU: address-sharded sketches (k-mer all-to-all over NVLink peer memory, see include/kmgpu.h)
+// ------------------------------------------------------------------------------------------------------
+struct kmgpu_shard {
+    kmgpu_sketch* local = nullptr;
+    int rank = 0, world = 1, nt = 0;
+    uint64_t full_sizes[MAX_TABLES];
+    uint64_t slice[MAX_TABLES];
+    SketchDev full;  // full-table sizes and magics: what the k-mers are hashed against
+    uint32_t* rq[MAX_TABLES];
+    unsigned long long* rcur = nullptr;
+    uint64_t qcap = 0, max_positions = 0;
+    struct PeerQ {
+        uint32_t* rq[MAX_TABLES];
+        unsigned long long* rcur;
+    } peers[8];
+    bool attached = false, ipc = false;
+};
+
+extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s);
+
+extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables, const uint64_t* full_sizes, int device, int rank, int world,
+                                  uint64_t max_positions, kmgpu_shard_t** out)
+{
+    if (!out) return fail(KMGPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
+    if (n_tables < 1 || n_tables > F_MAXT) return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported", n_tables);
+    if (max_positions == 0 || max_positions > chunk_bases()) max_positions = std::min<uint64_t>(chunk_bases(), 8ull << 20);
+    kmgpu_shard* s = new kmgpu_shard();
+    s->rank = rank;
+    s->world = world;
+    s->nt = n_tables;
+    s->max_positions = max_positions;
+    memset(&s->full, 0, sizeof s->full);
+    memset(s->rq, 0, sizeof s->rq);
+    memset(s->peers, 0, sizeof s->peers);
+    uint64_t local_sizes[MAX_TABLES];
+    for (int i = 0; i < n_tables; i++) {
+        if (full_sizes[i] == 0 || full_sizes[i] > 0xFFFFFFFEull - 128) {
+            delete s;
+            return fail(KMGPU_EUNSUPPORTED, "sharded tables are limited to 2^32 bins per table for now");
+        }
+        s->full_sizes[i] = full_sizes[i];
+        uint64_t per = (full_sizes[i] + world - 1) / world;
+        s->slice[i] = ((per + 127) / 128) * 128;  // slices start on a byte of every storage kind
+        uint64_t lo = std::min<uint64_t>(full_sizes[i], s->slice[i] * rank), hi = std::min<uint64_t>(full_sizes[i], s->slice[i] * (rank + 1));
+        local_sizes[i] = std::max<uint64_t>(hi - lo, 1);  // a rank past the end of a tiny table keeps a dummy bin
+        s->full.sizes[i] = full_sizes[i];
+        s->full.magic[i] = ~0ull / full_sizes[i];
+    }
+    s->full.n_tables = n_tables;
+    s->full.kind = storage;
+    int rc = kmgpu_create(storage, hash, ksize, n_tables, local_sizes, device, &s->local);
+    if (rc != KMGPU_OK) {
+        delete s;
+        return rc;
+    }
+    s->qcap = (uint64_t)world * max_positions;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n_tables && e == cudaSuccess; i++) e = cudaMalloc(&s->rq[i], s->qcap * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->rcur, MAX_TABLES * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(s->rcur, 0, MAX_TABLES * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        kmgpu_shard_destroy(s);
+        return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "shard queues: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s)
+{
+    if (!s) return KMGPU_OK;
+    if (s->local) cudaSetDevice(s->local->device);
+    if (s->ipc)
+        for (int q = 0; q < s->world; q++) {
+            if (q == s->rank) continue;
+            for (int i = 0; i < s->nt; i++)
+                if (s->peers[q].rq[i]) cudaIpcCloseMemHandle(s->peers[q].rq[i]);
+            if (s->peers[q].rcur) cudaIpcCloseMemHandle(s->peers[q].rcur);
+        }
+    for (int i = 0; i < s->nt; i++)
+        if (s->rq[i]) cudaFree(s->rq[i]);
+    if (s->rcur) cudaFree(s->rcur);
+    if (s->local) kmgpu_destroy(s->local);
+    delete s;
+    return KMGPU_OK;
+}
+
+extern "C" kmgpu_t* kmgpu_shard_local(kmgpu_shard_t* s) { return s ? s->local : nullptr; }
+
+extern "C" int kmgpu_shard_slice(kmgpu_shard_t* s, int table, uint64_t* lo, uint64_t* hi)
+{
+    if (!s || table < 0 || table >= s->nt) return fail(KMGPU_EINVAL, "bad table index");
+    if (lo) *lo = std::min<uint64_t>(s->full_sizes[table], s->slice[table] * s->rank);
+    if (hi) *hi = std::min<uint64_t>(s->full_sizes[table], s->slice[table] * (s->rank + 1));
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles)
+{
+    if (!s || !handles) return fail(KMGPU_EINVAL, "null argument");
+    CKR(set_device(s->local->device));
+    for (int i = 0; i <= s->nt; i++) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, i < s->nt ? (void*)s->rq[i] : (void*)s->rcur));
+        memcpy(handles + (size_t)i * KMGPU_IPC_HANDLE_BYTES, &mh, KMGPU_IPC_HANDLE_BYTES);
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all)
+{
+    if (!s || !all) return fail(KMGPU_EINVAL, "null argument");
+    CKR(set_device(s->local->device));
+    for (int q = 0; q < s->world; q++) {
+        for (int i = 0; i <= s->nt; i++) {
+            void* p = nullptr;
+            if (q == s->rank) {
+                p = i < s->nt ? (void*)s->rq[i] : (void*)s->rcur;
+            } else {
+                cudaIpcMemHandle_t mh;
+                memcpy(&mh, all + ((size_t)q * (s->nt + 1) + i) * KMGPU_IPC_HANDLE_BYTES, KMGPU_IPC_HANDLE_BYTES);
+                CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+            }
+            if (i < s->nt) s->peers[q].rq[i] = (uint32_t*)p;
+            else s->peers[q].rcur = (unsigned long long*)p;
+        }
+    }
+    s->attached = true;
+    s->ipc = true;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n)
+{
+    if (!all || n < 1 || n > 8) return fail(KMGPU_EINVAL, "bad shard list");
+    for (int a = 0; a < n; a++) {
+        if (!all[a] || all[a]->world != n || all[a]->rank != a) return fail(KMGPU_EINVAL, "shard %d is not rank %d of %d", a, a, n);
+        CKR(set_device(all[a]->local->device));
+        for (int b = 0; b < n; b++) {
+            if (all[b]->local->device != all[a]->local->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, all[a]->local->device, all[b]->local->device));
+                if (!can) return fail(KMGPU_EUNSUPPORTED, "devices %d and %d have no peer access", all[a]->local->device, all[b]->local->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(all[b]->local->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                cudaGetLastError();
+            }
+            for (int i = 0; i < all[a]->nt; i++) all[a]->peers[b].rq[i] = all[b]->rq[i];
+            all[a]->peers[b].rcur = all[b]->rcur;
+        }
+        all[a]->attached = true;
+        all[a]->ipc = false;
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                 uint64_t* n_kmers_out)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (!s->attached) return fail(KMGPU_EINVAL, "peers are not attached");
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    kmgpu_sketch* h = s->local;
+    const uint64_t first = offsets[0], last = offsets[n_reads];
+    if (last - first > s->max_positions)
+        return fail(KMGPU_EINVAL, "%llu bases in one route call; this shard was created for at most %llu", (unsigned long long)(last - first),
+                    (unsigned long long)s->max_positions);
+    if (last == first) return KMGPU_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    ChunkDev cd;
+    CKR(stage_range(h, seqs, offsets, n_reads, first, last, flags, &cd, needs_acgt_check(h, flags), 0, st));
+    Input in = make_input(cd);
+    const uint64_t stride = ((uint64_t)in.n_pos + 7) & ~7ull;
+    CKR(h->d_bins.ensure((size_t)s->nt * stride));
+    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    HashCfg H{h->hash, h->k};
+    Pred P;
+    memset(&P, 0, sizeof P);
+    unsigned gt = n_tiles(in.n_pos);
+    if (H.kind == TWOBIT) launch_hashbins<TWOBIT, 0>(false, gt, st, s->full, s->full, H, P, in, h->d_bins.p, stride, h->d_ctrl);
+    else launch_hashbins<MURMUR, 0>(false, gt, st, s->full, s->full, H, P, in, h->d_bins.p, stride, h->d_ctrl);
+    for (int i = 0; i < s->nt; i++) {
+        RouteDst dst;
+        dst.world = s->world;
+        for (int q = 0; q < 8; q++) {
+            dst.queue[q] = q < s->world ? s->peers[q].rq[i] : nullptr;
+            dst.cursor[q] = q < s->world ? s->peers[q].rcur + i : nullptr;
+        }
+        k_route<<<(in.n_pos + 2047) / 2048, 256, 0, st>>>(h->d_bins.p + (size_t)i * stride, in.n_pos, (uint32_t)s->slice[i], dst,
+                                                         (unsigned long long)s->qcap, h->d_ctrl);
+    }
+    h->all_launches += 1 + s->nt;
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    if (h->h_ctrl->non_acgt) return fail(KMGPU_ECUDA, "a receive queue overflowed (%llu updates dropped)", (unsigned long long)h->h_ctrl->non_acgt);
+    if (n_kmers_out) *n_kmers_out = h->h_ctrl->n_kmers;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    kmgpu_sketch* h = s->local;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    if (h->kind == BYTE && h->use_bigcount) return fail(KMGPU_EUNSUPPORTED, "bigcount is not maintained by sharded sketches");
+    cudaStream_t st = h->stream;
+    std::vector<DeltaPass> passes;
+    if (!plan_delta(h, passes)) return fail(KMGPU_EUNSUPPORTED, "slices of this size are not supported by the sharded path yet");
+    unsigned long long cur[MAX_TABLES];
+    CK(cudaMemcpyAsync(cur, s->rcur, sizeof cur, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t max_span = 0;
+    for (const DeltaPass& p : passes) max_span = std::max<uint64_t>(max_span, p.hi - p.lo);
+    size_t need_lanes = h->kind == BIT ? ((max_span + 127) / 128) * 8 + 8 : ((max_span + 7) & ~7ull) + 8;
+    if (h->d_delta.cap < need_lanes) h->delta_zeroed = 0;
+    CKR(h->d_delta.ensure(need_lanes));
+    if (h->delta_zeroed < h->d_delta.cap) {
+        CK(cudaMemsetAsync(h->d_delta.p, 0, h->d_delta.cap * 2, st));
+        h->delta_zeroed = h->d_delta.cap;
+    }
+    CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+    for (const DeltaPass& p : passes) {
+        uint64_t n = cur[p.table];
+        if (n > s->qcap) return fail(KMGPU_ECUDA, "receive queue overflow");
+        if (n == 0) continue;
+        unsigned gs = (unsigned)((n + 2047) / 2048);
+        if (h->kind == BIT) {
+            k_scatter<true><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
+            unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
+            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl);
+        } else {
+            k_scatter<false><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
+            unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
+            if (h->kind == BYTE) k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr);
+            else k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr);
+        }
+        h->all_launches += 2;
+    }
+    CK(cudaMemsetAsync(s->rcur, 0, MAX_TABLES * sizeof(unsigned long long), st));
+    CK(cudaGetLastError());
+    CKR(read_ctrl(h));
+    h->n_occupied += h->h_ctrl->n_z0;
+    h->satbits_valid = false;
+    return KMGPU_OK;
+}

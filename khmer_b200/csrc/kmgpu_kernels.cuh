@@ -1350,4 +1350,46 @@ __global__ void k_ev_compact(EvTable ev, EvOut* out, Ctrl* ctrl)
     out[at] = o;
 }
 
+// 7. address-sharded sketches: route every bin of one table to the rank that owns it.  Per CTA the bins are
+//    counted per owner in shared memory, one remote atomicAdd per owner reserves a run in that owner's receive
+//    queue (NVLink peer memory), then the slice-relative bins are written into the runs.
+struct RouteDst {
+    uint32_t* queue[8];              // receive queue of this table on every rank
+    unsigned long long* cursor[8];   // its fill cursor (same rank's memory)
+    int world;
+};
+
+__global__ void __launch_bounds__(256)
+k_route(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t slice, RouteDst dst, unsigned long long cap, Ctrl* ctrl)
+{
+    __shared__ unsigned cnt[8];
+    __shared__ unsigned long long base[8];
+    if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 8u;
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = i0 + j < n_pos ? __ldcs(bins + i0 + j) : BIN_NONE;
+    uint32_t own[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        own[j] = v[j] == BIN_NONE ? 0xFFu : v[j] / slice;
+        if (own[j] != 0xFFu) atomicAdd(&cnt[own[j]], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < (unsigned)dst.world) {
+        unsigned c = cnt[threadIdx.x];
+        base[threadIdx.x] = c ? atomicAdd(dst.cursor[threadIdx.x], (unsigned long long)c) : 0ull;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (own[j] == 0xFFu) continue;
+        unsigned long long at = base[own[j]] + atomicAdd(&cnt[own[j]], 1u);
+        if (at < cap) dst.queue[own[j]][at] = v[j] - own[j] * slice;
+        else atomicAdd(&ctrl->non_acgt, 1ull);   // overflow of a receive queue (reported by apply)
+    }
+}
+
 }  // namespace kmgpu

@@ -63,3 +63,70 @@ class ReplicaGroup:
             self.barrier()
             self.sketch.ipc_detach()
             self.attached = False
+
+
+def split_by_bases(buf, off, max_bases):
+    """Cut (buffer, offsets) into runs of whole reads of at most max_bases bases each (a single longer read gets
+    its own run: callers create their shards with max_positions >= the longest read)."""
+    runs = []
+    n = len(off) - 1
+    r = 0
+    while r < n:
+        r1 = r + 1
+        while r1 < n and int(off[r1 + 1]) - int(off[r]) <= max_bases:
+            r1 += 1
+        runs.append((r, r1))
+        r = r1
+    return runs
+
+
+class ShardedGroup:
+    """An address-sharded sketch across the ranks of a process group: every rank hashes its own reads, routes
+    each counter update to the owner of its bin through NVLink peer memory (route), and applies what it
+    received (apply).  The barriers between the two phases come from torch.distributed."""
+
+    def __init__(self, shard, dist=None, device=None):
+        self.shard = shard
+        self.dist = dist
+        self.device = device
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+
+    def barrier(self):
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier()
+
+    def attach(self):
+        import torch
+        mine = np.ascontiguousarray(self.shard.ipc_export(), dtype=np.uint8)
+        if self.world == 1:
+            self.shard.ipc_attach(mine)
+            return
+        t = torch.from_numpy(mine.copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(gathered, t)
+        self.shard.ipc_attach(torch.cat(gathered).cpu().numpy())
+        self.barrier()
+
+    def consume_reads(self, reads, clean=True):
+        """Collective: every rank passes its own shard of the reads; returns the k-mers this rank hashed."""
+        from . import cabi
+        buf, off = cabi.as_reads(reads)
+        runs = split_by_bases(buf, off, self.shard.max_positions)
+        rounds = len(runs)
+        if self.dist is not None and self.world > 1:
+            import torch
+            t = torch.tensor([rounds], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            rounds = int(t.item())
+        kmers = 0
+        for i in range(rounds):
+            if i < len(runs):
+                r0, r1 = runs[i]
+                kmers += self.shard.route((buf, off[r0:r1 + 1]), clean=clean)
+            self.barrier()          # every update of this round sits in its owner's queue
+            self.shard.apply()
+            self.barrier()          # queues are empty again before anyone routes the next round
+        return kmers

@@ -1,0 +1,108 @@
+"""Address-sharded sketches: ranks own bin ranges, k-mers are routed to the owners
+through peer memory, the concatenated slices equal the single-sketch tables byte for byte.  The ranks are
+emulated in one process on one GPU (peer pointers are then ordinary device pointers); with >= 2 GPUs the
+one-process-per-GPU CUDA-IPC form runs as well."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from common import synth_reads
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _assemble(shards, n_tables):
+    return [np.concatenate([s.slice_bytes(i) for s in shards]) for i in range(n_tables)]
+
+
+@pytest.mark.parametrize("cls,k", [("Countgraph", 20), ("SmallCountgraph", 17), ("Nodegraph", 31), ("Counttable", 40),
+                                   ("SmallCounttable", 33), ("Nodetable", 21)])
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_sharded_equals_single_sketch(cls, k, world):
+    from khmer_b200 import cabi
+    from khmer_b200.multigpu import split_by_bases, shard_range
+    kind, hk, _ = ol.CLASSES[cls]
+    sizes = ol.primes_near_x(4, 70000) if world < 8 else [1009, 997, 991, 64]     # tiny tables: some ranks own nothing
+    reads = synth_reads(world * 7 + k, 900, 130, 6000, err=0.01, with_n=True) + ["A" * 300] * 40 + ["", "ACG"]
+    shards = [cabi.Shard(kind, hk, k, sizes, r, world, max_positions=20000) for r in range(world)]
+    cabi.attach_local_shards(shards)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(len(reads), r, world)
+        buf, off = cabi.as_reads(reads[lo:hi])
+        parts.append((buf, off, split_by_bases(buf, off, 20000)))
+    rounds = max(len(p[2]) for p in parts)
+    kmers = 0
+    for i in range(rounds):
+        for r in range(world):                       # "all ranks route", then "all ranks apply"
+            buf, off, runs = parts[r]
+            if i < len(runs):
+                a, b = runs[i]
+                kmers += shards[r].route((buf, off[a:b + 1]))
+        for r in range(world):
+            shards[r].apply()
+    o = ol.Oracle(cls, k, sizes)
+    assert kmers == o.consume_reads(reads)
+    tables = _assemble(shards, 4)
+    for i in range(4):
+        assert np.array_equal(tables[i], o.table(i)), "table %d" % i
+    assert sum(s.local.n_occupied() for s in shards) == o.n_occupied()
+    for s in shards:
+        s.close()
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from khmer_b200 import cabi
+from khmer_b200.multigpu import ShardedGroup, shard_range
+import oracle_lib as ol
+from common import synth_reads
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+sizes = ol.primes_near_x(4, 3000000)
+reads = synth_reads(5, 6000, 150, 40000) + ["AC" * 100] * 300
+for cls, k in (("Countgraph", 20), ("SmallCountgraph", 31), ("Nodegraph", 32), ("Counttable", 40)):
+    kind, hk, _ = ol.CLASSES[cls]
+    sh = cabi.Shard(kind, hk, k, sizes, rank, world, device=rank, max_positions=200000)
+    g = ShardedGroup(sh, dist, device=dev)
+    g.attach()
+    lo, hi = shard_range(len(reads), rank, world)
+    mine = g.consume_reads(reads[lo:hi])
+    o = ol.Oracle(cls, k, sizes)
+    total = o.consume_reads(reads)
+    t = torch.tensor([mine, sh.local.n_occupied()], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    assert int(t[0]) == total and int(t[1]) == o.n_occupied(), (cls, t.tolist(), total, o.n_occupied())
+    for i in range(4):
+        lo_b, hi_b = sh.slice(i)
+        want = o.table(i)
+        got = sh.slice_bytes(i)
+        per = 1 if kind == ol.BYTE else 2 if kind == ol.NIBBLE else 8
+        assert np.array_equal(got, want[lo_b // per: lo_b // per + len(got)]), (cls, rank, i)
+    dist.barrier()
+    sh.close()
+if rank == 0:
+    print("SHARDED-IPC-OK")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_one_process_per_gpu(tmp_path):
+    from khmer_b200 import cabi
+    if cabi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    n = min(cabi.device_count(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+                        "127.0.0.1", "--master-port", "29621", str(script)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SHARDED-IPC-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
