@@ -181,6 +181,7 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_flags;
     DevBuf<uint32_t> d_newbits;
     DevBuf<uint32_t> d_filter;
+    DevBuf<uint32_t> d_rank;
     DevBuf<uint32_t> d_bins;
     DevBuf<uint16_t> d_delta;
     size_t delta_zeroed = 0;
@@ -455,7 +456,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -1077,6 +1078,30 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
                 uint64_t seg1 = c.pass_list_end[pi];
                 if (seg1 > seg0) {
                     const DeltaPass& p = passes[pi];
+                    const uint32_t span = p.hi - p.lo;
+                    if (span <= (1u << 26) && env_u64("KMGPU_COLD_RANK", 1)) {
+                        // direct-addressed form: ranked bitmap of the block's new bins + one min-position per new bin
+                        const uint32_t n_words = (span + 31) / 32;
+                        const unsigned gw = (n_words + 1023) / 1024;
+                        const uint64_t n_ent = seg1 - seg0;
+                        CKR(h->d_rank.ensure((size_t)n_words * 2 + gw));
+                        CKR(h->d_htkeys.ensure((n_ent + 1) / 2));
+                        uint2* rec = reinterpret_cast<uint2*>(h->d_rank.p);
+                        uint32_t* sums = h->d_rank.p + (size_t)n_words * 2;
+                        uint32_t* minpos = reinterpret_cast<uint32_t*>(h->d_htkeys.p);
+                        CK(cudaMemsetAsync(rec, 0, (size_t)n_words * 8, st));
+                        CK(cudaMemsetAsync(minpos, 0xFF, n_ent * 4, st));
+                        unsigned gl = (unsigned)std::min<uint64_t>((n_ent + 255) / 256, 148 * 8);
+                        k_rank_setbits<<<gl, 256, 0, st>>>(h->d_binlist.p + seg0, n_ent, p.lo, rec);
+                        k_rank_sums<<<gw, 256, 0, st>>>(rec, n_words, sums);
+                        k_rank_scan<<<1, 1024, 0, st>>>(sums, gw);
+                        k_rank_prefix<<<gw, 256, 0, st>>>(rec, n_words, sums);
+                        k_rank_replay<<<(in.n_pos + 2047) / 2048, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, rec, minpos);
+                        k_rank_mark<<<gl, 256, 0, st>>>(minpos, n_ent, h->d_newbits.p, h->d_ctrl);
+                        h->all_launches += 6;
+                        seg0 = seg1;
+                        continue;
+                    }
                     uint64_t slots = pow2_at_least(2 * (seg1 - seg0));
                     CKR(h->d_htkeys.ensure(slots));
                     sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);

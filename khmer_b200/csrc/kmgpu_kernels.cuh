@@ -1063,6 +1063,132 @@ __global__ void k_pk_mark(const unsigned long long* __restrict__ slots, uint64_t
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_unique, (unsigned long long)cnt);
 }
 
+// 4d. cold chunks, direct-addressed form: the block's new bins as a bitmap with running ranks (8 bytes per 32 bins:
+//     {bits, number of new bins before this word}), so that a toucher finds "is my bin new, and which one is it" with
+//     one 8-byte load from a few-MB structure, and lowers minpos[rank] with a return-less red.min.  Against the
+//     stamp hash table: no key compare, no probing, 4 instead of 16 bytes of L2 per new bin.
+__global__ void k_rank_setbits(const uint64_t* __restrict__ binlist, uint64_t n, uint32_t lo, uint2* rec)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = binlist[i];
+        if (!(e & BL_NEW)) continue;
+        uint32_t d = (uint32_t)((e & 0xFFFFFFFFFFFFull) >> 8) - lo;
+        atomicOr(&rec[d >> 5].x, 1u << (d & 31));
+    }
+}
+
+// three-step exclusive scan of the words' popcounts: 1024 words per CTA (4 per thread)
+__global__ void __launch_bounds__(256) k_rank_sums(const uint2* __restrict__ rec, uint32_t n_words, uint32_t* __restrict__ sums)
+{
+    const uint32_t w0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    unsigned c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (w0 + j < n_words) c += __popc(rec[w0 + j].x);
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ unsigned s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) sums[blockIdx.x] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
+}
+
+__global__ void __launch_bounds__(1024) k_rank_scan(uint32_t* sums, uint32_t n)   // one CTA; sums -> exclusive prefix
+{
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        unsigned v = i < n ? sums[i] : 0, incl = v;
+        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads();
+        unsigned before = s_carry;
+        for (unsigned w = 0; w < wid; w++) before += s_w[w];
+        if (i < n) sums[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rank_prefix(uint2* rec, uint32_t n_words, const uint32_t* __restrict__ sums)
+{
+    const uint32_t w0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    unsigned c[4], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        c[j] = w0 + j < n_words ? __popc(rec[w0 + j].x) : 0;
+        tot += c[j];
+    }
+    unsigned incl = tot;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    __shared__ unsigned s[8];
+    if (lane == 31) s[wid] = incl;
+    __syncthreads();
+    unsigned at = sums[blockIdx.x] + incl - tot;
+    for (unsigned w = 0; w < wid; w++) at += s[w];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (w0 + j < n_words) rec[w0 + j].y = at;
+        at += c[j];
+    }
+}
+
+// 8 consecutive positions per thread; all record loads are issued before any is used
+__global__ void __launch_bounds__(256)
+k_rank_replay(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32_t hi, const uint2* __restrict__ rec, uint32_t* minpos)
+{
+    const uint32_t p0 = (blockIdx.x * 256u + threadIdx.x) * 8u;
+    if (p0 >= n_pos) return;
+    uint32_t v[8];
+    if (p0 + 8 <= n_pos) {
+        uint4 a = __ldcs(reinterpret_cast<const uint4*>(bins + p0));
+        uint4 b = __ldcs(reinterpret_cast<const uint4*>(bins + p0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = p0 + j < n_pos ? __ldcs(bins + p0 + j) : BIN_NONE;
+    }
+    const uint32_t span = hi - lo;
+    uint2 r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        v[j] -= lo;                       // BIN_NONE and bins of other blocks wrap far above span
+        r[j] = v[j] < span ? __ldcg(&rec[v[j] >> 5]) : make_uint2(0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t bit = 1u << (v[j] & 31);
+        if (r[j].x & bit) atomicMin(&minpos[r[j].y + __popc(r[j].x & (bit - 1))], p0 + j);
+    }
+}
+
+__global__ void k_rank_mark(const uint32_t* __restrict__ minpos, uint64_t n, uint32_t* newbits, Ctrl* ctrl)
+{
+    unsigned cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t p = minpos[i];
+        if (p == 0xFFFFFFFFu) continue;
+        uint32_t bit = 1u << (p & 31);
+        uint32_t old = atomicOr(&newbits[p >> 5], bit);
+        cnt += !(old & bit);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctrl->n_unique, (unsigned long long)cnt);
+}
+
 // fused forms over all tables: table i owns slots [base[i], base[i] + mask[i] + 1) of one buffer
 struct PkLayout {
     uint64_t base[F_MAXT];

@@ -65,7 +65,7 @@ def _same_state(g, o, n_tables):
 
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
-@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold"])
+@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
@@ -76,8 +76,10 @@ def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
             env.update(KMGPU_DELTA="0", KMGPU_L2_BLOCK_BYTES="1500", KMGPU_MAX_PASSES="64", KMGPU_CHUNK_BASES="16384")
         elif chunk == "cas-8192":   # compare-and-swap path, all tables in one pass
             env.update(KMGPU_DELTA="0", KMGPU_CHUNK_BASES="8192")
-        elif chunk == "delta-cold":   # delta+fold path, per-block ("cold chunk") stamp resolution forced
+        elif chunk == "delta-cold":   # delta+fold path, per-block ("cold chunk") ranked-bitmap resolution forced
             env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768")
+        elif chunk == "delta-cold-stamps":   # same, through the stamp hash tables (blocks beyond 2^26 bins take this form)
+            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_COLD_RANK="0")
         elif chunk == "delta-blocks":   # delta+fold path with many blocks per table
             env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384")
         else:
