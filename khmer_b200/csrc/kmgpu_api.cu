@@ -64,7 +64,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt)
 static uint64_t chunk_bases()
 {
     static uint64_t c = [] {
-        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 64ull << 20);
+        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 128ull << 20);
         v = std::max<uint64_t>(TILE, std::min<uint64_t>(v, 1ull << 31));
         return (v / TILE) * TILE;
     }();
@@ -1032,21 +1032,20 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     const unsigned gs = (in.n_pos + 2047) / 2048;
     for (const DeltaPass& p : passes) {
+        const int pass_id = passes.size() <= 64 ? (int)(&p - passes.data()) : -1;   // per-pass entry counts for the cold resolution
         if (h->kind == BIT) {
             k_scatter<true><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
             unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
-            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl);
-            if (passes.size() <= 64) k_pass_snapshot<<<1, 1, 0, st>>>(h->d_ctrl, (int)(&p - passes.data()));
+            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, pass_id);
             continue;
         }
         k_scatter<false><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
         unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
         if (h->kind == BYTE)
             k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross,
-                                             want_cross ? h->d_satbits[p.table].p : nullptr);
+                                             want_cross ? h->d_satbits[p.table].p : nullptr, pass_id);
         else
-            k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, nullptr);
-        if (passes.size() <= 64) k_pass_snapshot<<<1, 1, 0, st>>>(h->d_ctrl, (int)(&p - passes.data()));
+            k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, nullptr, pass_id);
     }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
@@ -1075,7 +1074,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
             unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
             uint64_t seg0 = 0;
             for (size_t pi = 0; pi < passes.size(); pi++) {
-                uint64_t seg1 = c.pass_list_end[pi];
+                uint64_t seg1 = seg0 + c.pass_list_end[pi];   // entries the fold of pass pi appended (passes run in order)
                 if (seg1 > seg0) {
                     const DeltaPass& p = passes[pi];
                     const uint32_t span = p.hi - p.lo;
@@ -1213,6 +1212,18 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
 }
 
 // ------------------------------------------------------------------------------------------------------
+// equal-sized chunks (multiples of 32 bases) of at most `cap` bases covering [0, total): starts[i] .. starts[i+1]
+static void balanced_chunks(uint64_t total, uint64_t cap, std::vector<uint64_t>& starts)
+{
+    starts.assign(1, 0);
+    if (total == 0) return;
+    const uint64_t n = (total + cap - 1) / cap;
+    uint64_t size = (((total + n - 1) / n) + 31) & ~31ull;
+    if (size > cap) size = cap;
+    for (uint64_t b = size; b < total; b += size) starts.push_back(b);
+    starts.push_back(total);
+}
+
 // staging reads: split [seqs, offsets] into chunks of <= chunk_bases() positions, cutting at read
 // boundaries where possible; a read longer than a chunk continues in the next chunk with k-1 bases of
 // overlap, which yields exactly the same k-mer stream.
@@ -1385,13 +1396,29 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     // it: a clipped piece inside the k-1 overlap is shorter than k and yields nothing, the piece that continues past it
     // starts exactly at the first k-mer the previous chunk could not hold — the k-mer stream is unchanged.
     // Chunk i+1 is uploaded and packed on the copy stream while chunk i is ingested on the main stream.
-    const uint64_t first = offsets[0], last = offsets[n_reads], cap = chunk_bases();
+    const uint64_t first = offsets[0], last = offsets[n_reads];
     const bool chk = needs_acgt_check(h, flags);
     if (last <= first) return KMGPU_OK;
-    const uint64_t n_chunks = (last - first + cap - 1) / cap;
+    // Every chunk pays one sweep of the whole sketch (the folds) plus the fixed part of the resolutions, so there are
+    // as few chunks as the cap allows; nothing can start before chunk 0 has crossed PCIe, so chunk 0 is the short one
+    // (half of the others when the cap leaves that freedom) and the copy of chunk i+1 hides behind the ingest of chunk i.
+    std::vector<uint64_t> starts(1, 0);
+    {
+        const uint64_t total = last - first, cap = chunk_bases(), n = (total + cap - 1) / cap;
+        if (n >= 2) {
+            uint64_t c0 = std::max<uint64_t>(total - (n - 1) * cap, total / (2 * n - 1));
+            uint64_t c = (((total - c0) + (n - 2)) / (n - 1) + 31) & ~31ull;
+            c = std::min(c, cap);
+            c0 = total - (n - 1) * c;   // > 0: (n-1)*c < total since c0 was at least total/(2n-1) before rounding
+            if ((int64_t)c0 <= 0) c0 = 1;
+            for (uint64_t b = c0; b < total; b += c) starts.push_back(b);
+        }
+        starts.push_back(total);
+    }
+    const uint64_t n_chunks = starts.size() - 1;
     auto range = [&](uint64_t i, uint64_t* b0, uint64_t* b1) {
-        *b0 = first + i * cap;
-        *b1 = std::min(last, *b0 + cap + (uint64_t)(h->k - 1));
+        *b0 = first + starts[i];
+        *b1 = std::min(last, first + starts[i + 1] + (uint64_t)(h->k - 1));
     };
     ChunkDev cd[2];
     uint64_t b0, b1;
@@ -1439,11 +1466,13 @@ static int for_each_packed_chunk(kmgpu_sketch* h, const uint64_t* words, uint64_
 {
     cudaStream_t st = h->stream;
     const uint64_t n_bases = offsets[n_reads];
-    const uint64_t cap = chunk_bases();
+    std::vector<uint64_t> starts;
+    balanced_chunks(n_bases, chunk_bases(), starts);
     uint64_t r0 = 0;
     std::vector<uint32_t> offs;
-    for (uint64_t b0 = 0; b0 < n_bases; b0 += cap) {
-        uint64_t b1 = std::min(n_bases, b0 + cap + (uint64_t)(h->k - 1));
+    for (size_t ci = 0; ci + 1 < starts.size(); ci++) {
+        const uint64_t b0 = starts[ci];
+        uint64_t b1 = std::min(n_bases, starts[ci + 1] + (uint64_t)(h->k - 1));
         clip_offsets(offsets, n_reads, b0, b1, &r0, offs);
         uint32_t n_pos = (uint32_t)(b1 - b0);
         size_t nw = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
@@ -1510,7 +1539,12 @@ extern "C" int kmgpu_batch_create(int device, const char* seqs, const uint64_t* 
     b->n_reads = n_reads;
     b->n_bases = n_reads ? offsets[n_reads] - offsets[0] : 0;
     std::vector<ChunkPlan> plan;
-    if (n_reads) plan_chunks(offsets, n_reads, ksize, chunk_bases(), plan);
+    if (n_reads) {
+        // equal pieces (every piece costs one sweep of the sketch when it is consumed); cut at read boundaries
+        const uint64_t cap = chunk_bases(), n = (b->n_bases + cap - 1) / cap;
+        uint64_t piece = n ? (((b->n_bases + n - 1) / n + 65536 + TILE - 1) / TILE) * TILE : cap;
+        plan_chunks(offsets, n_reads, ksize, std::min(cap, piece), plan);
+    }
     uint8_t* d_ascii = nullptr;
     Ctrl* d_ctrl = nullptr;
     size_t ascii_cap = 0;
@@ -2333,12 +2367,12 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
         if (h->kind == BIT) {
             k_scatter<true><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
             unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
-            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl);
+            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, -1);
         } else {
             k_scatter<false><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
             unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
-            if (h->kind == BYTE) k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr);
-            else k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr);
+            if (h->kind == BYTE) k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr, -1);
+            else k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr, -1);
         }
         h->all_launches += 2;
     }

@@ -667,10 +667,36 @@ struct PeerPtrs {
 };
 __global__ void k_merge_peers(int kind, uint32_t* __restrict__ dst, PeerPtrs peers, uint64_t w0, uint64_t w1)
 {
-    for (uint64_t i = w0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < w1; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t a = dst[i];
-        for (int j = 0; j < peers.n; j++) a = merge_word(kind, a, __ldcg(peers.p[j] + i));
-        dst[i] = a;
+    // 16 bytes per thread and peer; the loads from all peers are issued before any is merged (the loop runs over the
+    // compile-time bound with a guard so that the pointer array stays in registers / constant space)
+    const uint64_t q0 = (w0 + 3) / 4, q1 = w1 / 4;   // whole uint4 groups inside [w0, w1)
+    for (uint64_t q = q0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < q1; q += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (j < peers.n) v[j] = __ldcg(reinterpret_cast<const uint4*>(peers.p[j]) + q);
+        uint4 a = reinterpret_cast<uint4*>(dst)[q];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j >= peers.n) continue;
+            a.x = merge_word(kind, a.x, v[j].x);
+            a.y = merge_word(kind, a.y, v[j].y);
+            a.z = merge_word(kind, a.z, v[j].z);
+            a.w = merge_word(kind, a.w, v[j].w);
+        }
+        reinterpret_cast<uint4*>(dst)[q] = a;
+    }
+    // ragged head and tail: at most 3 words each
+    if (blockIdx.x == 0 && threadIdx.x < 6) {
+        const uint64_t head_end = q0 * 4 < w1 ? q0 * 4 : w1, tail_begin = q1 * 4 > head_end ? q1 * 4 : head_end;
+        const uint64_t i = threadIdx.x < 3 ? w0 + threadIdx.x : tail_begin + (threadIdx.x - 3);
+        if (threadIdx.x < 3 ? i < head_end : i < w1) {
+            uint32_t a = dst[i];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < peers.n) a = merge_word(kind, a, __ldcg(peers.p[j] + i));
+            dst[i] = a;
+        }
     }
 }
 
@@ -780,7 +806,7 @@ k_scatter(const uint32_t* __restrict__ bins, uint32_t n_pos, uint32_t lo, uint32
 //     storage.hh:176-195: a k-mer is new iff one of its bits was clear); table |= block; block re-zeroed.
 __global__ void __launch_bounds__(256)
 k_fold_bits(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta, uint64_t* __restrict__ binlist,
-            unsigned long long list_cap, Ctrl* ctrl)
+            unsigned long long list_cap, Ctrl* ctrl, int pass)
 {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;   // group of 128 bins
     const uint32_t span = hi - lo;
@@ -816,6 +842,7 @@ k_fold_bits(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi
         for (int w = 0; w < 8; w++) tot += s_cnt[w];
         s_base = tot ? atomicAdd(&ctrl->n_events, (unsigned long long)tot) : 0ull;
         if (tot) {
+            if (pass >= 0) atomicAdd(&ctrl->pass_list_end[pass], (unsigned long long)tot);
             atomicAdd(&ctrl->n_zbits, (unsigned long long)tot);
             atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)tot);
             if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)tot);
@@ -846,17 +873,17 @@ k_fold_bits(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi
 template <int KIND>
 __global__ void __launch_bounds__(256)
 k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uint16_t* __restrict__ delta, uint64_t* __restrict__ binlist,
-       unsigned long long list_cap, Ctrl* ctrl, int want_cross, uint8_t* __restrict__ satbits)
+       unsigned long long list_cap, Ctrl* ctrl, int want_cross, uint8_t* __restrict__ satbits, int pass)
 {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;  // group of 8 bins
     const uint32_t span = hi - lo;
-    unsigned n_new = 0, n_sat = 0, n_cross = 0, n_ent = 0;
-    uint64_t ent[8];
+    const uint32_t b0 = lo + g * 8u;
+    // per-thread outcome as 8-bit masks over its bins (kept in registers: the list entries are rebuilt from them below)
+    unsigned newm = 0, crossm = 0, n_sat = 0;
+    uint64_t old64 = 0;
     if (g * 8u < span) {
         // both loads are issued before either is looked at (the table slice streams from HBM, the lanes from L2)
-        const uint32_t b0 = lo + g * 8u;
         uint4 d4 = __ldcg(reinterpret_cast<const uint4*>(delta + (size_t)g * 8));
-        uint64_t old64 = 0;
         uint32_t old32 = 0;
         if (KIND == BYTE) old64 = __ldcs(reinterpret_cast<const unsigned long long*>(table + b0));
         else old32 = __ldcs(reinterpret_cast<const uint32_t*>(table + (b0 >> 1)));
@@ -866,6 +893,7 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
             constexpr uint32_t CAP = KIND == BYTE ? 255u : 15u;
             uint64_t new64 = old64;
             uint32_t new32 = old32;
+            unsigned fullm = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 uint32_t hbits = (dw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
@@ -883,28 +911,19 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
                 uint32_t nv = t > CAP ? CAP : t;
                 if (KIND == BYTE) new64 = (new64 & ~(255ull << sh)) | ((uint64_t)nv << sh);
                 else new32 = (new32 & ~(15u << sh)) | (nv << sh);
-                uint64_t entry = 0;
-                if (s == 0) {
-                    entry |= BL_NEW;
-                    n_new++;
-                }
-                if (KIND == BYTE && t >= CAP) {
-                    if (t > CAP) n_sat++;   // at least one touch of this chunk found the byte already saturated
-                    if (s < CAP) {          // the byte reached 255 inside this chunk
-                        n_cross++;
-                        if (want_cross) entry |= BL_CROSS | ((uint64_t)s << 48);
-                    }
-                }
-                if (entry) {
-                    ent[n_ent++] = entry | ht_key((uint64_t)(b0 + j), table_idx);
+                newm |= (unsigned)(s == 0) << j;
+                if (KIND == BYTE) {
+                    n_sat += t > CAP;                               // a touch of this chunk found the byte already saturated
+                    crossm |= (unsigned)(t >= CAP && s < CAP) << j;  // the byte reached 255 inside this chunk
+                    fullm |= (unsigned)(nv == CAP) << j;
                 }
             }
             if (KIND == BYTE) {
                 *reinterpret_cast<uint64_t*>(table + b0) = new64;
-                if (satbits) {   // one bit per bin "byte is 255": this thread owns the whole byte of the bitmap
-                    uint32_t m = 0;
+                if (satbits && fullm) {   // one bit per bin "byte is 255": this thread owns the whole byte of the bitmap
+                    unsigned m = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) m |= (uint32_t)(((new64 >> (8 * j)) & 255u) == 255u) << j;
+                    for (int j = 0; j < 8; j++) m |= (unsigned)(((new64 >> (8 * j)) & 255u) == 255u) << j;
                     satbits[b0 >> 3] = (uint8_t)m;
                 }
             } else {
@@ -914,45 +933,56 @@ k_fold(uint8_t* __restrict__ table, int table_idx, uint32_t lo, uint32_t hi, uin
     }
     // one list reservation and one set of counter updates per CTA (same-address atomics from every warp of a
     // cold chunk were costing more than the fold itself)
-    {
-        __shared__ unsigned s_cnt[8][4];   // per warp: entries, new, sat, cross
-        __shared__ unsigned long long s_base;
-        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        unsigned incl = n_ent;
+    const unsigned entm = newm | (want_cross ? crossm : 0u);
+    const unsigned n_ent = __popc(entm);
+    __shared__ unsigned s_cnt[8][4];   // per warp: entries, new, sat, cross
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned incl = n_ent;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += v;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    unsigned w_new = __reduce_add_sync(0xffffffffu, (unsigned)__popc(newm));
+    unsigned w_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    unsigned w_cross = __reduce_add_sync(0xffffffffu, (unsigned)__popc(crossm));
+    if (lane == 31) {
+        s_cnt[wid][0] = incl;
+        s_cnt[wid][1] = w_new;
+        s_cnt[wid][2] = w_sat;
+        s_cnt[wid][3] = w_cross;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot[4] = {0, 0, 0, 0};
+        for (int w = 0; w < 8; w++)
+            for (int q = 0; q < 4; q++) tot[q] += s_cnt[w][q];
+        s_base = 0;
+        if (tot[0]) {
+            s_base = atomicAdd(&ctrl->n_events, (unsigned long long)tot[0]);
+            if (pass >= 0) atomicAdd(&ctrl->pass_list_end[pass], (unsigned long long)tot[0]);
         }
-        unsigned w_new = __reduce_add_sync(0xffffffffu, n_new);
-        unsigned w_sat = __reduce_add_sync(0xffffffffu, n_sat);
-        unsigned w_cross = __reduce_add_sync(0xffffffffu, n_cross);
-        if (lane == 31) {
-            s_cnt[wid][0] = incl;
-            s_cnt[wid][1] = w_new;
-            s_cnt[wid][2] = w_sat;
-            s_cnt[wid][3] = w_cross;
+        if (tot[1]) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)tot[1]);
+            atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)tot[1]);
+            if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)tot[1]);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned tot[4] = {0, 0, 0, 0};
-            for (int w = 0; w < 8; w++)
-                for (int q = 0; q < 4; q++) tot[q] += s_cnt[w][q];
-            s_base = tot[0] ? atomicAdd(&ctrl->n_events, (unsigned long long)tot[0]) : 0ull;
-            if (tot[1]) {
-                atomicAdd(&ctrl->n_zbits, (unsigned long long)tot[1]);
-                atomicAdd(&ctrl->n_new_t[table_idx], (unsigned long long)tot[1]);
-                if (table_idx == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)tot[1]);
-            }
-            if (tot[2]) atomicAdd(&ctrl->n_sat, (unsigned long long)tot[2]);
-            if (tot[3]) atomicAdd(&ctrl->n_cross, (unsigned long long)tot[3]);
-        }
-        __syncthreads();
-        if (n_ent) {
-            unsigned long long at = s_base + (incl - n_ent);
-            for (unsigned w = 0; w < wid; w++) at += s_cnt[w][0];
-            for (unsigned e = 0; e < n_ent; e++)
-                if (at + e < list_cap) binlist[at + e] = ent[e];
+        if (tot[2]) atomicAdd(&ctrl->n_sat, (unsigned long long)tot[2]);
+        if (tot[3]) atomicAdd(&ctrl->n_cross, (unsigned long long)tot[3]);
+    }
+    __syncthreads();
+    if (n_ent) {
+        unsigned long long at = s_base + (incl - n_ent);
+        for (unsigned w = 0; w < wid; w++) at += s_cnt[w][0];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!((entm >> j) & 1u)) continue;
+            uint64_t entry = ht_key((uint64_t)(b0 + j), table_idx);
+            if ((newm >> j) & 1u) entry |= BL_NEW;
+            if (KIND == BYTE && want_cross && ((crossm >> j) & 1u)) entry |= BL_CROSS | (((old64 >> (8 * j)) & 255ull) << 48);
+            if (at < list_cap) binlist[at] = entry;
+            at++;
         }
     }
 }
@@ -999,7 +1029,6 @@ __global__ void k_pk_register(const uint64_t* __restrict__ binlist, uint64_t n, 
     }
 }
 
-__global__ void k_pass_snapshot(Ctrl* ctrl, int pass) { ctrl->pass_list_end[pass] = ctrl->n_events; }
 
 // finish one probe whose first slot value `v` has already been loaded
 __device__ __forceinline__ void pk_finish(unsigned long long* tb, uint64_t mask, uint64_t s, unsigned long long v, uint32_t bin, uint32_t p)
