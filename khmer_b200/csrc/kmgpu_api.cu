@@ -182,6 +182,9 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_newbits;
     DevBuf<uint32_t> d_filter;
     DevBuf<uint32_t> d_rank;
+    DevBuf<unsigned long long> d_records;   // bucket path: update records, bucket-major
+    DevBuf<uint32_t> d_cursors;
+    bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
     DevBuf<uint16_t> d_delta;
     size_t delta_zeroed = 0;
@@ -456,7 +459,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -988,6 +991,39 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
     return KMGPU_OK;
 }
 
+// Bucket path eligibility for a chunk of n_pos positions: every table within BKT_MAX_BUCKETS buckets, and the expected
+// bucket load (+25% + 2048 of slack) within what a 16-bit touch lane can count.  Skewed input that overflows a bucket
+// anyway is caught on the device and the chunk falls back to the delta passes.
+static bool plan_buckets(const kmgpu_sketch* h, uint32_t n_pos, BucketLayout* L)
+{
+    if (!env_u64("KMGPU_BUCKETS", 1)) return false;
+    memset(L, 0, sizeof *L);
+    L->n_tables = h->nt;
+    uint64_t cap = 0, total = 0;
+    for (int i = 0; i < h->nt; i++) {
+        if (h->sizes[i] > 0xFFFFFFFEull - 128) return false;
+        uint64_t nb = (h->sizes[i] + BKT_BINS - 1) / BKT_BINS;
+        if (nb > (uint64_t)BKT_MAX_BUCKETS) return false;
+        L->first[i] = (uint32_t)total;
+        total += nb;
+        uint64_t expect = nb == 1 ? n_pos : (uint64_t)((double)n_pos * BKT_BINS / (double)h->sizes[i]) + 1;
+        cap = std::max(cap, expect + expect / 4 + 2048);
+    }
+    L->first[h->nt] = (uint32_t)total;
+    cap = std::min<uint64_t>(cap, (uint64_t)n_pos);
+    if (uint64_t forced = env_u64("KMGPU_BUCKET_CAP", 0)) cap = forced;   // tests: provoke the overflow fallback
+    if (cap > 65535 || cap == 0) return false;
+    L->cap = (uint32_t)cap;
+    return true;
+}
+
+template <int KIND>
+static void launch_apply(unsigned g, cudaStream_t st, const SketchDev& S, const BucketLayout& L, const unsigned long long* rec, const uint32_t* cur,
+                         uint32_t* newbits, uint64_t* binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const SatBits& sb)
+{
+    k_apply<KIND><<<g, 1024, BKT_APPLY_SMEM, st>>>(S, L, rec, cur, newbits, binlist, list_cap, ctrl, want_cross, sb);
+}
+
 // `between` (optional) runs on the host after the chunk's kernels have been queued and before the host waits for
 // them: the caller uses it to prepare and upload the next chunk while this one is being ingested.
 typedef std::function<int()> Between;
@@ -1030,6 +1066,63 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         }
         h->satbits_valid = true;
     }
+    bool kmers_counted = false;
+    BucketLayout BL;
+    if (plan_buckets(h, in.n_pos, &BL)) {
+        // bucket path: group the updates by 32 Ki-bin bucket, apply each bucket in shared memory (counters, n_occupied,
+        // first touchers -> newbits / n_unique, saturation bookkeeping in one sweep)
+        if (!h->bucket_attr_set) {
+            CK(cudaFuncSetAttribute(k_bucketize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_SORT_SMEM));
+            CK(cudaFuncSetAttribute(k_apply<BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
+            CK(cudaFuncSetAttribute(k_apply<NIBBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
+            CK(cudaFuncSetAttribute(k_apply<BIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
+            h->bucket_attr_set = true;
+        }
+        const uint32_t n_buckets = BL.first[h->nt];
+        CKR(h->d_records.ensure((size_t)n_buckets * BL.cap));
+        CKR(h->d_cursors.ensure(n_buckets));
+        const size_t nb_words = (in.n_pos + 31) / 32;
+        CKR(h->d_newbits.ensure(nb_words));
+        CK(cudaMemsetAsync(h->d_cursors.p, 0, (size_t)n_buckets * 4, st));
+        CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
+        SatBits sb;
+        memset(&sb, 0, sizeof sb);
+        if (want_cross)
+            for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
+        k_bucketize<<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), 1024, BKT_SORT_SMEM, st>>>(h->d_bins.p, stride, in.n_pos, BL, h->d_records.p,
+                                                                                                 h->d_cursors.p, h->d_ctrl);
+        if (h->kind == BYTE) launch_apply<BYTE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross, sb);
+        else if (h->kind == NIBBLE) launch_apply<NIBBLE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
+        else launch_apply<BIT>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaGetLastError());
+        if (between) CKR(between());
+        CKR(read_ctrl(h));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ingest_ms += ms;
+        h->ingest_launches += 3;
+        h->all_launches += 3;
+        Ctrl c = *h->h_ctrl;
+        res->n_kmers += c.n_kmers;
+        kmers_counted = true;
+        if (!c.overflow) {
+            if (c.n_events > list_cap) return fail(KMGPU_ECUDA, "internal: bin list overflow");
+            h->n_occupied += c.n_z0;
+            if (c.n_zbits) {
+                h->n_unique += c.n_unique;
+                res->n_new += c.n_unique;
+                res->have_newbits = true;
+            }
+            if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, in, stride, c.n_events, c.n_cross));
+            return KMGPU_OK;
+        }
+        // a bucket overflowed (heavily repeated k-mers): nothing was applied; redo the chunk with the delta passes
+        CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
+        CK(cudaEventRecord(h->ev0, st));
+    }
+    const Between none;
+    const Between& between2 = kmers_counted ? none : between;   // the hook has already run
     const unsigned gs = (in.n_pos + 2047) / 2048;
     for (const DeltaPass& p : passes) {
         const int pass_id = passes.size() <= 64 ? (int)(&p - passes.data()) : -1;   // per-pass entry counts for the cold resolution
@@ -1049,7 +1142,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
-    if (between) CKR(between());
+    if (between2) CKR(between2());
     CKR(read_ctrl(h));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1058,7 +1151,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     h->all_launches += 1 + 2 * passes.size();
     Ctrl c = *h->h_ctrl;
     if (c.n_events > list_cap) return fail(KMGPU_ECUDA, "internal: bin list overflow");
-    res->n_kmers += c.n_kmers;
+    if (!kmers_counted) res->n_kmers += c.n_kmers;
     h->n_occupied += c.n_z0;
     const uint64_t n_list = c.n_events;
     if (c.n_zbits) {

@@ -18,7 +18,8 @@ struct Ctrl {
     unsigned long long n_events;  // records appended by k_events / k_cross_replay
     unsigned long long non_acgt;  // pack kernel: bytes outside ACGT seen in raw mode
     unsigned long long n_new_t[10];  // delta path: newly occupied bins per table
-    unsigned long long pass_list_end[64];  // delta path: bin list length after each (table, block) pass
+    unsigned long long pass_list_end[64];  // delta path: bin list entries appended by each (table, block) pass
+    unsigned long long overflow;  // bucket path: a bucket ran out of room (the chunk is redone by the delta passes)
 };
 
 // flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
@@ -1273,6 +1274,279 @@ k_pk_replay_all(const uint32_t* __restrict__ bins, uint64_t stride, int n_tables
     }
 }
 
+// =====================================================================================================
+// Bucket path (tables of up to BKT_MAX_BUCKETS x 32 Ki bins): the chunk's updates are first grouped by 32 Ki-bin
+// bucket of their table, then one CTA per bucket applies them in SHARED memory and sweeps the result into the
+// table.  What the delta passes need 16 sweeps of the bin arrays, ~350 M L2 reductions and a separate
+// first-toucher replay for, happens here in two kernels: the per-bin touch counts and the smallest touching
+// position (the first toucher in stream order) both live in the CTA's 192 KB of shared memory, so the
+// counters, n_occupied, n_unique_kmers (marks in `newbits`) and the saturation bookkeeping all come out of
+// the same sweep.  DRAM sees: the bin arrays once, the 8-byte update records once out and once back, the
+// table once in and once out.
+// =====================================================================================================
+struct SatBits {
+    const uint8_t* t[F_MAXT];
+};
+
+constexpr int BKT_SHIFT = 15;
+constexpr uint32_t BKT_BINS = 1u << BKT_SHIFT;   // bins per bucket
+constexpr int BKT_TILE = 16384;                  // positions per k_bucketize CTA
+constexpr int BKT_MAX_BUCKETS = 6144;            // per table (shared-memory histogram of k_bucketize)
+constexpr size_t BKT_SORT_SMEM = (size_t)BKT_TILE * 8 + (size_t)BKT_MAX_BUCKETS * 8 + (size_t)BKT_TILE * 2;
+constexpr size_t BKT_APPLY_SMEM = (size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4;
+
+struct BucketLayout {
+    uint32_t first[F_MAXT + 1];   // table i owns buckets [first[i], first[i+1]) of the record store
+    uint32_t cap;                 // records per bucket (<= 65535: a 16-bit lane cannot overflow)
+    int n_tables;
+};
+
+// 1. group the bins of table blockIdx.y held by 16 Ki consecutive positions by bucket (counting sort in shared
+//    memory), reserve room in each bucket with one atomicAdd per (CTA, bucket), and write the records
+//    (position << 15 | bin within bucket) as runs of consecutive addresses.
+__global__ void __launch_bounds__(1024, 1)
+k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, BucketLayout L, unsigned long long* __restrict__ records,
+            uint32_t* __restrict__ cursors, Ctrl* ctrl)
+{
+    extern __shared__ __align__(16) unsigned char bk_raw[];
+    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(bk_raw);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sorted + BKT_TILE);   // count, later the run's index in its bucket
+    uint32_t* loc = hist + BKT_MAX_BUCKETS;                            // exclusive offset of the bucket's run in `sorted`
+    uint16_t* sbk = reinterpret_cast<uint16_t*>(loc + BKT_MAX_BUCKETS);
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const int t = blockIdx.y;
+    const uint32_t nb = L.first[t + 1] - L.first[t];
+    const uint32_t p0 = blockIdx.x * (uint32_t)BKT_TILE;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < nb; i += 1024) hist[i] = 0;
+    __syncthreads();
+    constexpr int PER = BKT_TILE / 1024;
+    uint32_t bin[PER], rk[PER / 2];
+    const uint32_t* src = bins + (size_t)t * stride;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        uint32_t p = p0 + j * 1024 + tid;
+        bin[j] = p < n_pos ? __ldcs(src + p) : BIN_NONE;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        uint32_t r = bin[j] != BIN_NONE ? atomicAdd(&hist[bin[j] >> BKT_SHIFT], 1u) : 0u;   // rank inside this CTA's run
+        if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
+    }
+    __syncthreads();
+    // exclusive scan of the bucket counts: 6 consecutive buckets per thread
+    constexpr int BPT = BKT_MAX_BUCKETS / 1024;
+    uint32_t c[BPT], mine = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        uint32_t b = tid * BPT + q;
+        c[q] = b < nb ? hist[b] : 0;
+        mine += c[q];
+    }
+    uint32_t incl = mine;
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = s_warp[lane], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += u;
+        }
+        s_warp[lane] = w - v;
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    uint32_t at = s_warp[wid] + incl - mine;
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        uint32_t b = tid * BPT + q;
+        if (b < nb) {
+            loc[b] = at;
+            if (c[q]) hist[b] = atomicAdd(&cursors[L.first[t] + b], c[q]);
+        }
+        at += c[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        if (bin[j] == BIN_NONE) continue;
+        uint32_t b = bin[j] >> BKT_SHIFT;
+        uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
+        uint32_t s = loc[b] + r;
+        sorted[s] = ((unsigned long long)(p0 + j * 1024 + tid) << BKT_SHIFT) | (bin[j] & (BKT_BINS - 1));
+        sbk[s] = (uint16_t)b;
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    bool over = false;
+    for (uint32_t s = tid; s < total; s += 1024) {
+        uint32_t b = sbk[s];
+        uint32_t idx = hist[b] + (s - loc[b]);
+        if (idx < L.cap) records[(size_t)(L.first[t] + b) * L.cap + idx] = sorted[s];
+        else over = true;
+    }
+    if (over) atomicExch(&ctrl->overflow, 1ull);
+}
+
+// 2. one CTA per bucket: touch counts (16-bit lanes) and first-toucher positions in shared memory, then the sweep:
+//    counter = min(cap, old + touches) (ByteStorage::add storage.hh:599-603, NibbleStorage::add :345-351,
+//    BitStorage::test_and_set_bits :176-195), newly occupied bins mark their first toucher in `newbits`.
+template <int KIND>
+__global__ void __launch_bounds__(1024, 1)
+k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ records, const uint32_t* __restrict__ cursors,
+        uint32_t* __restrict__ newbits, uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, SatBits sb)
+{
+    extern __shared__ __align__(16) uint32_t ap_smem[];
+    uint32_t* cnt = ap_smem;                    // BKT_BINS / 2 words, two 16-bit lanes each
+    uint32_t* minpos = ap_smem + BKT_BINS / 2;  // BKT_BINS words
+    if (ctrl->overflow) return;                 // the chunk is redone by the delta passes; leave the tables alone
+    const uint32_t n = cursors[blockIdx.x];
+    if (n == 0) return;
+    int t = 0;
+    uint32_t first_t = 0;
+    const uint8_t* sat = nullptr;
+#pragma unroll
+    for (int i = 0; i < F_MAXT; i++)   // compile-time bound: the parameter arrays stay in constant space
+        if (i < L.n_tables && blockIdx.x >= L.first[i]) {
+            t = i;
+            first_t = L.first[i];
+            sat = sb.t[i];
+        }
+    const uint32_t bin0 = (blockIdx.x - first_t) << BKT_SHIFT;
+    const uint32_t tid = threadIdx.x;
+    {
+        uint4* z = reinterpret_cast<uint4*>(cnt);
+        for (uint32_t i = tid; i < BKT_BINS / 8; i += 1024) z[i] = make_uint4(0, 0, 0, 0);
+        uint4* f = reinterpret_cast<uint4*>(minpos);
+        for (uint32_t i = tid; i < BKT_BINS / 4; i += 1024) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncthreads();
+    const unsigned long long* src = records + (size_t)blockIdx.x * L.cap;
+    for (uint32_t e0 = 0; e0 < n; e0 += 4096) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t e = e0 + j * 1024 + tid;
+            v[j] = e < n ? __ldcs(src + e) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (v[j] == ~0ull) continue;
+            uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
+            atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+            atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+        }
+    }
+    __syncthreads();
+    unsigned n_new = 0, n_sat = 0, n_cross = 0, n_uni = 0;
+    const uint64_t size = S.sizes[t];
+    uint8_t* table = S.tables[t];
+    for (uint32_t g = tid; g < BKT_BINS / 8; g += 1024) {
+        const uint32_t b0 = bin0 + g * 8;
+        if (b0 >= size) break;
+        const uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
+        if (!(c4.x | c4.y | c4.z | c4.w)) continue;
+        const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+        unsigned newm = 0, crossm = 0;
+        if (KIND == BYTE) {
+            uint64_t* tp = reinterpret_cast<uint64_t*>(table + b0);
+            const uint64_t old64 = *tp;
+            uint64_t new64 = old64;
+            unsigned fullm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (!m) continue;
+                uint32_t s = (uint32_t)(old64 >> (8 * j)) & 255u, tt = s + m, nv = tt > 255u ? 255u : tt;
+                new64 = (new64 & ~(255ull << (8 * j))) | ((uint64_t)nv << (8 * j));
+                newm |= (unsigned)(s == 0) << j;
+                n_sat += tt > 255u;
+                crossm |= (unsigned)(tt >= 255u && s < 255u) << j;
+                fullm |= (unsigned)(nv == 255u) << j;
+            }
+            *tp = new64;
+            if (want_cross && fullm) {
+                unsigned m = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) m |= (unsigned)(((new64 >> (8 * j)) & 255u) == 255u) << j;
+                const_cast<uint8_t*>(sat)[b0 >> 3] = (uint8_t)m;
+            }
+            n_cross += __popc(crossm);
+            if (want_cross && crossm) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!((crossm >> j) & 1u)) continue;
+                    unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+                    if (at < list_cap) binlist[at] = BL_CROSS | (((old64 >> (8 * j)) & 255ull) << 48) | ht_key((uint64_t)(b0 + j), t);
+                }
+            }
+        } else if (KIND == NIBBLE) {
+            uint32_t* tp = reinterpret_cast<uint32_t*>(table + (b0 >> 1));
+            const uint32_t old32 = *tp;
+            uint32_t new32 = old32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (!m) continue;
+                const uint32_t sh = (j >> 1) * 8 + ((j & 1) ? 0 : 4);   // even bin -> high nibble
+                uint32_t s = (old32 >> sh) & 15u, tt = s + m, nv = tt > 15u ? 15u : tt;
+                new32 = (new32 & ~(15u << sh)) | (nv << sh);
+                newm |= (unsigned)(s == 0) << j;
+            }
+            *tp = new32;
+        } else {
+            uint8_t* tp = table + (b0 >> 3);
+            const unsigned old8 = *tp;
+            unsigned touched = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) touched |= (unsigned)(((cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) != 0) << j;
+            newm = touched & ~old8;
+            if (newm) *tp = (uint8_t)(old8 | touched);
+        }
+        n_new += __popc(newm);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!((newm >> j) & 1u)) continue;
+            const uint32_t p = minpos[g * 8 + j];
+            const uint32_t bit = 1u << (p & 31);
+            n_uni += !(atomicOr(&newbits[p >> 5], bit) & bit);
+        }
+    }
+    // one set of counter updates per CTA
+    __shared__ unsigned s_tot[4];
+    if (tid < 4) s_tot[tid] = 0;
+    __syncthreads();
+    n_new = __reduce_add_sync(0xffffffffu, n_new);
+    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
+    n_uni = __reduce_add_sync(0xffffffffu, n_uni);
+    if ((tid & 31) == 0) {
+        if (n_new) atomicAdd(&s_tot[0], n_new);
+        if (n_sat) atomicAdd(&s_tot[1], n_sat);
+        if (n_cross) atomicAdd(&s_tot[2], n_cross);
+        if (n_uni) atomicAdd(&s_tot[3], n_uni);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_tot[0]) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)s_tot[0]);
+            atomicAdd(&ctrl->n_new_t[t], (unsigned long long)s_tot[0]);
+            if (t == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)s_tot[0]);
+        }
+        if (s_tot[1]) atomicAdd(&ctrl->n_sat, (unsigned long long)s_tot[1]);
+        if (s_tot[2]) atomicAdd(&ctrl->n_cross, (unsigned long long)s_tot[2]);
+        if (s_tot[3]) atomicAdd(&ctrl->n_unique, (unsigned long long)s_tot[3]);
+    }
+}
+
 // chunk-relative 32-bit read offsets from the caller's 64-bit ones, clipped to the chunk [b0, b1)
 __global__ void k_clip_offsets(const uint64_t* __restrict__ off64, uint32_t n, uint64_t b0, uint64_t b1, uint32_t* __restrict__ out)
 {
@@ -1287,9 +1561,6 @@ __global__ void k_clip_offsets(const uint64_t* __restrict__ off64, uint32_t n, u
 //    k_fold, rebuilt by k_build_satbits after uploads/merges), 12.5 MB per 1e8-bin table: L2-resident, so nearly
 //    every k-mer is dismissed after one cached load.  Reported: k-mers whose N bytes are all 255 now, and — when
 //    bins reached 255 inside this chunk — every k-mer touching such a bin (the host needs all their positions).
-struct SatBits {
-    const uint8_t* t[F_MAXT];
-};
 
 __global__ void k_build_satbits(const uint8_t* __restrict__ table, uint64_t n_groups, uint8_t* __restrict__ satbits)
 {

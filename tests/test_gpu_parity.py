@@ -52,7 +52,7 @@ def test_gpu_golden_cases_delta_many_blocks():
     """All reference goldens through the delta+fold path with ~2k-bin blocks (many blocks per table)."""
     import subprocess, sys
     env = dict(os.environ, KMGPU_DELTA_BLOCK_BINS="2048", KMGPU_DELTA_MAX_PASSES="1000000", KMGPU_CHUNK_BASES="65536",
-               KMGPU_COLD_MIN_NEW="64")
+               KMGPU_COLD_MIN_NEW="64", KMGPU_BUCKETS="0")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
                         "test_gpu_matches_reference_golden and not C1 and not 25k"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -65,7 +65,8 @@ def _same_state(g, o, n_tables):
 
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
-@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps"])
+@pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps", "buckets",
+                                   "buckets-overflow"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
@@ -77,11 +78,16 @@ def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
         elif chunk == "cas-8192":   # compare-and-swap path, all tables in one pass
             env.update(KMGPU_DELTA="0", KMGPU_CHUNK_BASES="8192")
         elif chunk == "delta-cold":   # delta+fold path, per-block ("cold chunk") ranked-bitmap resolution forced
-            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768")
+            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_BUCKETS="0")
+        elif chunk == "buckets":   # bucket path (records grouped by 32 Ki-bin bucket, applied in shared memory)
+            env.update(KMGPU_CHUNK_BASES="16384")
+        elif chunk == "buckets-overflow":   # bucket path with buckets far too small: every chunk falls back to the delta passes
+            env.update(KMGPU_CHUNK_BASES="16384", KMGPU_BUCKET_CAP="64")
         elif chunk == "delta-cold-stamps":   # same, through the stamp hash tables (blocks beyond 2^26 bins take this form)
-            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_COLD_RANK="0")
+            env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_COLD_RANK="0",
+                       KMGPU_BUCKETS="0")
         elif chunk == "delta-blocks":   # delta+fold path with many blocks per table
-            env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384")
+            env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384", KMGPU_BUCKETS="0")
         else:
             env.update(KMGPU_CHUNK_BASES=str(chunk))
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
@@ -290,3 +296,26 @@ def test_full_size_properties_C1():
     e = make_gpu("Countgraph", 20, sizes)
     e.merge(g)
     assert md5(e.table(0)) == md5(t0) and e.n_occupied() == g.n_occupied()
+
+
+@pytest.mark.parametrize("cls", list(ol.CLASSES))
+def test_bucket_path_many_buckets(cls):
+    """Tables of ~70 buckets each, chunks small enough for the bucket path: counters, n_occupied, n_unique_kmers and the
+    bigcount map against the oracle, state carried across calls (the second call meets occupied and saturating bins)."""
+    kind, hk, _ = ol.CLASSES[cls]
+    k = 21 if hk == ol.TWOBIT else 35
+    sizes = ol.primes_near_x(4, 2300000)
+    g = make_gpu(cls, k, sizes)
+    o = ol.Oracle(cls, k, sizes)
+    if kind == ol.BYTE:
+        g.set_use_bigcount(True)
+        o.set_use_bigcount(True)
+    for part in range(3):
+        reads = synth_reads(50 + part, 3000, 150, 20000, err=0.01, with_n=True) + ["ACGTTGCA" * 40] * 150
+        assert g.consume_reads(reads) == o.consume_reads(reads)
+        _same_state(g, o, 4)
+    if kind == ol.BYTE:
+        gk, gv = g.bigcounts()
+        want = o.bigcounts()
+        assert len(want) > 0 and dict(zip(gk.tolist(), gv.tolist())) == want
+    g.close()
