@@ -1072,7 +1072,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         // bucket path: group the updates by 32 Ki-bin bucket, apply each bucket in shared memory (counters, n_occupied,
         // first touchers -> newbits / n_unique, saturation bookkeeping in one sweep)
         if (!h->bucket_attr_set) {
-            CK(cudaFuncSetAttribute(k_bucketize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_SORT_SMEM));
+            CK(cudaFuncSetAttribute(k_bucketize<BKT_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkt_sort_smem(BKT_TILE)));
             CK(cudaFuncSetAttribute(k_apply<BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
             CK(cudaFuncSetAttribute(k_apply<NIBBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
             CK(cudaFuncSetAttribute(k_apply<BIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
@@ -1089,11 +1089,12 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         memset(&sb, 0, sizeof sb);
         if (want_cross)
             for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
-        k_bucketize<<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), 1024, BKT_SORT_SMEM, st>>>(h->d_bins.p, stride, in.n_pos, BL, h->d_records.p,
-                                                                                                 h->d_cursors.p, h->d_ctrl);
+        k_bucketize<BKT_TILE><<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), BKT_TILE / BKT_PER, bkt_sort_smem(BKT_TILE), st>>>(
+            h->d_bins.p, stride, in.n_pos, BL, h->d_records.p, h->d_cursors.p, h->d_ctrl);
         if (h->kind == BYTE) launch_apply<BYTE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross, sb);
         else if (h->kind == NIBBLE) launch_apply<NIBBLE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
         else launch_apply<BIT>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
+        k_popc<<<(unsigned)std::min<size_t>((nb_words + 255) / 256, 148 * 8), 256, 0, st>>>(h->d_newbits.p, nb_words, &h->d_ctrl->n_unique);
         CK(cudaEventRecord(h->ev1, st));
         CK(cudaGetLastError());
         if (between) CKR(between());
@@ -1101,8 +1102,8 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->ingest_ms += ms;
-        h->ingest_launches += 3;
-        h->all_launches += 3;
+        h->ingest_launches += 4;
+        h->all_launches += 4;
         Ctrl c = *h->h_ctrl;
         res->n_kmers += c.n_kmers;
         kmers_counted = true;

@@ -1290,10 +1290,13 @@ struct SatBits {
 
 constexpr int BKT_SHIFT = 15;
 constexpr uint32_t BKT_BINS = 1u << BKT_SHIFT;   // bins per bucket
-constexpr int BKT_TILE = 16384;                  // positions per k_bucketize CTA
 constexpr int BKT_MAX_BUCKETS = 6144;            // per table (shared-memory histogram of k_bucketize)
-constexpr size_t BKT_SORT_SMEM = (size_t)BKT_TILE * 8 + (size_t)BKT_MAX_BUCKETS * 8 + (size_t)BKT_TILE * 2;
+constexpr int BKT_PER = 16;                      // positions per k_bucketize thread
+constexpr int BKT_TILE = 16384;                  // positions per k_bucketize CTA (smaller tiles: more reservations, shorter runs — measured slower)
 constexpr size_t BKT_APPLY_SMEM = (size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4;
+// k_bucketize<T> works on T positions with T/16 threads: sorted records (4 B) + their destinations (4 B) + histogram
+// + run offsets (u16 would do; u32 keeps the atomics simple)
+constexpr size_t bkt_sort_smem(int tile) { return (size_t)tile * 8 + (size_t)BKT_MAX_BUCKETS * 12; }
 
 struct BucketLayout {
     uint32_t first[F_MAXT + 1];   // table i owns buckets [first[i], first[i+1]) of the record store
@@ -1301,42 +1304,43 @@ struct BucketLayout {
     int n_tables;
 };
 
-// 1. group the bins of table blockIdx.y held by 16 Ki consecutive positions by bucket (counting sort in shared
+// 1. group the bins of table blockIdx.y held by T consecutive positions by bucket (counting sort in shared
 //    memory), reserve room in each bucket with one atomicAdd per (CTA, bucket), and write the records
 //    (position << 15 | bin within bucket) as runs of consecutive addresses.
-__global__ void __launch_bounds__(1024, 1)
+template <int T>
+__global__ void __launch_bounds__(T / BKT_PER, 65536 / (T / BKT_PER) / 64)
 k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, BucketLayout L, unsigned long long* __restrict__ records,
             uint32_t* __restrict__ cursors, Ctrl* ctrl)
 {
+    constexpr int NT = T / BKT_PER;              // threads
+    constexpr int BPT = (BKT_MAX_BUCKETS + NT - 1) / NT;
     extern __shared__ __align__(16) unsigned char bk_raw[];
-    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(bk_raw);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(sorted + BKT_TILE);   // count, later the run's index in its bucket
-    uint32_t* loc = hist + BKT_MAX_BUCKETS;                            // exclusive offset of the bucket's run in `sorted`
-    uint16_t* sbk = reinterpret_cast<uint16_t*>(loc + BKT_MAX_BUCKETS);
+    uint2* stage = reinterpret_cast<uint2*>(bk_raw);          // per slot, grouped by bucket: {position in tile << 15 | bin in
+                                                              // bucket, bucket << 16 | rank in this CTA's run}
+    uint2* run = stage + T;                                   // per bucket: {offset of the run in `stage`, its first index in the bucket}
+    uint32_t* hist = reinterpret_cast<uint32_t*>(run + BKT_MAX_BUCKETS);
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const int t = blockIdx.y;
     const uint32_t nb = L.first[t + 1] - L.first[t];
-    const uint32_t p0 = blockIdx.x * (uint32_t)BKT_TILE;
+    const uint32_t p0 = blockIdx.x * (uint32_t)T;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < nb; i += 1024) hist[i] = 0;
-    __syncthreads();
-    constexpr int PER = BKT_TILE / 1024;
-    uint32_t bin[PER], rk[PER / 2];
+    uint32_t bin[BKT_PER], rk[BKT_PER / 2];
     const uint32_t* src = bins + (size_t)t * stride;
 #pragma unroll
-    for (int j = 0; j < PER; j++) {
-        uint32_t p = p0 + j * 1024 + tid;
+    for (int j = 0; j < BKT_PER; j++) {
+        uint32_t p = p0 + j * NT + tid;
         bin[j] = p < n_pos ? __ldcs(src + p) : BIN_NONE;
     }
+    for (uint32_t i = tid; i < nb; i += NT) hist[i] = 0;
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < PER; j++) {
+    for (int j = 0; j < BKT_PER; j++) {
         uint32_t r = bin[j] != BIN_NONE ? atomicAdd(&hist[bin[j] >> BKT_SHIFT], 1u) : 0u;   // rank inside this CTA's run
         if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
     }
     __syncthreads();
-    // exclusive scan of the bucket counts: 6 consecutive buckets per thread
-    constexpr int BPT = BKT_MAX_BUCKETS / 1024;
+    // exclusive scan of the bucket counts: BPT consecutive buckets per thread
     uint32_t c[BPT], mine = 0;
 #pragma unroll
     for (int q = 0; q < BPT; q++) {
@@ -1354,7 +1358,7 @@ k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, 
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        uint32_t v = s_warp[lane], w = v;
+        uint32_t v = lane < NT / 32 ? s_warp[lane] : 0, w = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
@@ -1364,41 +1368,55 @@ k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, 
         if (lane == 31) s_total = w;
     }
     __syncthreads();
-    uint32_t at = s_warp[wid] + incl - mine;
+    // run offsets, and one reservation per non-empty run: the atomics are in flight while the records are placed
+    uint32_t at = s_warp[wid] + incl - mine, gbase[BPT];
 #pragma unroll
     for (int q = 0; q < BPT; q++) {
         uint32_t b = tid * BPT + q;
-        if (b < nb) {
-            loc[b] = at;
-            if (c[q]) hist[b] = atomicAdd(&cursors[L.first[t] + b], c[q]);
-        }
+        if (b < nb) run[b].x = at;
+        gbase[q] = c[q] ? atomicAdd(&cursors[L.first[t] + b], c[q]) : 0u;
         at += c[q];
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < PER; j++) {
+    for (int j = 0; j < BKT_PER; j++) {
         if (bin[j] == BIN_NONE) continue;
-        uint32_t b = bin[j] >> BKT_SHIFT;
-        uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
-        uint32_t s = loc[b] + r;
-        sorted[s] = ((unsigned long long)(p0 + j * 1024 + tid) << BKT_SHIFT) | (bin[j] & (BKT_BINS - 1));
-        sbk[s] = (uint16_t)b;
+        const uint32_t b = bin[j] >> BKT_SHIFT;
+        const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
+        stage[run[b].x + r] = make_uint2(((uint32_t)(j * NT + tid) << BKT_SHIFT) | (bin[j] & (BKT_BINS - 1)), (b << 16) | r);
+    }
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        uint32_t b = tid * BPT + q;
+        if (b < nb) run[b].y = gbase[q];
     }
     __syncthreads();
     const uint32_t total = s_total;
+    const size_t base = (size_t)L.first[t] * L.cap;
     bool over = false;
-    for (uint32_t s = tid; s < total; s += 1024) {
-        uint32_t b = sbk[s];
-        uint32_t idx = hist[b] + (s - loc[b]);
-        if (idx < L.cap) records[(size_t)(L.first[t] + b) * L.cap + idx] = sorted[s];
-        else over = true;
+    for (uint32_t s = tid; s < total; s += NT) {
+        const uint2 m = stage[s];
+        const uint32_t b = m.y >> 16, idx = run[b].y + (m.y & 0xFFFFu);
+        if (idx < L.cap)
+            records[base + (size_t)b * L.cap + idx] = ((unsigned long long)(p0 + (m.x >> BKT_SHIFT)) << BKT_SHIFT) | (m.x & (BKT_BINS - 1));
+        else
+            over = true;
     }
     if (over) atomicExch(&ctrl->overflow, 1ull);
 }
 
+__global__ void k_popc(const uint32_t* __restrict__ words, uint64_t n, unsigned long long* out)
+{
+    unsigned cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) cnt += __popc(words[i]);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
 // 2. one CTA per bucket: touch counts (16-bit lanes) and first-toucher positions in shared memory, then the sweep:
 //    counter = min(cap, old + touches) (ByteStorage::add storage.hh:599-603, NibbleStorage::add :345-351,
-//    BitStorage::test_and_set_bits :176-195), newly occupied bins mark their first toucher in `newbits`.
+//    BitStorage::test_and_set_bits :176-195), newly occupied bins mark their first toucher in `newbits`
+//    (n_unique_kmers = the number of marks, counted by k_popc afterwards).
 template <int KIND>
 __global__ void __launch_bounds__(1024, 1)
 k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ records, const uint32_t* __restrict__ cursors,
@@ -1422,6 +1440,21 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
         }
     const uint32_t bin0 = (blockIdx.x - first_t) << BKT_SHIFT;
     const uint32_t tid = threadIdx.x;
+    const uint64_t size = S.sizes[t];
+    uint8_t* table = S.tables[t];
+    // the thread's four 8-bin groups of the table are fetched now and used after the records have been counted
+    constexpr int GPT = BKT_BINS / 8 / 1024;
+    uint64_t oldv[GPT];
+#pragma unroll
+    for (int q = 0; q < GPT; q++) {
+        const uint32_t b0 = bin0 + (q * 1024 + tid) * 8;
+        oldv[q] = 0;
+        if (b0 < size) {
+            if (KIND == BYTE) oldv[q] = __ldcs(reinterpret_cast<const unsigned long long*>(table + b0));
+            else if (KIND == NIBBLE) oldv[q] = __ldcs(reinterpret_cast<const uint32_t*>(table + (b0 >> 1)));
+            else oldv[q] = __ldcs(table + (b0 >> 3));
+        }
+    }
     {
         uint4* z = reinterpret_cast<uint4*>(cnt);
         for (uint32_t i = tid; i < BKT_BINS / 8; i += 1024) z[i] = make_uint4(0, 0, 0, 0);
@@ -1430,15 +1463,15 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
     }
     __syncthreads();
     const unsigned long long* src = records + (size_t)blockIdx.x * L.cap;
-    for (uint32_t e0 = 0; e0 < n; e0 += 4096) {
-        unsigned long long v[4];
+    for (uint32_t e0 = 0; e0 < n; e0 += 8192) {
+        unsigned long long v[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             uint32_t e = e0 + j * 1024 + tid;
             v[j] = e < n ? __ldcs(src + e) : ~0ull;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             if (v[j] == ~0ull) continue;
             uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
             atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
@@ -1446,19 +1479,18 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
         }
     }
     __syncthreads();
-    unsigned n_new = 0, n_sat = 0, n_cross = 0, n_uni = 0;
-    const uint64_t size = S.sizes[t];
-    uint8_t* table = S.tables[t];
-    for (uint32_t g = tid; g < BKT_BINS / 8; g += 1024) {
+    unsigned n_new = 0, n_sat = 0, n_cross = 0;
+#pragma unroll
+    for (int q = 0; q < GPT; q++) {
+        const uint32_t g = q * 1024 + tid;
         const uint32_t b0 = bin0 + g * 8;
-        if (b0 >= size) break;
+        if (b0 >= size) continue;
         const uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
         if (!(c4.x | c4.y | c4.z | c4.w)) continue;
         const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
         unsigned newm = 0, crossm = 0;
         if (KIND == BYTE) {
-            uint64_t* tp = reinterpret_cast<uint64_t*>(table + b0);
-            const uint64_t old64 = *tp;
+            const uint64_t old64 = oldv[q];
             uint64_t new64 = old64;
             unsigned fullm = 0;
 #pragma unroll
@@ -1472,7 +1504,7 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
                 crossm |= (unsigned)(tt >= 255u && s < 255u) << j;
                 fullm |= (unsigned)(nv == 255u) << j;
             }
-            *tp = new64;
+            *reinterpret_cast<uint64_t*>(table + b0) = new64;
             if (want_cross && fullm) {
                 unsigned m = 0;
 #pragma unroll
@@ -1489,8 +1521,7 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
                 }
             }
         } else if (KIND == NIBBLE) {
-            uint32_t* tp = reinterpret_cast<uint32_t*>(table + (b0 >> 1));
-            const uint32_t old32 = *tp;
+            const uint32_t old32 = (uint32_t)oldv[q];
             uint32_t new32 = old32;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -1501,38 +1532,34 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
                 new32 = (new32 & ~(15u << sh)) | (nv << sh);
                 newm |= (unsigned)(s == 0) << j;
             }
-            *tp = new32;
+            *reinterpret_cast<uint32_t*>(table + (b0 >> 1)) = new32;
         } else {
-            uint8_t* tp = table + (b0 >> 3);
-            const unsigned old8 = *tp;
+            const unsigned old8 = (unsigned)oldv[q];
             unsigned touched = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) touched |= (unsigned)(((cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) != 0) << j;
             newm = touched & ~old8;
-            if (newm) *tp = (uint8_t)(old8 | touched);
+            if (newm) table[b0 >> 3] = (uint8_t)(old8 | touched);
         }
         n_new += __popc(newm);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (!((newm >> j) & 1u)) continue;
             const uint32_t p = minpos[g * 8 + j];
-            const uint32_t bit = 1u << (p & 31);
-            n_uni += !(atomicOr(&newbits[p >> 5], bit) & bit);
+            atomicOr(&newbits[p >> 5], 1u << (p & 31));
         }
     }
     // one set of counter updates per CTA
-    __shared__ unsigned s_tot[4];
-    if (tid < 4) s_tot[tid] = 0;
+    __shared__ unsigned s_tot[3];
+    if (tid < 3) s_tot[tid] = 0;
     __syncthreads();
     n_new = __reduce_add_sync(0xffffffffu, n_new);
     n_sat = __reduce_add_sync(0xffffffffu, n_sat);
     n_cross = __reduce_add_sync(0xffffffffu, n_cross);
-    n_uni = __reduce_add_sync(0xffffffffu, n_uni);
     if ((tid & 31) == 0) {
         if (n_new) atomicAdd(&s_tot[0], n_new);
         if (n_sat) atomicAdd(&s_tot[1], n_sat);
         if (n_cross) atomicAdd(&s_tot[2], n_cross);
-        if (n_uni) atomicAdd(&s_tot[3], n_uni);
     }
     __syncthreads();
     if (tid == 0) {
@@ -1543,7 +1570,6 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
         }
         if (s_tot[1]) atomicAdd(&ctrl->n_sat, (unsigned long long)s_tot[1]);
         if (s_tot[2]) atomicAdd(&ctrl->n_cross, (unsigned long long)s_tot[2]);
-        if (s_tot[3]) atomicAdd(&ctrl->n_unique, (unsigned long long)s_tot[3]);
     }
 }
 
