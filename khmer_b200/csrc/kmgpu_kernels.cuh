@@ -1463,15 +1463,16 @@ k_apply(SketchDev S, BucketLayout L, const unsigned long long* __restrict__ reco
     }
     __syncthreads();
     const unsigned long long* src = records + (size_t)blockIdx.x * L.cap;
-    for (uint32_t e0 = 0; e0 < n; e0 += 8192) {
-        unsigned long long v[8];
+    constexpr int RIF = 16;   // records in flight per thread: the loop is latency-bound at one CTA per SM
+    for (uint32_t e0 = 0; e0 < n; e0 += RIF * 1024) {
+        unsigned long long v[RIF];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < RIF; j++) {
             uint32_t e = e0 + j * 1024 + tid;
             v[j] = e < n ? __ldcs(src + e) : ~0ull;
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < RIF; j++) {
             if (v[j] == ~0ull) continue;
             uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
             atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
