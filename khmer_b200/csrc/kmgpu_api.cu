@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -911,11 +912,23 @@ static inline void big_events(kmgpu_sketch* h, uint64_t hash, uint32_t count)
 static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Input& in, uint64_t stride, uint64_t n_list, uint64_t n_cross)
 {
     cudaStream_t st = h->stream;
+    // the small workspaces start at a size that rarely has to grow: a regrowth is a cudaFree + cudaMalloc, i.e. a device
+    // synchronisation plus milliseconds of driver time in the middle of the stream
+    constexpr uint64_t WS_MIN = 1ull << 20;
+    static const bool dbg = env_u64("KMGPU_DEBUG", 0) != 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what, uint64_t n) {
+        if (!dbg) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[kmgpu] bigcount %s: n=%llu t=%.3f ms\n", what, (unsigned long long)n,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
+    lap("begin (n_cross)", n_cross);
     uint64_t slots = 1024;
     if (n_cross) {
         slots = pow2_at_least(2 * n_cross);
-        CKR(h->d_htkeys.ensure(slots));
-        CKR(h->d_htvals.ensure(slots));
+        CKR(h->d_htkeys.ensure(std::max<uint64_t>(slots, WS_MIN)));
+        CKR(h->d_htvals.ensure(std::max<uint64_t>(slots, WS_MIN)));
         CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
         unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
         k_list_register<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, BL_CROSS, h->d_htkeys.p, h->d_htvals.p, slots - 1, nullptr, 1);
@@ -940,14 +953,15 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
     const uint64_t n_rec = h->h_ctrl->n_events;
+    lap("scan done (n_rec)", n_rec);
     if (n_rec > cap) return fail(KMGPU_ECUDA, "internal: bigcount scan overflow");
     if (n_rec == 0) return KMGPU_OK;
     const unsigned gr = (unsigned)((n_rec + 255) / 256);
     // 2. stream position of the saturating touch of every crossing bin (radix select over the reported touches)
     uint32_t* Tarr = nullptr;
     if (n_cross) {
-        CKR(h->d_sel.ensure(3 * slots));
-        CKR(h->d_recslot.ensure(n_rec * F_MAXT));
+        CKR(h->d_sel.ensure(std::max<uint64_t>(3 * slots, WS_MIN)));
+        CKR(h->d_recslot.ensure(std::max<uint64_t>(n_rec * F_MAXT, 4 * WS_MIN)));
         SelState ss{h->d_sel.p, h->d_sel.p + slots, h->d_sel.p + 2 * slots};
         const unsigned gsl = (unsigned)((slots + 255) / 256);
         k_sel_slots<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->dev, h->d_htkeys.p, slots - 1, h->d_recslot.p);
@@ -963,8 +977,8 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
     }
     // 3. decide and aggregate per k-mer
     uint64_t evslots = pow2_at_least(2 * n_rec);
-    CKR(h->d_evkeys.ensure(evslots));
-    CKR(h->d_evvals.ensure(2 * evslots));
+    CKR(h->d_evkeys.ensure(std::max<uint64_t>(evslots, WS_MIN)));
+    CKR(h->d_evvals.ensure(std::max<uint64_t>(2 * evslots, 2 * WS_MIN)));
     CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, evslots * 8, st));
     CK(cudaMemsetAsync(h->d_evvals.p, 0, evslots * 4, st));
     CK(cudaMemsetAsync(h->d_evvals.p + evslots, 0xFF, evslots * 4, st));
@@ -976,9 +990,10 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
     const uint64_t n_distinct = h->h_ctrl->n_unique;
+    lap("decided (n_distinct)", n_distinct);
     if (n_distinct == 0) return KMGPU_OK;
-    CKR(h->d_evout.ensure(n_distinct));
-    CKR(h->h_evout.ensure(n_distinct));
+    CKR(h->d_evout.ensure(std::max<uint64_t>(n_distinct, WS_MIN / 4)));
+    CKR(h->h_evout.ensure(std::max<uint64_t>(n_distinct, WS_MIN / 4)));
     k_ev_compact<<<(unsigned)((evslots + 255) / 256), 256, 0, st>>>(ev, h->d_evout.p, h->d_ctrl);
     h->all_launches += 1;
     CK(cudaGetLastError());
@@ -1119,6 +1134,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
             return KMGPU_OK;
         }
         // a bucket overflowed (heavily repeated k-mers): nothing was applied; redo the chunk with the delta passes
+        if (env_u64("KMGPU_DEBUG", 0)) fprintf(stderr, "[kmgpu] bucket overflow (cap %u, %u positions): chunk redone by the delta passes\n", BL.cap, in.n_pos);
         CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
         CK(cudaEventRecord(h->ev0, st));
     }
