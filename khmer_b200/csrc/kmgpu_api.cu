@@ -1083,7 +1083,8 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     bool kmers_counted = false;
     BucketLayout BL;
-    if (plan_buckets(h, in.n_pos, &BL)) {
+    bool use_buckets = plan_buckets(h, in.n_pos, &BL);
+    if (use_buckets) {
         // bucket path: group the updates by 32 Ki-bin bucket, apply each bucket in shared memory (counters, n_occupied,
         // first touchers -> newbits / n_unique, saturation bookkeeping in one sweep)
         if (!h->bucket_attr_set) {
@@ -1094,7 +1095,13 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
             h->bucket_attr_set = true;
         }
         const uint32_t n_buckets = BL.first[h->nt];
-        CKR(h->d_records.ensure((size_t)n_buckets * BL.cap));
+        if (h->d_records.ensure((size_t)n_buckets * BL.cap) != KMGPU_OK) {   // no room for the record store: delta passes
+            cudaGetLastError();
+            use_buckets = false;
+        }
+    }
+    if (use_buckets) {
+        const uint32_t n_buckets = BL.first[h->nt];
         CKR(h->d_cursors.ensure(n_buckets));
         const size_t nb_words = (in.n_pos + 31) / 32;
         CKR(h->d_newbits.ensure(nb_words));
