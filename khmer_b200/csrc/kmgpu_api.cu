@@ -65,7 +65,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt)
 static uint64_t chunk_bases()
 {
     static uint64_t c = [] {
-        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 128ull << 20);
+        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 150000000ull);   // ~0.85 ms of every chunk does not depend on its size
         v = std::max<uint64_t>(TILE, std::min<uint64_t>(v, 1ull << 31));
         return (v / TILE) * TILE;
     }();
@@ -1521,7 +1521,8 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     // (half of the others when the cap leaves that freedom) and the copy of chunk i+1 hides behind the ingest of chunk i.
     std::vector<uint64_t> starts(1, 0);
     {
-        const uint64_t total = last - first, cap = chunk_bases(), n = (total + cap - 1) / cap;
+        // one chunk more than a device-resident batch would get as soon as that leaves chunk 0 at most half of the others
+        const uint64_t total = last - first, cap = chunk_bases(), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
         if (n >= 2) {
             uint64_t c0 = std::max<uint64_t>(total - (n - 1) * cap, total / (2 * n - 1));
             uint64_t c = (((total - c0) + (n - 2)) / (n - 1) + 31) & ~31ull;
