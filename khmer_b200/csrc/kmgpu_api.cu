@@ -65,7 +65,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt)
 static uint64_t chunk_bases()
 {
     static uint64_t c = [] {
-        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 150000000ull);   // ~0.85 ms of every chunk does not depend on its size
+        uint64_t v = env_u64("KMGPU_CHUNK_BASES", 152000000ull);   // ~0.85 ms of every chunk does not depend on its size
         v = std::max<uint64_t>(TILE, std::min<uint64_t>(v, 1ull << 31));
         return (v / TILE) * TILE;
     }();
@@ -1524,7 +1524,7 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
         // one chunk more than a device-resident batch would get as soon as that leaves chunk 0 at most half of the others
         const uint64_t total = last - first, cap = chunk_bases(), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
         if (n >= 2) {
-            uint64_t c0 = std::max<uint64_t>(total - (n - 1) * cap, total / (2 * n - 1));
+            uint64_t c0 = std::max<uint64_t>(total > (n - 1) * cap ? total - (n - 1) * cap : 0, total / (2 * n - 1));
             uint64_t c = (((total - c0) + (n - 2)) / (n - 1) + 31) & ~31ull;
             c = std::min(c, cap);
             c0 = total - (n - 1) * c;   // > 0: (n-1)*c < total since c0 was at least total/(2n-1) before rounding
