@@ -895,8 +895,9 @@ template <int HK, int SRC>
 static void launch_hashbins(bool pred, unsigned g, cudaStream_t st, const SketchDev& S, const SketchDev& M, HashCfg H, const Pred& P,
                             const Input& in, uint32_t* bins, uint64_t stride, Ctrl* ctrl)
 {
-    if (pred) k_hashbins<HK, SRC, true><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
-    else k_hashbins<HK, SRC, false><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
+    if (pred) k_hashbins<HK, SRC, true, 0><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
+    else if (S.n_tables == 4) k_hashbins<HK, SRC, false, 4><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);   // khmer's default N
+    else k_hashbins<HK, SRC, false, 0><<<g, THREADS, 0, st>>>(S, M, H, P, in, bins, stride, ctrl);
 }
 
 // ByteStorage::add tail (storage.hh:606-617) applied `count` times to one k-mer
@@ -1088,7 +1089,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         // bucket path: group the updates by 32 Ki-bin bucket, apply each bucket in shared memory (counters, n_occupied,
         // first touchers -> newbits / n_unique, saturation bookkeeping in one sweep)
         if (!h->bucket_attr_set) {
-            CK(cudaFuncSetAttribute(k_bucketize<BKT_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkt_sort_smem(BKT_TILE)));
+            CK(cudaFuncSetAttribute(k_bucketize<BKT_TILE, BKT_PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkt_sort_smem(BKT_TILE)));
             CK(cudaFuncSetAttribute(k_apply<BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
             CK(cudaFuncSetAttribute(k_apply<NIBBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
             CK(cudaFuncSetAttribute(k_apply<BIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BKT_APPLY_SMEM));
@@ -1111,7 +1112,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         memset(&sb, 0, sizeof sb);
         if (want_cross)
             for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
-        k_bucketize<BKT_TILE><<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), BKT_TILE / BKT_PER, bkt_sort_smem(BKT_TILE), st>>>(
+        k_bucketize<BKT_TILE, BKT_PER><<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), BKT_TILE / BKT_PER, bkt_sort_smem(BKT_TILE), st>>>(
             h->d_bins.p, stride, in.n_pos, BL, h->d_records.p, h->d_cursors.p, h->d_ctrl);
         if (h->kind == BYTE) launch_apply<BYTE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross, sb);
         else if (h->kind == NIBBLE) launch_apply<NIBBLE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);

@@ -744,7 +744,9 @@ __device__ __forceinline__ void red_add_half_lane(uint16_t* lanes, uint32_t idx)
 }
 
 // 1. hash every k-mer once and keep its bin in each table: bins[i * stride + pos] (BIN_NONE if not consumed)
-template <int HK, int SRC, bool PRED>
+// NT > 0: the number of tables is a compile-time constant (table loop unrolled, sizes and magics read as immediate
+// constant-bank operands); NT == 0: any number of tables.
+template <int HK, int SRC, bool PRED, int NT>
 __global__ void __launch_bounds__(THREADS)
 k_hashbins(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __restrict__ bins, uint64_t stride, Ctrl* ctrl)
 {
@@ -762,9 +764,17 @@ k_hashbins(SketchDev S, SketchDev M, HashCfg H, Pred P, Input in, uint32_t* __re
             consumed = !PRED || pred_pass(P, M, h);
         }
         n_k += consumed;
-        for (int i = 0; i < S.n_tables; i++) {
-            uint32_t b = consumed ? (uint32_t)mod_magic(h, S.sizes[i], S.magic[i]) : BIN_NONE;
-            __stcs(&bins[i * stride + t0 + lp], b);
+        if (NT > 0) {
+#pragma unroll
+            for (int i = 0; i < NT; i++) {
+                uint32_t b = consumed ? (uint32_t)mod_magic(h, S.sizes[i], S.magic[i]) : BIN_NONE;
+                __stcs(&bins[i * stride + t0 + lp], b);
+            }
+        } else {
+            for (int i = 0; i < S.n_tables; i++) {
+                uint32_t b = consumed ? (uint32_t)mod_magic(h, S.sizes[i], S.magic[i]) : BIN_NONE;
+                __stcs(&bins[i * stride + t0 + lp], b);
+            }
         }
     }
     tile_accumulate(sm, 0, n_k);
@@ -1291,7 +1301,7 @@ struct SatBits {
 constexpr int BKT_SHIFT = 15;
 constexpr uint32_t BKT_BINS = 1u << BKT_SHIFT;   // bins per bucket
 constexpr int BKT_MAX_BUCKETS = 6144;            // per table (shared-memory histogram of k_bucketize)
-constexpr int BKT_PER = 16;                      // positions per k_bucketize thread
+constexpr int BKT_PER = 16;                      // positions per k_bucketize thread (32 with half the threads: measured slower)
 constexpr int BKT_TILE = 16384;                  // positions per k_bucketize CTA (smaller tiles: more reservations, shorter runs — measured slower)
 constexpr size_t BKT_APPLY_SMEM = (size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4;
 // k_bucketize<T> works on T positions with T/16 threads: sorted records (4 B) + their destinations (4 B) + histogram
@@ -1307,12 +1317,12 @@ struct BucketLayout {
 // 1. group the bins of table blockIdx.y held by T consecutive positions by bucket (counting sort in shared
 //    memory), reserve room in each bucket with one atomicAdd per (CTA, bucket), and write the records
 //    (position << 15 | bin within bucket) as runs of consecutive addresses.
-template <int T>
-__global__ void __launch_bounds__(T / BKT_PER, 65536 / (T / BKT_PER) / 64)
+template <int T, int PER>
+__global__ void __launch_bounds__(T / PER, 1)
 k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, BucketLayout L, unsigned long long* __restrict__ records,
             uint32_t* __restrict__ cursors, Ctrl* ctrl)
 {
-    constexpr int NT = T / BKT_PER;              // threads
+    constexpr int NT = T / PER;              // threads
     constexpr int BPT = (BKT_MAX_BUCKETS + NT - 1) / NT;
     extern __shared__ __align__(16) unsigned char bk_raw[];
     uint2* stage = reinterpret_cast<uint2*>(bk_raw);          // per slot, grouped by bucket: {position in tile << 15 | bin in
@@ -1325,17 +1335,17 @@ k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, 
     const uint32_t nb = L.first[t + 1] - L.first[t];
     const uint32_t p0 = blockIdx.x * (uint32_t)T;
     const uint32_t tid = threadIdx.x;
-    uint32_t bin[BKT_PER], rk[BKT_PER / 2];
+    uint32_t bin[PER], rk[PER / 2];
     const uint32_t* src = bins + (size_t)t * stride;
 #pragma unroll
-    for (int j = 0; j < BKT_PER; j++) {
+    for (int j = 0; j < PER; j++) {
         uint32_t p = p0 + j * NT + tid;
         bin[j] = p < n_pos ? __ldcs(src + p) : BIN_NONE;
     }
     for (uint32_t i = tid; i < nb; i += NT) hist[i] = 0;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < BKT_PER; j++) {
+    for (int j = 0; j < PER; j++) {
         uint32_t r = bin[j] != BIN_NONE ? atomicAdd(&hist[bin[j] >> BKT_SHIFT], 1u) : 0u;   // rank inside this CTA's run
         if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
     }
@@ -1379,7 +1389,7 @@ k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, 
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < BKT_PER; j++) {
+    for (int j = 0; j < PER; j++) {
         if (bin[j] == BIN_NONE) continue;
         const uint32_t b = bin[j] >> BKT_SHIFT;
         const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
