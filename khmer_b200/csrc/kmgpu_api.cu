@@ -1524,7 +1524,22 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     {
         // one chunk more than a device-resident batch would get as soon as that leaves chunk 0 at most half of the others
         const uint64_t total = last - first, cap = chunk_bases(), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
-        if (n >= 2) {
+        bool ramp = false;
+        if (n >= 2 && 2 * total <= (n + 1) * cap) {
+            // sizes 1 : 2 : ... : n — the copy of every chunk still hides behind the ingest of the one before it (PCIe
+            // moves a base about twice as fast as the kernels consume it) and chunk 0 is as short as that allows
+            const uint64_t unit = ((2 * total / (n * (n + 1))) + 31) & ~31ull;
+            const uint64_t head = unit * (n * (n - 1) / 2);   // everything but the last chunk
+            if (unit && head < total && total - head <= cap && (n - 1) * unit <= cap) {
+                uint64_t b = 0;
+                for (uint64_t i = 1; i < n; i++) {
+                    b += i * unit;
+                    starts.push_back(b);
+                }
+                ramp = true;
+            }
+        }
+        if (!ramp && n >= 2) {
             uint64_t c0 = std::max<uint64_t>(total > (n - 1) * cap ? total - (n - 1) * cap : 0, total / (2 * n - 1));
             uint64_t c = (((total - c0) + (n - 2)) / (n - 1) + 31) & ~31ull;
             c = std::min(c, cap);
