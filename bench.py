@@ -88,6 +88,11 @@ def synth_batch(seed, n_reads, pinned=False):
         codes[strands] = (3 - codes[strands])[:, ::-1]
         view[i0:i0 + m] = lut[codes]
     off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    if pinned:   # the read offsets are part of the step's input: page-locked like the sequence bytes
+        to = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
+        po = to.numpy().view(np.uint64)
+        po[:] = off
+        return buf, po, (t, to)
     return buf, off, t
 
 
@@ -373,7 +378,7 @@ def run_ours(args):
                        "parallelism": "replicated sketch per GPU, disjoint read shards, saturating-add NVLink merge per job"
                        if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": bases + 4 * (R + 1),
+            "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": bases + 8 * (R + 1),
                     "d2h_bytes_per_step": 64 * ((bases + (32 << 20) - 1) // (32 << 20)), "ms_per_step": e2e["ms"] / args.steps},
             "gpu_launches": int(hbm["launches"]), "clocks": clocks,
         }

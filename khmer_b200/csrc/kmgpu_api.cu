@@ -166,6 +166,8 @@ struct kmgpu_sketch {
 
     // staging of read chunks: two slots so that the upload + packing of chunk i+1 (copy stream) overlaps the
     // ingestion of chunk i (main stream)
+    static constexpr int MAX_PARTS = 16;           // parts of a chunk of host input (each staged in its own slot)
+    static constexpr int N_STAGE = 2 * MAX_PARTS;   // two sets: the next chunk is uploaded while this one is ingested
     struct Stage {
         DevBuf<uint8_t> ascii;
         DevBuf<uint64_t> words;
@@ -173,8 +175,9 @@ struct kmgpu_sketch {
         DevBuf<uint64_t> offs64;
         DevBuf<uint32_t> tfr;
         PinBuf<uint32_t> h_offs;
+        PinBuf<uint64_t> h_offs64;
         cudaEvent_t ready = nullptr;
-    } stage[2];
+    } stage[N_STAGE];
     cudaStream_t copy_stream = nullptr;
     Ctrl* d_ctrl_copy = nullptr;
     Ctrl* h_ctrl_copy = nullptr;  // pinned
@@ -429,10 +432,14 @@ extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, cons
     if (e == cudaSuccess) e = cudaEventCreate(&h->tev1);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {   // the copy stream's small kernels (pack, offsets) must not queue behind the ingest grids
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        e = cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi_prio);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_ctrl_copy, sizeof(Ctrl));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_ctrl_copy, sizeof(Ctrl));
-    for (int sl = 0; sl < 2 && e == cudaSuccess; sl++) e = cudaEventCreateWithFlags(&h->stage[sl].ready, cudaEventDisableTiming);
+    for (int sl = 0; sl < kmgpu_sketch::N_STAGE && e == cudaSuccess; sl++) e = cudaEventCreateWithFlags(&h->stage[sl].ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         kmgpu_destroy(h);
         return fail(KMGPU_ECUDA, "handle setup: %s", cudaGetErrorString(e));
@@ -452,9 +459,9 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     for (int i = 0; i < h->nt; i++)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    for (int sl = 0; sl < 2; sl++) {
+    for (int sl = 0; sl < kmgpu_sketch::N_STAGE; sl++) {
         h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].offs64.release(); h->stage[sl].tfr.release();
-        h->stage[sl].h_offs.release();
+        h->stage[sl].h_offs.release(); h->stage[sl].h_offs64.release();
         if (h->stage[sl].ready) cudaEventDestroy(h->stage[sl].ready);
     }
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
@@ -910,7 +917,16 @@ static inline void big_events(kmgpu_sketch* h, uint64_t hash, uint32_t count)
     h->big_dirty = true;
 }
 
-static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Input& in, uint64_t stride, uint64_t n_list, uint64_t n_cross)
+// A chunk may arrive in parts (host input: one staged range each, uploaded while the previous part is hashed): part j holds
+// positions [pos_off, pos_off + in.n_pos) of the chunk; the main stream waits for `ready` before it touches the part.
+struct Part {
+    Input in;
+    uint32_t pos_off;
+    cudaEvent_t ready;
+};
+
+static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const std::vector<Part>& parts, uint32_t n_pos, uint64_t stride, uint64_t n_list,
+                                  uint64_t n_cross)
 {
     cudaStream_t st = h->stream;
     // the small workspaces start at a size that rarely has to grow: a regrowth is a cudaFree + cudaMalloc, i.e. a device
@@ -936,21 +952,24 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
         h->all_launches += 1;
     }
     // 1. candidates and touches of crossing bins
-    uint64_t cap = in.n_pos;
+    uint64_t cap = n_pos;
     CKR(h->d_events.ensure(cap));
     CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
     SatBits sb;
     for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
-    {
+    for (const Part& pt : parts) {
+        const Input& in = pt.in;
+        if (in.n_pos == 0) continue;
+        const uint32_t* bins = h->d_bins.p + pt.pos_off;
         unsigned gb = (in.n_pos + 255) / 256;
-        if (src == 1) k_bigscan<TWOBIT, 1><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
-                                                                h->d_events.p, (unsigned long long)cap, h->d_ctrl);
-        else if (H.kind == TWOBIT) k_bigscan<TWOBIT, 0><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1,
-                                                                            n_cross ? 1 : 0, h->d_events.p, (unsigned long long)cap, h->d_ctrl);
-        else k_bigscan<MURMUR, 0><<<gb, 256, 0, st>>>(h->nt, H, in, h->d_bins.p, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
-                                                      h->d_events.p, (unsigned long long)cap, h->d_ctrl);
+        if (src == 1) k_bigscan<TWOBIT, 1><<<gb, 256, 0, st>>>(h->nt, H, in, bins, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
+                                                                h->d_events.p, (unsigned long long)cap, h->d_ctrl, pt.pos_off);
+        else if (H.kind == TWOBIT) k_bigscan<TWOBIT, 0><<<gb, 256, 0, st>>>(h->nt, H, in, bins, stride, sb, h->d_htkeys.p, slots - 1,
+                                                                            n_cross ? 1 : 0, h->d_events.p, (unsigned long long)cap, h->d_ctrl, pt.pos_off);
+        else k_bigscan<MURMUR, 0><<<gb, 256, 0, st>>>(h->nt, H, in, bins, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
+                                                      h->d_events.p, (unsigned long long)cap, h->d_ctrl, pt.pos_off);
+        h->all_launches += 1;
     }
-    h->all_launches += 1;
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
     const uint64_t n_rec = h->h_ctrl->n_events;
@@ -968,7 +987,7 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const Inp
         k_sel_slots<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->dev, h->d_htkeys.p, slots - 1, h->d_recslot.p);
         k_sel_init<<<gsl, 256, 0, st>>>(h->d_htkeys.p, h->d_htvals.p, slots, ss);
         int top = 0;
-        while (top < 31 && (1ull << (top + 1)) <= (uint64_t)in.n_pos) top++;
+        while (top < 31 && (1ull << (top + 1)) <= (uint64_t)n_pos) top++;
         for (int bit = top; bit >= 0; bit--) {
             k_sel_count<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->nt, h->d_recslot.p, bit, ss);
             k_sel_update<<<gsl, 256, 0, st>>>(slots, bit, ss);
@@ -1044,16 +1063,18 @@ static void launch_apply(unsigned g, cudaStream_t st, const SketchDev& S, const 
 // them: the caller uses it to prepare and upload the next chunk while this one is being ingested.
 typedef std::function<int()> Between;
 
-static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& passes, int src, HashCfg H, const Input& in, const Pred& P,
+static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& passes, int src, HashCfg H, const std::vector<Part>& parts, const Pred& P,
                               bool pred, const SketchDev* M, ChunkResult* res, const Between& between)
 {
     cudaStream_t st = h->stream;
-    const uint64_t stride = ((uint64_t)in.n_pos + 7) & ~7ull;
+    uint32_t n_pos = 0;
+    for (const Part& pt : parts) n_pos = std::max(n_pos, pt.pos_off + pt.in.n_pos);
+    const uint64_t stride = ((uint64_t)n_pos + 7) & ~7ull;
     CKR(h->d_bins.ensure((size_t)h->nt * stride));
     uint64_t total_bins = 0, max_span = 0;
     for (int i = 0; i < h->nt; i++) total_bins += h->sizes[i];
     for (const DeltaPass& p : passes) max_span = std::max<uint64_t>(max_span, p.hi - p.lo);
-    const uint64_t list_cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nt * in.n_pos, total_bins));
+    const uint64_t list_cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nt * n_pos, total_bins));
     CKR(h->d_binlist.ensure(list_cap));
     // block storage in 2-byte units: one half lane per bin, or one bit per bin for BitStorage
     size_t need_lanes = h->kind == BIT ? ((max_span + 127) / 128) * 8 + 8 : ((max_span + 7) & ~7ull) + 8;
@@ -1065,13 +1086,6 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
     CK(cudaEventRecord(h->ev0, st));
-    {
-        unsigned g = n_tiles(in.n_pos);
-        const SketchDev& MS = M ? *M : h->dev;
-        if (src == 1) launch_hashbins<TWOBIT, 1>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
-        else if (H.kind == TWOBIT) launch_hashbins<TWOBIT, 0>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
-        else launch_hashbins<MURMUR, 0>(pred, g, st, h->dev, MS, H, P, in, h->d_bins.p, stride, h->d_ctrl);
-    }
     const int want_cross = h->kind == BYTE && h->use_bigcount;
     if (want_cross && !h->satbits_valid) {
         for (int i = 0; i < h->nt; i++) {
@@ -1084,7 +1098,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     }
     bool kmers_counted = false;
     BucketLayout BL;
-    bool use_buckets = plan_buckets(h, in.n_pos, &BL);
+    bool use_buckets = plan_buckets(h, n_pos, &BL);
     if (use_buckets) {
         // bucket path: group the updates by 32 Ki-bin bucket, apply each bucket in shared memory (counters, n_occupied,
         // first touchers -> newbits / n_unique, saturation bookkeeping in one sweep)
@@ -1104,16 +1118,35 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     if (use_buckets) {
         const uint32_t n_buckets = BL.first[h->nt];
         CKR(h->d_cursors.ensure(n_buckets));
-        const size_t nb_words = (in.n_pos + 31) / 32;
+        const size_t nb_words = (n_pos + 31) / 32;
         CKR(h->d_newbits.ensure(nb_words));
         CK(cudaMemsetAsync(h->d_cursors.p, 0, (size_t)n_buckets * 4, st));
         CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
+    }
+    // hash every part as soon as it has arrived; on the bucket path its records follow at once
+    for (const Part& pt : parts) {
+        const Input& in = pt.in;
+        if (pt.ready) CK(cudaStreamWaitEvent(st, pt.ready, 0));
+        if (in.n_pos == 0) continue;
+        uint32_t* bins = h->d_bins.p + pt.pos_off;
+        const unsigned g = n_tiles(in.n_pos);
+        const SketchDev& MS = M ? *M : h->dev;
+        if (src == 1) launch_hashbins<TWOBIT, 1>(pred, g, st, h->dev, MS, H, P, in, bins, stride, h->d_ctrl);
+        else if (H.kind == TWOBIT) launch_hashbins<TWOBIT, 0>(pred, g, st, h->dev, MS, H, P, in, bins, stride, h->d_ctrl);
+        else launch_hashbins<MURMUR, 0>(pred, g, st, h->dev, MS, H, P, in, bins, stride, h->d_ctrl);
+        if (use_buckets)
+            k_bucketize<BKT_TILE, BKT_PER><<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), BKT_TILE / BKT_PER, bkt_sort_smem(BKT_TILE), st>>>(
+                bins, stride, in.n_pos, pt.pos_off, BL, h->d_records.p, h->d_cursors.p, h->d_ctrl);
+        h->ingest_launches += use_buckets ? 2 : 1;
+        h->all_launches += use_buckets ? 2 : 1;
+    }
+    if (use_buckets) {
+        const uint32_t n_buckets = BL.first[h->nt];
+        const size_t nb_words = (n_pos + 31) / 32;
         SatBits sb;
         memset(&sb, 0, sizeof sb);
         if (want_cross)
             for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
-        k_bucketize<BKT_TILE, BKT_PER><<<dim3((in.n_pos + BKT_TILE - 1) / BKT_TILE, h->nt), BKT_TILE / BKT_PER, bkt_sort_smem(BKT_TILE), st>>>(
-            h->d_bins.p, stride, in.n_pos, BL, h->d_records.p, h->d_cursors.p, h->d_ctrl);
         if (h->kind == BYTE) launch_apply<BYTE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross, sb);
         else if (h->kind == NIBBLE) launch_apply<NIBBLE>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
         else launch_apply<BIT>(n_buckets, st, h->dev, BL, h->d_records.p, h->d_cursors.p, h->d_newbits.p, h->d_binlist.p, list_cap, h->d_ctrl, 0, sb);
@@ -1125,8 +1158,8 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->ingest_ms += ms;
-        h->ingest_launches += 4;
-        h->all_launches += 4;
+        h->ingest_launches += 2;
+        h->all_launches += 2;
         Ctrl c = *h->h_ctrl;
         res->n_kmers += c.n_kmers;
         kmers_counted = true;
@@ -1138,26 +1171,26 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
                 res->n_new += c.n_unique;
                 res->have_newbits = true;
             }
-            if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, in, stride, c.n_events, c.n_cross));
+            if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, parts, n_pos, stride, c.n_events, c.n_cross));
             return KMGPU_OK;
         }
         // a bucket overflowed (heavily repeated k-mers): nothing was applied; redo the chunk with the delta passes
-        if (env_u64("KMGPU_DEBUG", 0)) fprintf(stderr, "[kmgpu] bucket overflow (cap %u, %u positions): chunk redone by the delta passes\n", BL.cap, in.n_pos);
+        if (env_u64("KMGPU_DEBUG", 0)) fprintf(stderr, "[kmgpu] bucket overflow (cap %u, %u positions): chunk redone by the delta passes\n", BL.cap, n_pos);
         CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
         CK(cudaEventRecord(h->ev0, st));
     }
     const Between none;
     const Between& between2 = kmers_counted ? none : between;   // the hook has already run
-    const unsigned gs = (in.n_pos + 2047) / 2048;
+    const unsigned gs = (n_pos + 2047) / 2048;
     for (const DeltaPass& p : passes) {
         const int pass_id = passes.size() <= 64 ? (int)(&p - passes.data()) : -1;   // per-pass entry counts for the cold resolution
         if (h->kind == BIT) {
-            k_scatter<true><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
+            k_scatter<true><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, n_pos, p.lo, p.hi, h->d_delta.p);
             unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
             k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, pass_id);
             continue;
         }
-        k_scatter<false><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, h->d_delta.p);
+        k_scatter<false><<<gs, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, n_pos, p.lo, p.hi, h->d_delta.p);
         unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
         if (h->kind == BYTE)
             k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, h->d_binlist.p, list_cap, h->d_ctrl, want_cross,
@@ -1172,8 +1205,8 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->ingest_ms += ms;
-    h->ingest_launches += 1 + 2 * passes.size();
-    h->all_launches += 1 + 2 * passes.size();
+    h->ingest_launches += 2 * passes.size();
+    h->all_launches += 2 * passes.size();
     Ctrl c = *h->h_ctrl;
     if (c.n_events > list_cap) return fail(KMGPU_ECUDA, "internal: bin list overflow");
     if (!kmers_counted) res->n_kmers += c.n_kmers;
@@ -1181,7 +1214,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
     const uint64_t n_list = c.n_events;
     if (c.n_zbits) {
         // first-toucher stamps: per-table sub-tables of packed 8-byte slots in one buffer, bitmap prefilter
-        size_t nb_words = (in.n_pos + 31) / 32;
+        size_t nb_words = (n_pos + 31) / 32;
         CKR(h->d_newbits.ensure(nb_words));
         CK(cudaMemsetAsync(h->d_newbits.p, 0, nb_words * 4, st));
         CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
@@ -1213,7 +1246,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
                         k_rank_sums<<<gw, 256, 0, st>>>(rec, n_words, sums);
                         k_rank_scan<<<1, 1024, 0, st>>>(sums, gw);
                         k_rank_prefix<<<gw, 256, 0, st>>>(rec, n_words, sums);
-                        k_rank_replay<<<(in.n_pos + 2047) / 2048, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, rec, minpos);
+                        k_rank_replay<<<(n_pos + 2047) / 2048, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, n_pos, p.lo, p.hi, rec, minpos);
                         k_rank_mark<<<gl, 256, 0, st>>>(minpos, n_ent, h->d_newbits.p, h->d_ctrl);
                         h->all_launches += 6;
                         seg0 = seg1;
@@ -1225,7 +1258,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
                     CK(cudaMemsetAsync(sl, 0xFF, slots * 8, st));
                     unsigned gl = (unsigned)std::min<uint64_t>((seg1 - seg0 + 255) / 256, 148 * 8);
                     k_pk_register<<<gl, 256, 0, st>>>(h->d_binlist.p + seg0, seg1 - seg0, p.table, sl, slots - 1, nullptr);
-                    k_pk_replay<<<(in.n_pos + 1023) / 1024, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, in.n_pos, p.lo, p.hi, sl,
+                    k_pk_replay<<<(n_pos + 1023) / 1024, 256, 0, st>>>(h->d_bins.p + (size_t)p.table * stride, n_pos, p.lo, p.hi, sl,
                                                                     slots - 1, nullptr);
                     unsigned gm = (unsigned)std::min<uint64_t>((slots + 255) / 256, 148 * 8);
                     k_pk_mark<<<gm, 256, 0, st>>>(sl, slots, h->d_newbits.p, h->d_ctrl);
@@ -1261,7 +1294,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         unsigned long long* sl = reinterpret_cast<unsigned long long*>(h->d_htkeys.p);
         unsigned gl = (unsigned)std::min<uint64_t>((n_list + 255) / 256, 148 * 8);
         k_pk_register_all<<<gl, 256, 0, st>>>(h->d_binlist.p, n_list, L, sl, h->d_filter.p);
-        k_pk_replay_all<<<(in.n_pos + 255) / 256, 256, 0, st>>>(h->d_bins.p, stride, h->nt, in.n_pos, L, sl, h->d_filter.p);
+        k_pk_replay_all<<<(n_pos + 255) / 256, 256, 0, st>>>(h->d_bins.p, stride, h->nt, n_pos, L, sl, h->d_filter.p);
         unsigned gm = (unsigned)std::min<uint64_t>((total_slots + 255) / 256, 148 * 8);
         k_pk_mark<<<gm, 256, 0, st>>>(sl, total_slots, h->d_newbits.p, h->d_ctrl);
         h->all_launches += 3;
@@ -1272,7 +1305,7 @@ static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& pas
         res->n_new += h->h_ctrl->n_unique;
         res->have_newbits = true;
     }
-    if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, in, stride, n_list, c.n_cross));
+    if (want_cross && c.n_sat) CKR(resolve_bigcount_delta(h, src, H, parts, n_pos, stride, n_list, c.n_cross));
     return KMGPU_OK;
 }
 
@@ -1283,7 +1316,7 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
     if (in.n_pos == 0) return between ? between() : KMGPU_OK;
     {
         std::vector<DeltaPass> dp;
-        if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, in, P, pred, M, res, between);
+        if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, std::vector<Part>(1, Part{in, 0u, nullptr}), P, pred, M, res, between);
     }
     cudaStream_t st = h->stream;
     CKR(h->d_flags.ensure(in.n_pos));
@@ -1472,7 +1505,20 @@ static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offset
     CKR(S.offs64.ensure(nr + 1));
     CKR(S.tfr.ensure(n_tiles(n_pos) + 1));
     if (n_pos) CK(cudaMemcpyAsync(S.ascii.p, seqs + b0, n_pos, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(S.offs64.p, offsets + r_lo, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, st));
+    // the caller's offsets may be pageable: a copy from pageable memory would block this thread until everything queued
+    // before it on the stream (the sequence bytes just above) has gone over the bus; go through a pinned slice instead
+    {
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, offsets) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const uint64_t* src = offsets + r_lo;
+        if (!pinned) {
+            CKR(S.h_offs64.ensure(nr + 1));
+            memcpy(S.h_offs64.p, src, (size_t)(nr + 1) * 8);
+            src = S.h_offs64.p;
+        }
+        CK(cudaMemcpyAsync(S.offs64.p, src, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
     k_clip_offsets<<<(nr + 1 + 255) / 256, 256, 0, st>>>(S.offs64.p, nr + 1, b0, b1, S.offs.p);
     if (need_acgt_check) CK(cudaMemsetAsync(h->d_ctrl_copy, 0, sizeof(Ctrl), st));
     k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(S.ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, S.words.p,
@@ -1517,6 +1563,51 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     const uint64_t first = offsets[0], last = offsets[n_reads];
     const bool chk = needs_acgt_check(h, flags);
     if (last <= first) return KMGPU_OK;
+    {
+        // Sketches on the bucket path take host input in PARTS: a chunk (the unit that pays one sweep of the sketch) is as
+        // large as for device-resident input, but it is uploaded, packed, hashed and bucketized part by part, so that only
+        // the first part's trip over PCIe is exposed.  All of a chunk's copies are queued on the copy stream at once (one
+        // staging slot per part, two sets of slots: the next chunk's parts are queued while this chunk is being applied).
+        std::vector<DeltaPass> dp;
+        BucketLayout BL;
+        const uint64_t total = last - first, cap = chunk_bases();
+        const uint64_t n_chunks = (total + cap - 1) / cap;
+        const uint64_t per_chunk = (((total + n_chunks - 1) / n_chunks) + 31) & ~31ull;
+        const uint64_t part_cap = std::max<uint64_t>(std::min<uint64_t>(env_u64("KMGPU_PART_BASES", 24ull << 20), per_chunk),
+                                                     (per_chunk + kmgpu_sketch::MAX_PARTS - 1) / kmgpu_sketch::MAX_PARTS);
+        const uint64_t worst_pos = per_chunk + (uint64_t)kmgpu_sketch::MAX_PARTS * h->k;
+        if (env_u64("KMGPU_PARTS", 1) && total > part_cap && worst_pos < (1ull << 31) && plan_delta(h, dp) && plan_buckets(h, (uint32_t)worst_pos, &BL)) {
+            struct Staged { std::vector<Part> parts; };
+            Staged set[2];
+            auto stage_chunk_parts = [&](uint64_t ci, Staged* out) -> int {
+                out->parts.clear();
+                const uint64_t c0 = first + ci * per_chunk, c1 = std::min(last, c0 + per_chunk);
+                std::vector<uint64_t> cuts;   // equal parts (a short, growing first part was measured: no gain)
+                for (uint64_t b = c0; b < c1; b += part_cap) cuts.push_back(b);
+                cuts.push_back(c1);
+                uint32_t pos = 0;
+                int slot = (int)(ci & 1) * kmgpu_sketch::MAX_PARTS;
+                for (size_t pi = 0; pi + 1 < cuts.size(); pi++, slot++) {
+                    const uint64_t b0 = cuts[pi];
+                    const uint64_t b1 = std::min(last, cuts[pi + 1] + (uint64_t)(h->k - 1));
+                    ChunkDev cd;
+                    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd, chk, slot, h->copy_stream));
+                    CK(cudaEventRecord(h->stage[slot].ready, h->copy_stream));
+                    out->parts.push_back(Part{make_input(cd), pos, h->stage[slot].ready});
+                    pos += cd.n_pos;
+                }
+                return KMGPU_OK;
+            };
+            CKR(stage_chunk_parts(0, &set[0]));
+            for (uint64_t ci = 0; ci < n_chunks; ci++) {
+                CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &res, [&]() -> int {
+                    return ci + 1 < n_chunks ? stage_chunk_parts(ci + 1, &set[(ci + 1) & 1]) : KMGPU_OK;
+                }));
+            }
+            if (n_kmers_out) *n_kmers_out = res.n_kmers;
+            return KMGPU_OK;
+        }
+    }
     // Every chunk pays one sweep of the whole sketch (the folds) plus the fixed part of the resolutions, so there are
     // as few chunks as the cap allows; nothing can start before chunk 0 has crossed PCIe, so chunk 0 is the short one
     // (half of the others when the cap leaves that freedom) and the copy of chunk i+1 hides behind the ingest of chunk i.

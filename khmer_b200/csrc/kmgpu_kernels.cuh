@@ -1316,11 +1316,12 @@ struct BucketLayout {
 
 // 1. group the bins of table blockIdx.y held by T consecutive positions by bucket (counting sort in shared
 //    memory), reserve room in each bucket with one atomicAdd per (CTA, bucket), and write the records
-//    (position << 15 | bin within bucket) as runs of consecutive addresses.
+//    (position << 15 | bin within bucket) as runs of consecutive addresses.  `bins` and `n_pos` describe one part of the
+//    chunk (host input arrives in parts); `pos_base` is the part's first position within the chunk.
 template <int T, int PER>
 __global__ void __launch_bounds__(T / PER, 1)
-k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, BucketLayout L, unsigned long long* __restrict__ records,
-            uint32_t* __restrict__ cursors, Ctrl* ctrl)
+k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, uint32_t pos_base, BucketLayout L,
+            unsigned long long* __restrict__ records, uint32_t* __restrict__ cursors, Ctrl* ctrl)
 {
     constexpr int NT = T / PER;              // threads
     constexpr int BPT = (BKT_MAX_BUCKETS + NT - 1) / NT;
@@ -1408,7 +1409,7 @@ k_bucketize(const uint32_t* __restrict__ bins, uint64_t stride, uint32_t n_pos, 
         const uint2 m = stage[s];
         const uint32_t b = m.y >> 16, idx = run[b].y + (m.y & 0xFFFFu);
         if (idx < L.cap)
-            records[base + (size_t)b * L.cap + idx] = ((unsigned long long)(p0 + (m.x >> BKT_SHIFT)) << BKT_SHIFT) | (m.x & (BKT_BINS - 1));
+            records[base + (size_t)b * L.cap + idx] = ((unsigned long long)(pos_base + p0 + (m.x >> BKT_SHIFT)) << BKT_SHIFT) | (m.x & (BKT_BINS - 1));
         else
             over = true;
     }
@@ -1663,9 +1664,9 @@ __device__ __forceinline__ uint64_t hash_at(const Input& in, int k, uint32_t p)
 template <int HK, int SRC>
 __global__ void __launch_bounds__(256)
 k_bigscan(int n_tables, HashCfg H, Input in, const uint32_t* __restrict__ bins, uint64_t stride, SatBits sat,
-          const uint64_t* __restrict__ keys, uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl)
+          const uint64_t* __restrict__ keys, uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl, uint32_t pos_base)
 {
-    const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t p = blockIdx.x * 256u + threadIdx.x;   // position inside this part of the chunk (`bins` points at the part)
     if (p >= in.n_pos) return;
     uint32_t b[F_MAXT];
 #pragma unroll
@@ -1689,7 +1690,7 @@ k_bigscan(int n_tables, HashCfg H, Input in, const uint32_t* __restrict__ bins, 
     if (!cross && !allsat) return;
     Event e;
     e.hash = hash_at<HK, SRC>(in, H.k, p);
-    e.pos = p;
+    e.pos = pos_base + p;
     e.info = cross | (allsat << 30);
     unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
     if (at < cap) out[at] = e;

@@ -66,7 +66,7 @@ def _same_state(g, o, n_tables):
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
 @pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps", "buckets",
-                                   "buckets-overflow"])
+                                   "buckets-overflow", "buckets-whole"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
@@ -80,9 +80,11 @@ def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
         elif chunk == "delta-cold":   # delta+fold path, per-block ("cold chunk") ranked-bitmap resolution forced
             env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_BUCKETS="0")
         elif chunk == "buckets":   # bucket path (records grouped by 32 Ki-bin bucket, applied in shared memory)
-            env.update(KMGPU_CHUNK_BASES="16384")
+            env.update(KMGPU_CHUNK_BASES="16384", KMGPU_PART_BASES="1000")   # host input in 16 parts per chunk
+        elif chunk == "buckets-whole":   # bucket path, every chunk uploaded in one piece
+            env.update(KMGPU_CHUNK_BASES="16384", KMGPU_PARTS="0")
         elif chunk == "buckets-overflow":   # bucket path with buckets far too small: every chunk falls back to the delta passes
-            env.update(KMGPU_CHUNK_BASES="16384", KMGPU_BUCKET_CAP="64")
+            env.update(KMGPU_CHUNK_BASES="16384", KMGPU_BUCKET_CAP="64", KMGPU_PART_BASES="3000")
         elif chunk == "delta-cold-stamps":   # same, through the stamp hash tables (blocks beyond 2^26 bins take this form)
             env.update(KMGPU_DELTA_BLOCK_BINS="2000", KMGPU_COLD_MIN_NEW="1", KMGPU_CHUNK_BASES="32768", KMGPU_COLD_RANK="0",
                        KMGPU_BUCKETS="0")
