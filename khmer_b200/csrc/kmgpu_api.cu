@@ -1582,6 +1582,7 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
             auto stage_chunk_parts = [&](uint64_t ci, Staged* out) -> int {
                 out->parts.clear();
                 const uint64_t c0 = first + ci * per_chunk, c1 = std::min(last, c0 + per_chunk);
+                if (c0 >= last) return KMGPU_OK;   // rounding per_chunk up to 32 can leave nothing for the last chunk
                 std::vector<uint64_t> cuts;   // equal parts (a short, growing first part was measured: no gain)
                 for (uint64_t b = c0; b < c1; b += part_cap) cuts.push_back(b);
                 cuts.push_back(c1);
@@ -1600,6 +1601,7 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
             };
             CKR(stage_chunk_parts(0, &set[0]));
             for (uint64_t ci = 0; ci < n_chunks; ci++) {
+                if (set[ci & 1].parts.empty()) break;
                 CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &res, [&]() -> int {
                     return ci + 1 < n_chunks ? stage_chunk_parts(ci + 1, &set[(ci + 1) & 1]) : KMGPU_OK;
                 }));
