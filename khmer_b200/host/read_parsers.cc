@@ -230,8 +230,8 @@ struct FastxReader::Impl {
         skip_blank();
         int c = peek();
         if (c < 0) return 1;
-        const char* s;
-        size_t n;
+        const char* s = nullptr;
+        size_t n = 0;
         if (c == '>') {
             get_line(s, n);
             name.assign(s + 1, n - 1);
