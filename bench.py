@@ -233,6 +233,90 @@ def run_reference(args):
     emit(line)
 
 
+def table_md5s(sk):
+    import hashlib
+    return [hashlib.md5(sk.table(i).tobytes()).hexdigest() for i in range(N_TABLES)]
+
+
+def parity_check(cabi, local_rank, n_reads, seed=31337):
+    """One fixed batch into a fresh sketch through the same call the e2e leg times, compared with the reference at one
+    thread (oracle/_ref; the oracle port when the compiled reference is absent): table images, n_occupied, n_unique_kmers.
+    The checker is never the thing measured."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hashlib
+    import oracle_lib as ol
+    buf, off, _ = synth_batch(seed, n_reads)
+    sizes = primes_near_x(N_TABLES, TABLE_X)
+    sk = cabi.Sketch(cabi.BYTE, cabi.TWOBIT, K, sizes, device=local_rank)
+    sk.set_use_bigcount(True)
+    kmers = sk.consume_reads((buf, off), clean=True)
+    got = {"kmers": int(kmers), "n_occupied": int(sk.stats()[0]), "n_unique_kmers": int(sk.stats()[1]), "table_md5": table_md5s(sk)}
+    sk.close()
+    if ol.have_ref():
+        kind = "reference"
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "reads.fa")
+            rows = buf.reshape(n_reads, READ_LEN)
+            block = np.empty((n_reads, READ_LEN + 4), dtype=np.uint8)
+            block[:, :3] = np.frombuffer(b">r\n", dtype=np.uint8)
+            block[:, 3:3 + READ_LEN] = rows
+            block[:, -1] = ord("\n")
+            with open(path, "wb") as fh:
+                fh.write(block.tobytes())
+            ref = ol.Ref("Countgraph", K, sizes)
+            ref.set_use_bigcount(True)
+            _, rk = ref.consume_seqfile(path, threads=1)
+        want = {"kmers": int(rk), "n_occupied": int(ref.n_occupied()), "n_unique_kmers": int(ref.n_unique_kmers()),
+                "table_md5": [hashlib.md5(ref.table(i).tobytes()).hexdigest() for i in range(N_TABLES)]}
+    else:
+        kind = "port"
+        o = ol.Oracle("Countgraph", K, sizes)
+        o.set_use_bigcount(True)
+        rk = o.L.ko_consume_reads(o.h, buf.ctypes.data_as(ol.C.c_char_p), off.ctypes.data_as(ol.u64p), n_reads, 1, 0, 0, 0)
+        want = {"kmers": int(rk), "n_occupied": int(o.n_occupied()), "n_unique_kmers": int(o.n_unique_kmers()),
+                "table_md5": [hashlib.md5(o.table(i).tobytes()).hexdigest() for i in range(N_TABLES)]}
+    ok = got == want
+    return {"ok": ok, "checker": kind, "reads": n_reads, "kmers": got["kmers"], "n_unique_kmers": got["n_unique_kmers"],
+            "n_occupied": got["n_occupied"], "table_md5_0": got["table_md5"][0],
+            "mismatch": None if ok else {"got": got, "want": want}}
+
+
+def merge_check(cabi, dist, torch, group_cls, rank, world, local_rank, n_reads=125_000):
+    """N > 1: every rank ingests its own fixed batch into a fresh replica, the replicas are merged over NVLink exactly as in
+    the timed region; all ranks must then hold identical tables, and rank 0 compares them with ONE sketch fed every rank's
+    batch (saturating add is associative, so the images must be byte-identical)."""
+    import hashlib
+    sizes = primes_near_x(N_TABLES, TABLE_X)
+    sk = cabi.Sketch(cabi.BYTE, cabi.TWOBIT, K, sizes, device=local_rank)
+    sk.set_use_bigcount(False)
+    buf, off, _ = synth_batch(555000 + rank, n_reads)
+    sk.consume_reads((buf, off), clean=True)
+    grp = group_cls(sk, dist, device=torch.device("cuda", local_rank))
+    grp.attach()
+    grp.merge()
+    mine = hashlib.md5("".join(table_md5s(sk)).encode()).digest()
+    occ = sk.stats()[0]
+    t = torch.tensor(list(mine) + [occ % 251], dtype=torch.int64, device="cuda")
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    same = all(bool((g == gathered[0]).all().item()) for g in gathered)
+    res = {"ok": same, "ranks_identical": same, "reads_per_rank": n_reads}
+    if rank == 0:
+        one = cabi.Sketch(cabi.BYTE, cabi.TWOBIT, K, sizes, device=local_rank)
+        one.set_use_bigcount(False)
+        for r in range(world):
+            b, o, _ = synth_batch(555000 + r, n_reads)
+            one.consume_reads((b, o), clean=True)
+        single = hashlib.md5("".join(table_md5s(one)).encode()).digest()
+        res["equals_single_sketch"] = single == mine and one.stats()[0] == occ
+        res["ok"] = bool(same and res["equals_single_sketch"])
+        res["n_occupied"] = int(occ)
+        one.close()
+    grp.detach()
+    sk.close()
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
@@ -339,6 +423,27 @@ def run_ours(args):
                         "kern_launches": kern_launches, "launches": all_launches, "local_kmers": kmers,
                         "wall_ms": 1e3 * (t1 - t0)}
 
+    # the same device-timed leg with bigcount off (what every N > 1 run uses): the N = 1 denominator of a scaling ratio
+    value_nobig = None
+    if world == 1:
+        sk.set_use_bigcount(False)
+        sk.reset()
+        run_steps(P, "hbm", 0)
+        barrier()
+        sk.timer_start()
+        kk = run_steps(P, "hbm", P)
+        ms_nb = sk.timer_stop()
+        value_nobig = kk / (ms_nb * 1e-3)
+        sk.set_use_bigcount(True)
+        sk.reset()
+
+    checks = {}
+    if not args.no_check:
+        if rank == 0:
+            checks["parity_check"] = parity_check(cabi, local_rank, args.check_reads)
+        if world > 1:
+            checks["merge_check"] = merge_check(cabi, dist, torch, ReplicaGroup, rank, world, local_rank)
+
     hbm, e2e = results["hbm"], results["e2e"]
     value = hbm["kmers"] / (hbm["ms"] * 1e-3)
     e2e_value = e2e["kmers"] / (e2e["ms"] * 1e-3)
@@ -351,12 +456,16 @@ def run_ours(args):
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_kmer"] * kmers_per_launch if traffic else None,
-                "kernel": "ingest kernel group per chunk: k_hashbins + k_bucketize + k_apply<BYTE> + k_popc (bucket path)",
+                "kernel": "ingest kernel group per chunk: k_part (fused hash + grouping) + k_apply2<BYTE> + k_popc (grouped path)",
                 "kernel_ms_per_launch": avg_launch_ms, "kernel_launches": int(hbm["kern_launches"]),
                 "kmers_per_launch": kmers_per_launch, "algorithmic_bytes_per_launch": kmers_per_launch * ALGO_BYTES_PER_KMER,
                 "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
                 "peak_source": peak_src, "kernel_share_of_step": hbm["kern_ms"] / hbm["ms"] if world == 1 else None,
-                "traffic_source": traffic.get("source") if traffic else None}
+                "traffic_source": traffic.get("source") if traffic else None,
+                # frac above is the distance to the spec's random-sector model (N x 64 B per k-mer); dram_frac is
+                # real DRAM utilisation: bytes ncu saw the group move per k-mer x the measured k-mer rate / peak
+                "dram_frac": (traffic["dram_bytes_per_kmer"] * hbm["local_kmers"] / (hbm["kern_ms"] * 1e-3) / 1e9 / peak) if traffic else None,
+                "dram_bytes_per_kmer": traffic["dram_bytes_per_kmer"] if traffic else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -382,9 +491,16 @@ def run_ours(args):
                     "d2h_bytes_per_step": 64 * ((bases + (32 << 20) - 1) // (32 << 20)), "ms_per_step": e2e["ms"] / args.steps},
             "gpu_launches": int(hbm["launches"]), "clocks": clocks,
         }
+        if value_nobig is not None:
+            line["value_bigcount_off"] = value_nobig
+        line.update(checks)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    bad = [k for k, v in checks.items() if not v.get("ok")]
+    if bad:
+        print("[bench] FAILED checks: %s" % ", ".join(bad), file=sys.stderr, flush=True)
+        raise SystemExit(3)
 
 
 def emit(line):
@@ -415,6 +531,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-reads", type=int, default=250_000, help="reads per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip parity_check / merge_check")
+    ap.add_argument("--check-reads", type=int, default=250_000, help="reads of the parity_check batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

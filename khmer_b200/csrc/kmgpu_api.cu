@@ -17,6 +17,7 @@
 
 #include "../../include/kmgpu.h"
 #include "kmgpu_kernels.cuh"
+#include "kmgpu_group.cuh"
 
 using namespace kmgpu;
 
@@ -85,7 +86,15 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         size_t want = std::max<size_t>(n, cap + cap / 2);
-        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = 0;   // a failed allocation leaves an empty buffer, not a stale capacity
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaErrorMemoryAllocation && want > n) {   // no room for the growth margin: take exactly what is needed
+            cudaGetLastError();
+            want = n;
+            e = cudaMalloc(&p, want * sizeof(T));
+        }
+        if (e != cudaSuccess) p = nullptr;
+        CK(e);
         cap = want;
         return KMGPU_OK;
     }
@@ -107,6 +116,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         size_t want = std::max<size_t>(n, cap + cap / 2);
+        cap = 0;
         CK(cudaMallocHost(&p, want * sizeof(T)));
         cap = want;
         return KMGPU_OK;
@@ -188,6 +198,11 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_rank;
     DevBuf<unsigned long long> d_records;   // bucket path: update records, bucket-major
     DevBuf<uint32_t> d_cursors;
+    DevBuf<unsigned long long> d_rec1;      // grouped path, two-level: records by super-bucket
+    DevBuf<uint32_t> d_cur1;
+    DevBuf<unsigned long long> d_off1, d_off2;   // exact region offsets of a regrouping run
+    DevBuf<uint64_t> d_hash64;              // Murmur: 64-bit hash of every position of the chunk
+    uint64_t n_regroups = 0;
     bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
     DevBuf<uint16_t> d_delta;
@@ -394,8 +409,8 @@ extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, cons
     if (ksize < 1 || ksize > MAX_K) return fail(KMGPU_EINVAL, "ksize %d out of range", ksize);
     if (hash == KMGPU_TWOBIT && ksize > 32)
         return fail(KMGPU_EINVAL, "Supplied kmer string doesn't match the underlying k-size.");  // kmer_hash.cc:70-72
-    if (n_tables < 1 || n_tables > F_MAXT)
-        return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported (1..%d)", n_tables, F_MAXT);
+    if (n_tables < 1 || n_tables > MAX_TABLES)
+        return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported (1..%d)", n_tables, MAX_TABLES);
     for (int i = 0; i < n_tables; i++)
         if (sizes[i] == 0 || sizes[i] >= (1ull << 55)) return fail(KMGPU_EINVAL, "table size %llu out of range", (unsigned long long)sizes[i]);
     int ndev = 0;
@@ -417,11 +432,12 @@ extern "C" int kmgpu_create(int storage, int hash, int ksize, int n_tables, cons
         cudaError_t e = cudaMalloc(&h->dev.tables[i], h->alloc_bytes[i]);
         if (e == cudaSuccess) e = cudaMemset(h->dev.tables[i], 0, h->alloc_bytes[i]);
         if (e != cudaSuccess) {
+            const unsigned long long want = h->alloc_bytes[i];
+            cudaGetLastError();
             for (int j = 0; j <= i; j++)
                 if (h->dev.tables[j]) cudaFree(h->dev.tables[j]);
             delete h;
-            return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "table %d (%llu bytes): %s", i,
-                        (unsigned long long)h->alloc_bytes[i], cudaGetErrorString(e));
+            return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "table %d (%llu bytes): %s", i, want, cudaGetErrorString(e));
         }
     }
     refresh_dev(h);
@@ -467,7 +483,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -545,7 +561,7 @@ extern "C" int kmgpu_table_nbytes(kmgpu_t* h, int table, uint64_t* nbytes)
 extern "C" int kmgpu_download_table(kmgpu_t* h, int table, uint8_t* dst, uint64_t offset, uint64_t nbytes)
 {
     if (!h || table < 0 || table >= h->nt) return fail(KMGPU_EINVAL, "bad table index");
-    if (offset + nbytes > h->nbytes[table]) return fail(KMGPU_EINVAL, "range past end of table");
+    if (offset > h->nbytes[table] || nbytes > h->nbytes[table] - offset) return fail(KMGPU_EINVAL, "range past end of table");
     std::lock_guard<std::mutex> g(h->mu);
     CKR(set_device(h->device));
     CK(cudaStreamSynchronize(h->stream));
@@ -555,7 +571,7 @@ extern "C" int kmgpu_download_table(kmgpu_t* h, int table, uint8_t* dst, uint64_
 extern "C" int kmgpu_upload_table(kmgpu_t* h, int table, const uint8_t* src, uint64_t offset, uint64_t nbytes)
 {
     if (!h || table < 0 || table >= h->nt) return fail(KMGPU_EINVAL, "bad table index");
-    if (offset + nbytes > h->nbytes[table]) return fail(KMGPU_EINVAL, "range past end of table");
+    if (offset > h->nbytes[table] || nbytes > h->nbytes[table] - offset) return fail(KMGPU_EINVAL, "range past end of table");
     std::lock_guard<std::mutex> g(h->mu);
     CKR(set_device(h->device));
     CK(cudaStreamSynchronize(h->stream));
@@ -925,8 +941,9 @@ struct Part {
     cudaEvent_t ready;
 };
 
+// `rehash`: the chunk has no bins[] array (grouped path): candidates are found by hashing the stream again (k_bigscan2)
 static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const std::vector<Part>& parts, uint32_t n_pos, uint64_t stride, uint64_t n_list,
-                                  uint64_t n_cross)
+                                  uint64_t n_cross, bool rehash = false, const Pred* P = nullptr, bool pred = false, const SketchDev* MS = nullptr)
 {
     cudaStream_t st = h->stream;
     // the small workspaces start at a size that rarely has to grow: a regrowth is a cudaFree + cudaMalloc, i.e. a device
@@ -955,11 +972,33 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const std
     uint64_t cap = n_pos;
     CKR(h->d_events.ensure(cap));
     CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+    if (rehash) {
+        SatBitsG sg;
+        memset(&sg, 0, sizeof sg);
+        for (int i = 0; i < h->nt; i++) sg.t[i] = h->d_satbits[i].p;
+        Pred P0;
+        memset(&P0, 0, sizeof P0);
+        const Pred& PP = P ? *P : P0;
+        const SketchDev& MM = MS ? *MS : h->dev;
+        for (const Part& pt : parts) {
+            const Input& in = pt.in;
+            if (in.n_pos == 0) continue;
+            const unsigned gt = n_tiles(in.n_pos);
+            if (src == 1) k_bigscan2<TWOBIT, 1><<<gt, THREADS, 0, st>>>(h->dev, H, in, sg, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0, h->d_events.p,
+                                                                       (unsigned long long)cap, h->d_ctrl, pt.pos_off, MM, PP, pred ? 1 : 0);
+            else if (H.kind == TWOBIT) k_bigscan2<TWOBIT, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, sg, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0, h->d_events.p,
+                                                                                   (unsigned long long)cap, h->d_ctrl, pt.pos_off, MM, PP, pred ? 1 : 0);
+            else k_bigscan2<MURMUR, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, sg, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0, h->d_events.p,
+                                                             (unsigned long long)cap, h->d_ctrl, pt.pos_off, MM, PP, pred ? 1 : 0);
+            h->all_launches += 1;
+        }
+    }
     SatBits sb;
-    for (int i = 0; i < h->nt; i++) sb.t[i] = h->d_satbits[i].p;
+    memset(&sb, 0, sizeof sb);
+    for (int i = 0; i < h->nt && i < F_MAXT; i++) sb.t[i] = h->d_satbits[i].p;
     for (const Part& pt : parts) {
         const Input& in = pt.in;
-        if (in.n_pos == 0) continue;
+        if (in.n_pos == 0 || rehash) continue;
         const uint32_t* bins = h->d_bins.p + pt.pos_off;
         unsigned gb = (in.n_pos + 255) / 256;
         if (src == 1) k_bigscan<TWOBIT, 1><<<gb, 256, 0, st>>>(h->nt, H, in, bins, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,
@@ -981,7 +1020,7 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const std
     uint32_t* Tarr = nullptr;
     if (n_cross) {
         CKR(h->d_sel.ensure(std::max<uint64_t>(3 * slots, WS_MIN)));
-        CKR(h->d_recslot.ensure(std::max<uint64_t>(n_rec * F_MAXT, 4 * WS_MIN)));
+        CKR(h->d_recslot.ensure(std::max<uint64_t>(n_rec * h->nt, 4 * WS_MIN)));
         SelState ss{h->d_sel.p, h->d_sel.p + slots, h->d_sel.p + 2 * slots};
         const unsigned gsl = (unsigned)((slots + 255) / 256);
         k_sel_slots<<<gr, 256, 0, st>>>(h->d_events.p, n_rec, h->dev, h->d_htkeys.p, slots - 1, h->d_recslot.p);
@@ -1062,6 +1101,8 @@ static void launch_apply(unsigned g, cudaStream_t st, const SketchDev& S, const 
 // `between` (optional) runs on the host after the chunk's kernels have been queued and before the host waits for
 // them: the caller uses it to prepare and upload the next chunk while this one is being ingested.
 typedef std::function<int()> Between;
+
+#include "kmgpu_group_host.inc"
 
 static int ingest_chunk_delta(kmgpu_sketch* h, const std::vector<DeltaPass>& passes, int src, HashCfg H, const std::vector<Part>& parts, const Pred& P,
                               bool pred, const SketchDev* M, ChunkResult* res, const Between& between)
@@ -1315,6 +1356,10 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
 {
     if (in.n_pos == 0) return between ? between() : KMGPU_OK;
     {
+        GroupPlan G;
+        if (plan_group(h, in.n_pos, h->nt > F_MAXT, &G))
+            return ingest_chunk_grouped(h, G, src, H, std::vector<Part>(1, Part{in, 0u, nullptr}), P, pred, M, res, between);
+        if (h->nt > F_MAXT) return fail(KMGPU_EUNSUPPORTED, "sketches with more than %d tables need the grouped path, which this shape cannot take", F_MAXT);
         std::vector<DeltaPass> dp;
         if (plan_delta(h, dp)) return ingest_chunk_delta(h, dp, src, H, std::vector<Part>(1, Part{in, 0u, nullptr}), P, pred, M, res, between);
     }
@@ -1470,13 +1515,26 @@ static int make_pred(kmgpu_sketch* h, const kmgpu_band_t* band, const kmgpu_mask
         *pred = true;
     }
     if (mask) {
-        if (!mask->mask) return fail(KMGPU_EINVAL, "mask sketch is NULL");
-        if (mask->mask->device != h->device) return fail(KMGPU_EINVAL, "mask sketch lives on another device");
+        kmgpu_sketch* m = mask->mask;
+        if (!m) return fail(KMGPU_EINVAL, "mask sketch is NULL");
+        if (m->device != h->device) return fail(KMGPU_EINVAL, "mask sketch lives on another device");
         P->mask_on = 1;
         P->mask_threshold = mask->threshold;
         P->mask_ge = mask->consume_masked ? 1 : 0;
-        *M = &mask->mask->dev;
+        *M = &m->dev;
         *pred = true;
+        if (m != h) {
+            // whatever the mask sketch still has queued (a reset, an ingest) must have landed before this stream reads its
+            // tables; its bigcount map goes along as a sorted device copy (mask->get_count, hashtable.cc:177-178)
+            std::lock_guard<std::mutex> gm(m->mu);
+            CK(cudaStreamSynchronize(m->stream));
+            if (m->kind == BYTE && m->use_bigcount && !m->big.empty()) {
+                CKR(sync_big_to_device(m));
+                P->mask_big_keys = m->big_keys.p;
+                P->mask_big_vals = m->big_vals.p;
+                P->mask_n_big = m->n_big_dev;
+            }
+        }
     }
     return KMGPU_OK;
 }
@@ -1576,7 +1634,10 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
         const uint64_t part_cap = std::max<uint64_t>(std::min<uint64_t>(env_u64("KMGPU_PART_BASES", 24ull << 20), per_chunk),
                                                      (per_chunk + kmgpu_sketch::MAX_PARTS - 1) / kmgpu_sketch::MAX_PARTS);
         const uint64_t worst_pos = per_chunk + (uint64_t)kmgpu_sketch::MAX_PARTS * h->k;
-        if (env_u64("KMGPU_PARTS", 1) && total > part_cap && worst_pos < (1ull << 31) && plan_delta(h, dp) && plan_buckets(h, (uint32_t)worst_pos, &BL)) {
+        GroupPlan GP;
+        const bool grouped = worst_pos < (1ull << 31) && plan_group(h, (uint32_t)worst_pos, h->nt > F_MAXT, &GP);
+        if (env_u64("KMGPU_PARTS", 1) && total > part_cap && worst_pos < (1ull << 31) &&
+            (grouped || (h->nt <= F_MAXT && plan_delta(h, dp) && plan_buckets(h, (uint32_t)worst_pos, &BL)))) {
             struct Staged { std::vector<Part> parts; };
             Staged set[2];
             auto stage_chunk_parts = [&](uint64_t ci, Staged* out) -> int {
@@ -1602,9 +1663,16 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
             CKR(stage_chunk_parts(0, &set[0]));
             for (uint64_t ci = 0; ci < n_chunks; ci++) {
                 if (set[ci & 1].parts.empty()) break;
-                CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &res, [&]() -> int {
-                    return ci + 1 < n_chunks ? stage_chunk_parts(ci + 1, &set[(ci + 1) & 1]) : KMGPU_OK;
-                }));
+                const Between next = [&]() -> int { return ci + 1 < n_chunks ? stage_chunk_parts(ci + 1, &set[(ci + 1) & 1]) : KMGPU_OK; };
+                if (grouped) {
+                    uint32_t np = 0;
+                    for (const Part& pt : set[ci & 1].parts) np = std::max(np, pt.pos_off + pt.in.n_pos);
+                    GroupPlan G;   // the regions are sized for this chunk's positions
+                    if (!plan_group(h, np, true, &G)) return fail(KMGPU_ECUDA, "internal: grouped plan changed between chunks");
+                    CKR(ingest_chunk_grouped(h, G, 0, H, set[ci & 1].parts, P, pred, M, &res, next));
+                } else {
+                    CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &res, next));
+                }
             }
             if (n_kmers_out) *n_kmers_out = res.n_kmers;
             return KMGPU_OK;

@@ -35,6 +35,9 @@ struct Pred {  // band and mask predicates; both off in the plain path
     int mask_on;
     uint32_t mask_threshold;
     int mask_ge;  // consume_masked: consume iff count >= threshold, else iff count <= threshold
+    const uint64_t* mask_big_keys;  // sorted device copy of the mask sketch's bigcount map (ByteStorage with bigcount)
+    const uint16_t* mask_big_vals;
+    uint32_t mask_n_big;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,777 @@
+// Grouped ingestion, second generation (the headline path).
+//
+// A chunk's counter updates are grouped by 32 Ki-bin BUCKET of their table and every bucket is then applied by one CTA
+// in shared memory (touch counts, first touchers, the table slice itself), exactly like the first bucket path — but:
+//
+//   * hashing is fused into the grouping kernel: k_part walks the 2-bit read stream, hashes, reduces modulo the table
+//     size and sorts the records of its tile by bucket in shared memory; the bins[N][n_pos] array (37 B per k-mer of
+//     DRAM traffic) and the k_hashbins launch are gone;
+//   * tables of any size: a table with more than PART_MAXP buckets is grouped in two levels — first by SUPER-BUCKET
+//     (2^27 bins = 4096 buckets), then each super-bucket's records by bucket; bins are 64-bit throughout;
+//   * a bucket that receives more records than its home region holds does not fail the chunk: the grouping is redone
+//     once with exact (CSR) offsets taken from the demand the first run counted, and k_apply clamps its 16-bit touch
+//     lanes between rounds of 32 Ki records, so any load is exact;
+//   * k_apply moves its table slice with bulk asynchronous copies (cp.async.bulk + mbarrier: global -> shared before the
+//     records are counted, shared -> global after the sweep) and keeps it in shared memory, which also tells every
+//     record for free whether its bin was empty before the chunk — only those records pay the first-toucher atomicMin;
+//   * sparse regimes (a few hundred records per bucket: tables far larger than a chunk) use k_apply_sparse, whose cost
+//     is proportional to the records, not to the bucket.
+//
+// Reference semantics: Storage::add for the three storages (include/oxli/storage.hh:571-624, :320-359, :172-199) applied
+// to the k-mer stream of Hashtable::consume_string (src/oxli/hashtable.cc:280-294) in stream order.
+#pragma once
+#include "kmgpu_kernels.cuh"
+
+namespace kmgpu {
+
+constexpr int G_MAXT = MAX_TABLES;                       // tables per sketch on this path
+constexpr int SB_SHIFT = 12;                             // buckets per super-bucket (two-level grouping)
+constexpr int SB_BIN_SHIFT = BKT_SHIFT + SB_SHIFT;       // 27: bins per super-bucket
+constexpr int PART_MAXP = 6144;                          // partitions one k_part CTA can sort into (shared-memory histogram)
+
+struct GroupLayout {
+    uint32_t first[G_MAXT + 1];      // table i owns buckets [first[i], first[i+1])
+    uint32_t first_sb[G_MAXT + 1];   // two-level: table i owns super-buckets [first_sb[i], first_sb[i+1])
+    uint32_t cap;                    // home region of a bucket, in records (uniform layout)
+    uint32_t cap1;                   // home region of a super-bucket
+    int n_tables;
+    int two_level;
+};
+
+struct SatBitsG {
+    uint8_t* t[G_MAXT];
+};
+
+// a record store: region of partition p = [off ? off[p] : p * cap, + (off ? off[p+1] - off[p] : cap))
+struct Store {
+    unsigned long long* rec;
+    const unsigned long long* off;   // exact (CSR) offsets of partitions p0 .. (indexed p - p0), or nullptr for the uniform layout
+    uint32_t* cursor;                // records written to (demanded of) every partition (indexed by p)
+    uint32_t cap;
+    uint32_t p0;                     // first partition held (tables are grouped in turns when memory is short)
+    __device__ __forceinline__ unsigned long long base(uint32_t p) const { return off ? off[p - p0] : (unsigned long long)(p - p0) * cap; }
+    __device__ __forceinline__ uint32_t room(uint32_t p) const { return off ? (uint32_t)(off[p - p0 + 1] - off[p - p0]) : cap; }
+};
+
+// ---- bulk asynchronous copies + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KM_DONE_%=;\n"
+        "bra KM_WAIT_%=;\n"
+        "KM_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// =====================================================================================================================
+// 1. k_part: sort the records of one tile by partition in shared memory and append each partition's run to its region.
+//
+//   MODE 0  stream -> buckets            partition = bin >> 15            record = position << 15 | bin & 0x7FFF
+//   MODE 1  stream -> super-buckets      partition = bin >> 27            record = position << 27 | bin & 0x7FFFFFF
+//   MODE 2  super-bucket -> its buckets  partition = (rec >> 15) & 0xFFF  record = position << 15 | bin & 0x7FFF
+//
+//   SRC 0: the k-mers are hashed here from the 2-bit stream (TwoBit);  SRC 1: 64-bit hashes precomputed by k_hash64
+//   (Murmur: hashing 2 x k letters per table would dominate) or supplied by the caller (kmgpu_add_hashes).
+//   grid = (tiles, tables) for MODE 0/1, (tiles of the largest super-bucket, super-buckets) for MODE 2.
+// =====================================================================================================================
+struct PartArgs {
+    SketchDev S;          // full table sizes and magics
+    HashCfg H;
+    Input in;             // MODE 0/1: the part of the chunk being grouped
+    uint32_t pos_base;    // its first position within the chunk
+    int have_valid;       // SRC 1: 0 = every position of `in` is a k-mer (caller-supplied hashes), 1 = validity from the read offsets
+    int table0;           // MODE 0/1: first table of this launch (blockIdx.y is relative to it); MODE 2: first super-bucket
+    uint32_t tiles_per_src;   // MODE 2: blockIdx.x = (super-bucket - table0) * tiles_per_src + tile
+    int count_kmers;      // MODE 0/1: table 0's CTAs add the k-mers they consumed to ctrl->n_kmers (off in a regrouping run)
+    GroupLayout L;
+    Store dst;            // MODE 0/2: bucket store; MODE 1: super-bucket store
+    Store src;            // MODE 2: super-bucket store
+    Ctrl* ctrl;
+    unsigned long long ovf_bit;   // set in ctrl->overflow when a destination region runs out of room
+};
+
+template <int T>
+struct PartTile {
+    uint64_t words[T / 32 + TILE_PAD_WORDS];
+    uint32_t valid[T / 32];
+};
+
+// WIDE: run bases kept in 32 bits (super-buckets; regions with exact offsets, which may hold more than 65535 records)
+__host__ __device__ constexpr size_t part_smem(int T, bool wide)
+{
+    return (size_t)T * 8 + (size_t)PART_MAXP * 4 * (wide ? 2 : 1) + (size_t)(T / 32 + TILE_PAD_WORDS) * 8 + (size_t)(T / 32) * 4 + 16;
+}
+
+// stage the tile's stream words and the bitmap of valid k-mer starts (cf. tile_begin, for tiles of T positions)
+template <int T, int NTHR, int SRC>
+__device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t t0, int have_valid, PartTile<T>& sm)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < T / 32; i += NTHR) sm.valid[i] = 0;
+    if (SRC == 0) {
+        const uint32_t total_words = ((in.n_pos + TILE - 1) / TILE) * (TILE / 32) + TILE_PAD_WORDS;
+        const uint32_t w0 = t0 >> 5;
+        for (int i = tid; i < T / 32 + TILE_PAD_WORDS; i += NTHR) sm.words[i] = w0 + i < total_words ? __ldg(in.words + w0 + i) : 0ull;
+    }
+    __syncthreads();
+    if (SRC == 1 && !have_valid) {
+        const uint32_t n = in.n_pos - t0 < (uint32_t)T ? in.n_pos - t0 : (uint32_t)T;
+        for (int i = tid; i < T / 32; i += NTHR) {
+            uint32_t lo = i * 32;
+            sm.valid[i] = lo >= n ? 0u : (n - lo >= 32 ? ~0u : ((1u << (n - lo)) - 1));
+        }
+        __syncthreads();
+        return;
+    }
+    const uint32_t n_tiles4k = (in.n_pos + TILE - 1) / TILE;
+    const uint32_t tb = t0 / TILE;
+    const uint32_t te = tb + T / TILE < n_tiles4k ? tb + T / TILE : n_tiles4k;
+    const uint32_t r_lo = in.tfr[tb];
+    uint32_t r_hi = in.tfr[te] + 1;
+    if (r_hi > in.n_reads) r_hi = in.n_reads;
+    for (uint32_t r = r_lo + tid; r < r_hi; r += NTHR) {
+        uint32_t s = in.offs[r], e = in.offs[r + 1];
+        if (e - s < (uint32_t)k) continue;
+        uint32_t first = s > t0 ? s : t0;
+        uint32_t last = e - k;  // inclusive
+        if (last >= t0 + T) last = t0 + T - 1;
+        if (first > last || last < t0) continue;
+        uint32_t a = first - t0, b = last - t0;
+        for (uint32_t wd = a >> 5; wd <= (b >> 5); wd++) {
+            uint32_t lo = wd == (a >> 5) ? (a & 31) : 0;
+            uint32_t hi = wd == (b >> 5) ? (b & 31) : 31;
+            uint32_t m = (hi == 31 ? ~0u : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+            atomicOr(&sm.valid[wd], m);
+        }
+    }
+    __syncthreads();
+}
+
+template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP>
+__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
+k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P)
+{
+    constexpr bool WIDE = MODE == 1 || WIDEP;
+    constexpr int PER = T / NTHR;
+    constexpr int BPT = (PART_MAXP + NTHR - 1) / NTHR;
+    constexpr int PB = MODE == 1 ? SB_BIN_SHIFT : BKT_SHIFT;   // payload bits of the records written
+    extern __shared__ __align__(16) unsigned char pt_raw[];
+    uint2* stage = reinterpret_cast<uint2*>(pt_raw);                          // T slots, grouped by partition
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // PART_MAXP: count, then run start | cursor base << 16
+    uint32_t* gb32 = hist + PART_MAXP;                                        // WIDE only: 32-bit cursor bases
+    PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(hist + PART_MAXP * (WIDE ? 2 : 1));
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t p0 = (MODE == 2 ? blockIdx.x % A.tiles_per_src : blockIdx.x) * (uint32_t)T;
+
+    // which partitions this CTA sorts into
+    int t;                 // table
+    uint32_t np;           // number of partitions
+    uint32_t cur0;         // index of partition 0 in dst.cursor / dst regions
+    uint32_t n_src = 0;    // MODE 2: records of the source super-bucket
+    const unsigned long long* srec = nullptr;
+    if (MODE == 2) {
+        const uint32_t sb = (uint32_t)A.table0 + blockIdx.x / A.tiles_per_src;
+        t = 0;
+#pragma unroll 1
+        for (int i = 1; i < A.L.n_tables; i++)
+            if (sb >= A.L.first_sb[i]) t = i;
+        const uint32_t sbi = sb - A.L.first_sb[t];
+        const uint32_t nb_t = A.L.first[t + 1] - A.L.first[t];
+        np = nb_t - (sbi << SB_SHIFT);
+        if (np > (1u << SB_SHIFT)) np = 1u << SB_SHIFT;
+        cur0 = A.L.first[t] + (sbi << SB_SHIFT);
+        n_src = A.src.cursor[sb];
+        const uint32_t room = A.src.room(sb);
+        if (n_src > room) n_src = room;   // the super-bucket overflowed: ctrl->overflow is set, the chunk is regrouped
+        if (p0 >= n_src) return;
+        srec = A.src.rec + A.src.base(sb);
+    } else {
+        t = A.table0 + blockIdx.y;
+        if (MODE == 0) {
+            np = A.L.first[t + 1] - A.L.first[t];
+            cur0 = A.L.first[t];
+        } else {
+            np = A.L.first_sb[t + 1] - A.L.first_sb[t];
+            cur0 = A.L.first_sb[t];
+        }
+        if (p0 >= A.in.n_pos) return;
+    }
+
+    // ---- phase 1: keys, ranks within this CTA's runs (one shared-memory atomic per record) --------------------------
+    uint32_t key[PER];              // MODE 0/2: partition << 15 | payload (15 bits);  MODE 1: payload (27 bits)
+    uint32_t pid1[(PER + 1) / 2];   // MODE 1: partitions, two per word
+    uint32_t rk[(PER + 1) / 2];     // ranks, two per word
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < np; i += NTHR) hist[i] = 0;
+    unsigned n_k = 0;
+    if (MODE == 2) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t e = p0 + j * NTHR + tid;
+            key[j] = NONE;
+            if (e < n_src) key[j] = (uint32_t)__ldcs(srec + e) & ((1u << SB_BIN_SHIFT) - 1);   // partition << 15 | bin in bucket
+        }
+    } else {
+        part_tile_begin<T, NTHR, SRC>(A.in, A.H.k, p0, A.have_valid, tile);   // ends with __syncthreads()
+        const uint64_t size = A.S.sizes[t], magic = A.S.magic[t];
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t lp = j * NTHR + tid;
+            key[j] = NONE;
+            if (MODE == 1) {
+                if (j & 1) pid1[j >> 1] |= 0xFFFF0000u; else pid1[j >> 1] = 0xFFFFu;
+            }
+            if (p0 + lp < A.in.n_pos && ((tile.valid[lp >> 5] >> (lp & 31)) & 1u)) {
+                const uint64_t h = SRC == 1 ? __ldcs(A.in.hashes + p0 + lp) : hash_twobit(tile.words, lp, A.H.k);
+                if (!PRED || pred_pass(P, M, h)) {
+                    const uint64_t bin = mod_magic(h, size, magic);
+                    n_k++;
+                    if (MODE == 1) {
+                        key[j] = (uint32_t)bin & ((1u << SB_BIN_SHIFT) - 1);
+                        const uint32_t pid = (uint32_t)(bin >> SB_BIN_SHIFT);
+                        if (j & 1) pid1[j >> 1] = (pid1[j >> 1] & 0xFFFFu) | (pid << 16); else pid1[j >> 1] = (pid1[j >> 1] & 0xFFFF0000u) | pid;
+                    } else {
+                        key[j] = (uint32_t)bin;   // MODE 0 tables have at most PART_MAXP << 15 < 2^28 bins
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        uint32_t r = 0;
+        if (key[j] != NONE) {
+            const uint32_t pid = MODE == 1 ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
+            r = atomicAdd(&hist[pid], 1u);
+        }
+        if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
+    }
+    if (MODE != 2 && t == 0 && A.count_kmers) {   // the k-mers of the chunk are counted once, by the CTAs of table 0
+        n_k = __reduce_add_sync(0xffffffffu, n_k);
+        if ((tid & 31) == 0 && n_k) atomicAdd(&A.ctrl->n_kmers, (unsigned long long)n_k);
+    }
+    __syncthreads();
+
+    // ---- phase 2: exclusive scan of the partition counts (BPT consecutive partitions per thread), reservations -------
+    uint32_t c[BPT], mine = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const uint32_t b = tid * BPT + q;
+        c[q] = b < np ? hist[b] : 0;
+        mine += c[q];
+    }
+    uint32_t incl = mine;
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < NTHR / 32 ? s_warp[lane] : 0, w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += u;
+        }
+        s_warp[lane] = w - v;
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    uint32_t at = s_warp[wid] + incl - mine, gbase[BPT];
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const uint32_t b = tid * BPT + q;
+        if (b < np) hist[b] = at;   // run start (the count has been read by its only reader, this thread)
+        gbase[q] = c[q] ? atomicAdd(&A.dst.cursor[cur0 + b], c[q]) : 0u;   // in flight while the records are placed
+        at += c[q];
+    }
+    __syncthreads();
+
+    // ---- phase 3: place the records in partition order -----------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        if (key[j] == NONE) continue;
+        const uint32_t pid = MODE == 1 ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
+        const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
+        const uint32_t slot = (hist[pid] & 0xFFFFu) + r;
+        if (MODE == 2) {
+            // the position travels with the record: fetch it again (L1/L2 hit) rather than hold 16 more registers
+            const unsigned long long v = __ldcs(srec + p0 + j * NTHR + tid);
+            stage[slot] = make_uint2((uint32_t)(v >> SB_BIN_SHIFT), key[j]);
+        } else if (MODE == 1) {
+            stage[slot] = make_uint2(key[j], (pid << 14) | (uint32_t)(j * NTHR + tid));
+        } else {
+            stage[slot] = make_uint2(key[j] & (BKT_BINS - 1), (pid << 14) | (uint32_t)(j * NTHR + tid));
+        }
+    }
+    // run start (low half) and cursor base: the low half is not changed by this store, so a placement still reading
+    // hist[pid] & 0xFFFF sees the same value before and after it
+#pragma unroll
+    for (int q = 0; q < BPT; q++) {
+        const uint32_t b = tid * BPT + q;
+        if (b < np) {
+            if (WIDE) gb32[b] = gbase[q];
+            else hist[b] = (hist[b] & 0xFFFFu) | (gbase[q] << 16);   // uniform regions hold <= 65535 records; a base past 2^16
+                                                                     // belongs to a region that has already been reported full
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: runs of consecutive records leave for their regions ---------------------------------------------------
+    const uint32_t total = s_total;
+    bool over = false;
+    for (uint32_t s = tid; s < total; s += NTHR) {
+        const uint2 m = stage[s];
+        const uint32_t pid = MODE == 2 ? m.y >> BKT_SHIFT : m.y >> 14;
+        const uint32_t hv = hist[pid];
+        const uint32_t idx = (WIDE ? gb32[pid] : hv >> 16) + (s - (hv & 0xFFFFu));
+        unsigned long long rec;
+        if (MODE == 2) rec = ((unsigned long long)m.x << BKT_SHIFT) | (m.y & (BKT_BINS - 1));
+        else rec = ((unsigned long long)(A.pos_base + p0 + (m.y & 0x3FFFu)) << PB) | m.x;
+        if (idx < A.dst.room(cur0 + pid)) A.dst.rec[A.dst.base(cur0 + pid) + idx] = rec;
+        else over = true;
+    }
+    if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
+}
+
+// 64-bit hashes of every position (Murmur): one pass, then k_part<SRC 1> per table
+template <int HK>
+__global__ void __launch_bounds__(THREADS)
+k_hash64(HashCfg H, Input in, uint64_t* __restrict__ out)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, 0>(in, H.k, t0, sm);
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (tile_valid<HK, 0>(sm, lp)) __stcs(&out[t0 + lp], tile_hash<HK, 0>(in, sm, H.k, t0, lp));
+    }
+}
+
+// exclusive scan of the demanded counts into exact offsets (regrouping run): off[p] for p in [0, n], single CTA
+__global__ void __launch_bounds__(1024) k_exact_offsets(const uint32_t* __restrict__ cnt, uint32_t n, unsigned long long* __restrict__ off)
+{
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        // regions start on even record indices (16-byte alignment of every run's first record is not required, but an
+        // even start keeps 16-byte loads of whole regions possible)
+        unsigned long long v = i < n ? (((unsigned long long)cnt[i] + 1) & ~1ull) : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads();
+        unsigned long long before = s_carry;
+        for (uint32_t w = 0; w < wid; w++) before += s_w[w];
+        if (i < n) off[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = s_carry;
+}
+
+// =====================================================================================================================
+// 2. k_apply2: one CTA per bucket.  Shared memory: 16-bit touch lanes (64 KB), first-toucher positions (128 KB), the
+//    bucket's slice of the table (32 / 16 / 4 KB).
+// =====================================================================================================================
+template <int KIND>
+__host__ __device__ constexpr uint32_t slice_bytes_full() { return KIND == BYTE ? BKT_BINS : KIND == NIBBLE ? BKT_BINS / 2 : BKT_BINS / 8; }
+template <int KIND>
+constexpr size_t apply2_smem() { return (size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4 + slice_bytes_full<KIND>() + 64; }
+
+template <int KIND>
+__device__ __forceinline__ bool slice_empty(const uint8_t* slice, uint32_t lb)
+{
+    if (KIND == BYTE) return slice[lb] == 0;
+    if (KIND == NIBBLE) return ((slice[lb >> 1] >> ((lb & 1) ? 0 : 4)) & 15u) == 0;
+    return !((slice[lb >> 3] >> (lb & 7)) & 1u);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(1024, 1)
+k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
+         uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
+         unsigned long long ovf_mask)
+{
+    extern __shared__ __align__(128) unsigned char ap_raw[];
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // BKT_BINS / 2 words, two 16-bit lanes each
+    uint32_t* minpos = cnt + BKT_BINS / 2;                                     // BKT_BINS words
+    uint8_t* slice = reinterpret_cast<uint8_t*>(minpos + BKT_BINS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(slice + slice_bytes_full<KIND>());
+    if (ctrl->overflow & ovf_mask) return;      // a region of this table group ran out of room: the group is regrouped with exact offsets
+    const uint32_t b = bucket0 + blockIdx.x;
+    const uint32_t n = st.cursor[b];
+    if (n == 0) return;
+    int t = 0;
+#pragma unroll 1
+    for (int i = 1; i < L.n_tables; i++)
+        if (b >= L.first[i]) t = i;
+    const uint64_t bin0 = (uint64_t)(b - L.first[t]) << BKT_SHIFT;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t size = S.sizes[t];
+    int changed = 0;
+    uint8_t* table = S.tables[t];
+    // bytes of the table this bucket covers, rounded up to the 16-byte granule of bulk copies (tables are allocated in
+    // whole granules; bytes past the last bin are written back as they were read)
+    const uint64_t tbytes = KIND == BYTE ? size : KIND == NIBBLE ? size / 2 + 1 : size / 8 + 1;
+    const uint64_t byte0 = KIND == BYTE ? bin0 : KIND == NIBBLE ? bin0 >> 1 : bin0 >> 3;
+    uint32_t sbytes = (uint32_t)(tbytes - byte0 < slice_bytes_full<KIND>() ? tbytes - byte0 : slice_bytes_full<KIND>());
+    sbytes = (sbytes + 15u) & ~15u;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, sbytes);
+        bulk_g2s(slice, table + byte0, sbytes, bar);
+    }
+    {
+        uint4* f = reinterpret_cast<uint4*>(minpos);
+        for (uint32_t i = tid; i < BKT_BINS / 4; i += 1024) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (KIND != BIT) {
+            uint4* z = reinterpret_cast<uint4*>(cnt);
+            for (uint32_t i = tid; i < BKT_BINS / 8; i += 1024) z[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const unsigned long long* src = st.rec + st.base(b);
+    constexpr int RIF = 16;   // records in flight per thread
+    for (uint32_t e0 = 0; e0 < n; e0 += RIF * 1024) {
+        unsigned long long v[RIF];
+#pragma unroll
+        for (int j = 0; j < RIF; j++) {
+            uint32_t e = e0 + j * 1024 + tid;
+            v[j] = e < n ? __ldcs(src + e) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < RIF; j++) {
+            if (v[j] == ~0ull) continue;
+            const uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
+            if (KIND != BIT) atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+            // only a bin that was empty before the chunk can make its first toucher a new k-mer
+            if (slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+        }
+        if (KIND != BIT && n > 65535u && ((e0 / (RIF * 1024)) & 1u)) {
+            // more records than a 16-bit lane can count: clamp every lane to 0x7FFF after each 32 Ki records (any value
+            // >= the counter's cap saturates it just the same), so the next 32 Ki cannot wrap a lane into its neighbour
+            __syncthreads();
+            for (uint32_t i = tid; i < BKT_BINS / 2; i += 1024) {
+                const uint32_t w = cnt[i];
+                const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
+                cnt[i] = (lo > 0x7FFFu ? 0x7FFFu : lo) | ((hi > 0x7FFFu ? 0x7FFFu : hi) << 16);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    unsigned n_new = 0, n_sat = 0, n_cross = 0;
+    constexpr int GPT = BKT_BINS / 8 / 1024;
+#pragma unroll
+    for (int q = 0; q < GPT; q++) {
+        const uint32_t g = q * 1024 + tid;
+        const uint64_t b0 = bin0 + (uint64_t)g * 8;
+        unsigned newm = 0;
+        if (KIND == BIT) {
+            const uint4 m0 = reinterpret_cast<const uint4*>(minpos)[g * 2], m1 = reinterpret_cast<const uint4*>(minpos)[g * 2 + 1];
+            const uint32_t mp[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) newm |= (unsigned)(mp[j] != ~0u) << j;   // only bins that were clear carry a position
+            if (!newm) continue;
+            changed = 1;
+            slice[g] = (uint8_t)(slice[g] | newm);
+            n_new += __popc(newm);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((newm >> j) & 1u) atomicOr(&newbits[mp[j] >> 5], 1u << (mp[j] & 31));
+            continue;
+        }
+        const uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
+        if (!(c4.x | c4.y | c4.z | c4.w)) continue;
+        const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+        unsigned crossm = 0;
+        changed = 1;
+        if (KIND == BYTE) {
+            const uint64_t old64 = *reinterpret_cast<const uint64_t*>(slice + (size_t)g * 8);
+            uint64_t new64 = old64;
+            unsigned fullm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (!m) continue;
+                uint32_t s = (uint32_t)(old64 >> (8 * j)) & 255u, tt = s + m, nv = tt > 255u ? 255u : tt;
+                new64 = (new64 & ~(255ull << (8 * j))) | ((uint64_t)nv << (8 * j));
+                newm |= (unsigned)(s == 0) << j;
+                n_sat += tt > 255u;
+                crossm |= (unsigned)(tt >= 255u && s < 255u) << j;
+                fullm |= (unsigned)(nv == 255u) << j;
+            }
+            *reinterpret_cast<uint64_t*>(slice + (size_t)g * 8) = new64;
+            if (want_cross && fullm) {
+                unsigned m = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) m |= (unsigned)(((new64 >> (8 * j)) & 255u) == 255u) << j;
+                sb.t[t][b0 >> 3] = (uint8_t)m;
+            }
+            n_cross += __popc(crossm);
+            if (want_cross && crossm) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!((crossm >> j) & 1u)) continue;
+                    unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+                    if (at < list_cap) binlist[at] = BL_CROSS | (((old64 >> (8 * j)) & 255ull) << 48) | ht_key(b0 + j, t);
+                }
+            }
+        } else {
+            const uint32_t old32 = *reinterpret_cast<const uint32_t*>(slice + (size_t)g * 4);
+            uint32_t new32 = old32;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                if (!m) continue;
+                const uint32_t sh = (j >> 1) * 8 + ((j & 1) ? 0 : 4);   // even bin -> high nibble
+                uint32_t s = (old32 >> sh) & 15u, tt = s + m, nv = tt > 15u ? 15u : tt;
+                new32 = (new32 & ~(15u << sh)) | (nv << sh);
+                newm |= (unsigned)(s == 0) << j;
+            }
+            *reinterpret_cast<uint32_t*>(slice + (size_t)g * 4) = new32;
+        }
+        n_new += __popc(newm);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!((newm >> j) & 1u)) continue;
+            const uint32_t p = minpos[g * 8 + j];
+            atomicOr(&newbits[p >> 5], 1u << (p & 31));
+        }
+    }
+    // the slice goes back in one bulk copy (generic-proxy writes made visible to the async proxy first)
+    fence_proxy_async();
+    __shared__ unsigned s_tot[3];
+    if (tid < 3) s_tot[tid] = 0;
+    changed = __syncthreads_or(changed);
+    if (tid == 0 && changed) {   // a bucket whose touches changed nothing (a warm Bloom filter) writes nothing
+        bulk_s2g(table + byte0, slice, sbytes);
+        bulk_commit_wait_read();
+    }
+    n_new = __reduce_add_sync(0xffffffffu, n_new);
+    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
+    if ((tid & 31) == 0) {
+        if (n_new) atomicAdd(&s_tot[0], n_new);
+        if (n_sat) atomicAdd(&s_tot[1], n_sat);
+        if (n_cross) atomicAdd(&s_tot[2], n_cross);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_tot[0]) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)s_tot[0]);
+            atomicAdd(&ctrl->n_new_t[t], (unsigned long long)s_tot[0]);
+            if (t == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)s_tot[0]);
+        }
+        if (s_tot[1]) atomicAdd(&ctrl->n_sat, (unsigned long long)s_tot[1]);
+        if (s_tot[2]) atomicAdd(&ctrl->n_cross, (unsigned long long)s_tot[2]);
+    }
+}
+
+// =====================================================================================================================
+// 3. k_apply_sparse: buckets that receive few records (tables far larger than a chunk).  The records of a bucket are
+//    aggregated per bin in a small shared-memory hash table (slots = power of two >= 2 n), then every distinct bin is
+//    updated in place with a compare-and-swap on its 32-bit word — DRAM sees only the sectors that are touched.
+//    One CTA of 128 threads per bucket; shared memory 12 bytes per slot.
+// =====================================================================================================================
+constexpr uint32_t SPARSE_MAX_RECORDS = 4096;   // per bucket (8192 slots = 96 KB)
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+k_apply_sparse(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
+               uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
+               unsigned long long ovf_mask)
+{
+    extern __shared__ __align__(16) uint32_t sp_raw[];
+    if (ctrl->overflow & ovf_mask) return;
+    const uint32_t b = bucket0 + blockIdx.x;
+    const uint32_t n = st.cursor[b];
+    if (n == 0) return;
+    if (n > st.room(b) || n > SPARSE_MAX_RECORDS) return;   // reported by k_part (regions of this launch hold <= SPARSE_MAX_RECORDS)
+    uint32_t slots = 64;
+    while (slots < 2 * n) slots <<= 1;
+    uint32_t* hk = sp_raw;            // bin in bucket + 1, 0 = free
+    uint32_t* hc = hk + slots;        // touches
+    uint32_t* hp = hc + slots;        // smallest touching position
+    int t = 0;
+#pragma unroll 1
+    for (int i = 1; i < L.n_tables; i++)
+        if (b >= L.first[i]) t = i;
+    const uint64_t bin0 = (uint64_t)(b - L.first[t]) << BKT_SHIFT;
+    uint8_t* table = S.tables[t];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < slots; i += 128) {
+        hk[i] = 0;
+        hc[i] = 0;
+        hp[i] = ~0u;
+    }
+    __syncthreads();
+    const unsigned long long* src = st.rec + st.base(b);
+    const uint32_t mask = slots - 1;
+    for (uint32_t e = tid; e < n; e += 128) {
+        const unsigned long long v = __ldcs(src + e);
+        const uint32_t lb = (uint32_t)v & (BKT_BINS - 1), key = lb + 1;
+        uint32_t s = (lb * 0x9E3779B1u) >> 7 & mask;
+        while (true) {
+            const uint32_t prev = atomicCAS(&hk[s], 0u, key);
+            if (prev == 0u || prev == key) break;
+            s = (s + 1) & mask;
+        }
+        atomicAdd(&hc[s], 1u);
+        atomicMin(&hp[s], (uint32_t)(v >> BKT_SHIFT));
+    }
+    __syncthreads();
+    unsigned n_new = 0, n_sat = 0, n_cross = 0;
+    for (uint32_t s = tid; s < slots; s += 128) {
+        if (!hk[s]) continue;
+        const uint64_t bin = bin0 + (hk[s] - 1);
+        const uint32_t m = hc[s];
+        uint32_t before;
+        if (KIND == BIT) {
+            uint32_t* word = reinterpret_cast<uint32_t*>(table) + (bin >> 5);
+            const uint32_t bit = 1u << (bin & 31);
+            before = (atomicOr(word, bit) & bit) ? 1u : 0u;
+        } else {
+            constexpr uint32_t CAP = KIND == BYTE ? 255u : 15u;
+            uint32_t* word;
+            uint32_t sh;
+            if (KIND == BYTE) {
+                word = reinterpret_cast<uint32_t*>(table + (bin & ~3ull));
+                sh = (uint32_t)(bin & 3) * 8;
+            } else {
+                const uint64_t byte = bin >> 1;
+                word = reinterpret_cast<uint32_t*>(table + (byte & ~3ull));
+                sh = (uint32_t)(byte & 3) * 8 + ((bin & 1) ? 0 : 4);
+            }
+            uint32_t cur = __ldcg(word);
+            while (true) {
+                before = (cur >> sh) & CAP;
+                const uint32_t tt = before + m, nv = tt > CAP ? CAP : tt;
+                if (nv == before) break;
+                const uint32_t seen = atomicCAS(word, cur, (cur & ~(CAP << sh)) | (nv << sh));
+                if (seen == cur) break;
+                cur = seen;
+            }
+            if (KIND == BYTE) {
+                const uint32_t tt = before + m;
+                n_sat += tt > 255u;
+                if (tt >= 255u && before < 255u) {
+                    n_cross++;
+                    if (want_cross) {
+                        unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+                        if (at < list_cap) binlist[at] = BL_CROSS | ((unsigned long long)before << 48) | ht_key(bin, t);
+                    }
+                }
+                if (want_cross && tt >= 255u) atomicOr(reinterpret_cast<uint32_t*>(sb.t[t]) + (bin >> 5), 1u << (bin & 31));
+            }
+        }
+        if (before == 0) {
+            n_new++;
+            const uint32_t p = hp[s];
+            atomicOr(&newbits[p >> 5], 1u << (p & 31));
+        }
+    }
+    n_new = __reduce_add_sync(0xffffffffu, n_new);
+    n_sat = __reduce_add_sync(0xffffffffu, n_sat);
+    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
+    if ((tid & 31) == 0) {
+        if (n_new) {
+            atomicAdd(&ctrl->n_zbits, (unsigned long long)n_new);
+            atomicAdd(&ctrl->n_new_t[t], (unsigned long long)n_new);
+            if (t == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)n_new);
+        }
+        if (n_sat) atomicAdd(&ctrl->n_sat, (unsigned long long)n_sat);
+        if (n_cross) atomicAdd(&ctrl->n_cross, (unsigned long long)n_cross);
+    }
+}
+
+// =====================================================================================================================
+// 4. bigcount scan for this path (no bins[] array): re-hash the stream, probe the saturation bitmaps (one bit per bin,
+//    kept by k_apply2 / k_apply_sparse).  Reports the same events as k_bigscan.
+// =====================================================================================================================
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_bigscan2(const __grid_constant__ SketchDev S, HashCfg H, Input in, const __grid_constant__ SatBitsG sat, const uint64_t* __restrict__ keys,
+           uint64_t mask, int have_cross, Event* out, unsigned long long cap, Ctrl* ctrl, uint32_t pos_base, const __grid_constant__ SketchDev M,
+           const __grid_constant__ Pred P, int pred)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    const int nt = S.n_tables;
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        if (pred && !pred_pass(P, M, h)) continue;
+        bool allsat = true;
+        uint32_t cross = 0;
+        for (int i = 0; i < nt; i++) {
+            const uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+            const bool s = (__ldg(&sat.t[i][bin >> 3]) >> (bin & 7)) & 1u;
+            allsat &= s;
+            if (!s && !have_cross) break;
+            if (s && have_cross && ht_find(keys, mask, ht_key(bin, i)) != ~0ull) cross |= 1u << i;
+        }
+        if (!cross && !allsat) continue;
+        Event e;
+        e.hash = h;
+        e.pos = pos_base + t0 + lp;
+        e.info = cross | ((uint32_t)allsat << 30);
+        unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+        if (at < cap) out[at] = e;
+    }
+}
+
+}  // namespace kmgpu

@@ -17,9 +17,12 @@ struct Ctrl {
     unsigned long long n_unique;  // result of the first-toucher resolution
     unsigned long long n_events;  // records appended by k_events / k_cross_replay
     unsigned long long non_acgt;  // pack kernel: bytes outside ACGT seen in raw mode
-    unsigned long long n_new_t[10];  // delta path: newly occupied bins per table
+    unsigned long long n_new_t[32];  // newly occupied bins per table
     unsigned long long pass_list_end[64];  // delta path: bin list entries appended by each (table, block) pass
-    unsigned long long overflow;  // bucket path: a bucket ran out of room (the chunk is redone by the delta passes)
+    unsigned long long overflow;  // bucket path: a bucket ran out of room (the chunk is redone by the delta passes);
+                                  // grouped path: bit 2g = a super-bucket region of table group g ran out of room,
+                                  // bit 2g+1 = a bucket region did (the group is regrouped with exact offsets)
+    unsigned long long queue_overflow;  // address-sharded mode: updates that did not fit a receive queue
 };
 
 // flags word per position: bits 0..9 table mask "saw 0", 10..19 "saw 255", 20..29 "saw 254", 31 consumed
@@ -130,6 +133,16 @@ __device__ __forceinline__ bool pred_pass(const Pred& P, const SketchDev& M, uin
     if (P.band_on && !(h >= P.band_lo && h < P.band_hi)) return false;
     if (P.mask_on) {
         uint32_t c = sketch_count(M, h);
+        // mask->get_count(kmer) (hashtable.cc:177-178) is Storage::get_count: a saturated ByteStorage count is replaced by
+        // the bigcount map's value (storage.hh:640-647)
+        if (c == 255u && P.mask_n_big) {
+            uint32_t lo = 0, hi = P.mask_n_big;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (P.mask_big_keys[mid] < h) lo = mid + 1; else hi = mid;
+            }
+            if (lo < P.mask_n_big && P.mask_big_keys[lo] == h) c = P.mask_big_vals[lo];
+        }
         return P.mask_ge ? c >= P.mask_threshold : c <= P.mask_threshold;
     }
     return true;
@@ -1715,11 +1728,11 @@ __global__ void k_sel_slots(const Event* __restrict__ recs, uint64_t n_rec, Sket
     uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (r >= n_rec) return;
     Event e = recs[r];
-    uint32_t cross = e.info & 0x3ffu;
+    uint32_t cross = e.info & 0x3FFFFFFFu;
     for (int i = 0; i < S.n_tables; i++) {
         uint32_t sl = 0xFFFFFFFFu;
         if (cross >> i & 1u) sl = (uint32_t)ht_find(keys, mask, ht_key(mod_magic(e.hash, S.sizes[i], S.magic[i]), i));
-        rec_slot[r * F_MAXT + i] = sl;
+        rec_slot[r * S.n_tables + i] = sl;
     }
 }
 
@@ -1740,7 +1753,7 @@ __global__ void k_sel_count(const Event* __restrict__ recs, uint64_t n_rec, int 
     uint32_t pos = recs[r].pos;
     if ((pos >> bit) & 1u) return;
     for (int i = 0; i < n_tables; i++) {
-        uint32_t sl = rec_slot[r * F_MAXT + i];
+        uint32_t sl = rec_slot[r * n_tables + i];
         if (sl == 0xFFFFFFFFu) continue;
         // same bits above `bit` as the prefix decided so far
         if (bit == 31 || (pos >> (bit + 1)) == (st.prefix[sl] >> (bit + 1))) atomicAdd(&st.cnt[sl], 1u);
@@ -1779,7 +1792,7 @@ __global__ void k_ev_decide(const Event* __restrict__ recs, uint64_t n_rec, int 
     if (!(e.info >> 30 & 1u)) return;   // some byte of this k-mer is still below 255
     if (have_cross) {
         for (int i = 0; i < n_tables; i++) {
-            uint32_t sl = rec_slot[r * F_MAXT + i];
+            uint32_t sl = rec_slot[r * n_tables + i];
             if (sl != 0xFFFFFFFFu && !(e.pos > T[sl])) return;   // arrived before (or as) the saturating touch
         }
     }

@@ -66,7 +66,8 @@ def _same_state(g, o, n_tables):
 
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
 @pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps", "buckets",
-                                   "buckets-overflow", "buckets-whole"])
+                                   "buckets-overflow", "buckets-whole", "group", "group-whole", "group-regroup", "group-two",
+                                   "group-two-regroup", "group-turns", "group-t16k"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""
@@ -90,6 +91,21 @@ def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
                        KMGPU_BUCKETS="0")
         elif chunk == "delta-blocks":   # delta+fold path with many blocks per table
             env.update(KMGPU_DELTA_BLOCK_BINS="1000", KMGPU_DELTA_MAX_PASSES="100000", KMGPU_CHUNK_BASES="16384", KMGPU_BUCKETS="0")
+        elif isinstance(chunk, str) and chunk.startswith("group"):
+            # grouped path (fused hash + grouping, apply in shared memory) forced on these tiny tables
+            env.update(KMGPU_GROUP_MIN_BUCKETS="0", KMGPU_CHUNK_BASES="16384", KMGPU_PART_BASES="1000")
+            if chunk == "group-whole":      # every chunk uploaded in one piece
+                env.update(KMGPU_PARTS="0")
+            elif chunk == "group-regroup":  # regions far too small: every chunk is regrouped with exact offsets
+                env.update(KMGPU_BUCKET_CAP="64")
+            elif chunk == "group-two":      # two-level grouping (super-buckets first)
+                env.update(KMGPU_FORCE_TWO_LEVEL="1")
+            elif chunk == "group-two-regroup":
+                env.update(KMGPU_FORCE_TWO_LEVEL="1", KMGPU_SB_CAP="200", KMGPU_BUCKET_CAP="64")
+            elif chunk == "group-turns":    # record store too small for all tables at once: one table per turn
+                env.update(KMGPU_GROUP_MAX_RECORDS="20000")
+            elif chunk == "group-t16k":
+                env.update(KMGPU_PART_T="16384")
         else:
             env.update(KMGPU_CHUNK_BASES=str(chunk))
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
@@ -321,3 +337,26 @@ def test_bucket_path_many_buckets(cls):
         want = o.bigcounts()
         assert len(want) > 0 and dict(zip(gk.tolist(), gv.tolist())) == want
     g.close()
+
+
+@pytest.mark.parametrize("variant", ["dense", "sparse", "sparse-two", "dense-two", "regroup", "turns", "t16k"])
+def test_group_path_many_buckets(variant):
+    """test_bucket_path_many_buckets (six classes, ~70 buckets per table, state carried across calls, bigcount map) with the
+    grouped path forced on and steered into each of its forms."""
+    import subprocess, sys
+    env = dict(os.environ, KMGPU_GROUP_MIN_BUCKETS="0")
+    if variant == "sparse":        # ~230 records per bucket and chunk: k_apply_sparse
+        env.update(KMGPU_CHUNK_BASES="16384")
+    elif variant == "sparse-two":
+        env.update(KMGPU_CHUNK_BASES="16384", KMGPU_FORCE_TWO_LEVEL="1")
+    elif variant == "dense-two":
+        env.update(KMGPU_FORCE_TWO_LEVEL="1")
+    elif variant == "regroup":     # regions of 500 records against ~6.7 K expected: exact offsets, dense apply with clamping rounds
+        env.update(KMGPU_BUCKET_CAP="500")
+    elif variant == "turns":
+        env.update(KMGPU_GROUP_MAX_RECORDS="900000")
+    elif variant == "t16k":
+        env.update(KMGPU_PART_T="16384")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_bucket_path_many_buckets"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
