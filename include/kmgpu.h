@@ -156,6 +156,17 @@ int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, const char*
                                  const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                                  uint64_t* hist);
 
+/* Digital normalization, the loop of scripts/normalize-by-median.py:155-179 (Normalizer.__call__) with khmer/utils.py:178-180
+ * (ReadBundle.coverages_at_least) for a batch of reads in stream order: a bundle (one read, or a read and the next one when
+ * pair_with_next[r] != 0; pair_with_next may be NULL) is kept iff NOT every read of it has median_at_least(cutoff)
+ * (src/oxli/hashtable.cc:333-364) in the table as it is when the bundle arrives, and a kept bundle is consumed
+ * (Hashtable::consume_string) before the next bundle is looked at.  keep_out[r] = 1 for kept reads.  Reads without a k-mer never
+ * make their bundle kept (the script drops them before this loop).  Results equal the serial loop bit for bit: keep flags,
+ * tables, n_occupied, n_unique_kmers, bigcount map.  Cutoffs above 255 on a bigcount ByteStorage are not supported. */
+int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                          const uint8_t* pair_with_next, uint32_t cutoff, uint8_t* keep_out, uint64_t* n_kept_out,
+                          uint64_t* n_kmers_out);
+
 /* ---- state -----------------------------------------------------------------------------
  * Storage::n_occupied / n_unique_kmers / n_tables / get_tablesizes (storage.hh:65-74). */
 int kmgpu_stats(kmgpu_t* h, uint64_t* n_occupied, uint64_t* n_unique_kmers);

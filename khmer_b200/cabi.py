@@ -28,7 +28,7 @@ SYMBOLS = [
     "kmgpu_set_use_bigcount", "kmgpu_get_use_bigcount", "kmgpu_consume_reads", "kmgpu_consume_packed",
     "kmgpu_batch_create", "kmgpu_batch_destroy", "kmgpu_batch_info", "kmgpu_consume_batch", "kmgpu_add_hashes",
     "kmgpu_get_counts", "kmgpu_kmer_counts", "kmgpu_kmer_hashes", "kmgpu_read_medians", "kmgpu_median_at_least",
-    "kmgpu_abundance_distribution", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
+    "kmgpu_abundance_distribution", "kmgpu_normalize_batch", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
     "kmgpu_table_nbytes", "kmgpu_download_table", "kmgpu_upload_table", "kmgpu_bigcount_size",
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
@@ -88,6 +88,8 @@ def lib():
                                             C.c_void_p]
         L.kmgpu_abundance_distribution.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                    C.c_uint32, C.c_void_p]
+        L.kmgpu_normalize_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.c_void_p, u64p, u64p]
         L.kmgpu_stats.argtypes = [C.c_void_p, u64p, u64p]
         L.kmgpu_set_stats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.kmgpu_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -310,6 +312,22 @@ class Sketch:
         check(lib().kmgpu_abundance_distribution(self.h, tracking.h, _ptr(buf), _ptr(off), len(off) - 1,
                                                  CLEAN if clean else 0, _ptr(hist)))
         return hist
+
+    def normalize_batch(self, reads, cutoff, paired=None, clean=False):
+        """Digital normalization of a batch in stream order (scripts/normalize-by-median.py:155-179): returns the keep flags
+        (uint8 per read) and the number of k-mers consumed.  `paired`: optional uint8 per read, 1 = forms a pair with the next."""
+        buf, off = as_reads(reads)
+        nr = len(off) - 1
+        keep = np.zeros(max(nr, 1), dtype=np.uint8)
+        pw = None
+        if paired is not None:
+            pw = np.ascontiguousarray(paired, dtype=np.uint8)
+            assert len(pw) == nr
+        kept, kmers = C.c_uint64(), C.c_uint64()
+        check(lib().kmgpu_normalize_batch(self.h, _ptr(buf), _ptr(off), nr, CLEAN if clean else 0,
+                                          _ptr(pw) if pw is not None else None, int(cutoff), _ptr(keep), C.byref(kept),
+                                          C.byref(kmers)))
+        return keep[:nr], kmers.value
 
     # -- state
     def stats(self):

@@ -202,6 +202,11 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_cur1;
     DevBuf<unsigned long long> d_off1, d_off2;   // exact region offsets of a regrouping run
     DevBuf<uint64_t> d_hash64;              // Murmur: 64-bit hash of every position of the chunk
+    DevBuf<uint32_t> d_readbits;            // one bit per read of a window (normalization: candidates / kept)
+    DevBuf<uint32_t> d_upos, d_hitpos;      // normalization: positions of in-between reads; hits of their bins
+    DevBuf<uint64_t> d_ubins, d_hitkey;
+    DevBuf<uint16_t> d_uc0;
+    uint64_t n_norm_unsure = 0;
     uint64_t n_regroups = 0;
     bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
@@ -255,6 +260,7 @@ static Input make_input(const ChunkDev& c)
     in.n_reads = c.n_reads;
     in.hashes = nullptr;
     in.n_pos = c.n_pos;
+    in.read_keep = nullptr;
     return in;
 }
 static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
@@ -266,6 +272,7 @@ static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
     in.n_reads = 0;
     in.hashes = d_hashes;
     in.n_pos = n;
+    in.read_keep = nullptr;
     return in;
 }
 
@@ -483,7 +490,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -2175,6 +2182,264 @@ extern "C" int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, 
     CK(cudaMemcpyAsync(hh.data(), t->d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int i = 0; i < 65536; i++) hist[i] += hh[i];
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// digital normalization
+// ------------------------------------------------------------------------------------------------------
+// Hashtable::median_at_least's threshold (hashtable.cc:337): (unsigned)(0.5 + float(n) / 2)
+static inline unsigned median_min_req(uint32_t n) { return (unsigned)(0.5 + (double)((float)n / 2)); }
+
+extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                     const uint8_t* pair_with_next, uint32_t cutoff, uint8_t* keep_out, uint64_t* n_kept_out,
+                                     uint64_t* n_kmers_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kept_out) *n_kept_out = 0;
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets || !keep_out) return fail(KMGPU_EINVAL, "null argument");
+    if (h->kind == BYTE && h->use_bigcount && cutoff > 255)
+        return fail(KMGPU_EUNSUPPORTED, "normalize_batch: cutoffs above 255 on a bigcount table are not supported");
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] - offsets[r] > chunk_bases() / 4)
+            return fail(KMGPU_EUNSUPPORTED, "read %llu is too long for a normalization window", (unsigned long long)r);
+    if (pair_with_next && pair_with_next[n_reads - 1]) return fail(KMGPU_EINVAL, "the last read cannot be paired with a next one");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    const HashCfg H{h->hash, h->k};
+    const int N = h->nt;
+    const uint32_t cap_c = h->kind == BYTE ? 255u : h->kind == NIBBLE ? 15u : 1u;
+    const uint64_t W = std::max<uint64_t>(2, env_u64("KMGPU_NORM_WINDOW", 65536));
+    const uint64_t max_bases = chunk_bases() / 2;
+    Pred P0;
+    memset(&P0, 0, sizeof P0);
+    uint64_t kept_total = 0, kmers_total = 0;
+    std::vector<uint8_t> al1, al2;
+    std::vector<uint32_t> bits;
+    auto upload_bits = [&](const std::vector<uint8_t>& flag, uint32_t nr) -> int {   // one bit per read -> d_readbits
+        bits.assign((nr + 31) / 32, 0u);
+        for (uint32_t r = 0; r < nr; r++)
+            if (flag[r]) bits[r >> 5] |= 1u << (r & 31);
+        CKR(h->d_readbits.ensure(bits.size()));
+        CK(cudaMemcpyAsync(h->d_readbits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // `bits` is reused
+        return KMGPU_OK;
+    };
+    for (uint64_t r0 = 0; r0 < n_reads;) {
+        // window of whole bundles, at most W reads and max_bases bases
+        uint64_t r1 = r0;
+        while (r1 < n_reads && r1 - r0 < W && offsets[r1 + 1] - offsets[r0] <= max_bases) r1++;
+        if (r1 == r0) r1 = r0 + 1;
+        while (r1 < n_reads && pair_with_next && pair_with_next[r1 - 1]) r1++;   // do not cut a pair
+        const uint32_t nr = (uint32_t)(r1 - r0);
+        ChunkPlan c;
+        c.base0 = offsets[r0];
+        c.base1 = offsets[r1];
+        c.offs.resize(nr + 1);
+        for (uint32_t r = 0; r <= nr; r++) c.offs[r] = (uint32_t)(offsets[r0 + r] - offsets[r0]);
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
+        auto bundle_end = [&](uint32_t r) { uint32_t e = r + 1; while (e < nr && pair_with_next && pair_with_next[r0 + e - 1]) e++; return e; };
+        std::vector<uint8_t> keep(nr, 0);
+        if (cd.n_pos) {
+            Input in = make_input(cd);
+            // 1. median_at_least of every read in the table as it is at the window's start
+            if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+            const uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+            CKR(h->d_counts.ensure(cd.n_pos));
+            CKR(h->d_stat_n.ensure(nr));
+            CKR(h->d_stat_b.ensure(nr));
+            launch_counts(0, h->dev, H, in, h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr, st);
+            k_read_stats<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, nullptr, nullptr, nullptr, h->d_stat_n.p, cutoff, h->d_stat_b.p);
+            h->all_launches += 2;
+            CK(cudaGetLastError());
+            al1.resize(nr);
+            CK(cudaMemcpyAsync(al1.data(), h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            // candidates: bundles with a read below the cutoff (a read without k-mers never makes its bundle a candidate)
+            std::vector<uint8_t> cand(nr, 0);
+            uint64_t cand_bases = 0, n_cand = 0;
+            for (uint32_t r = 0; r < nr;) {
+                const uint32_t e = bundle_end(r);
+                bool below = false;
+                for (uint32_t q = r; q < e; q++) below |= al1[q] == 0;
+                if (below)
+                    for (uint32_t q = r; q < e; q++) {
+                        cand[q] = 1;
+                        cand_bases += c.offs[q + 1] - c.offs[q];
+                        n_cand++;
+                    }
+                r = e;
+            }
+            if (n_cand) {
+                // 2. the same test with every candidate of the window added on top (overlay): still below => kept for good
+                CKR(upload_bits(cand, nr));
+                const uint64_t slots = pow2_at_least(2 * cand_bases * (uint64_t)N);
+                CKR(h->d_htkeys.ensure(slots));
+                CKR(h->d_htvals.ensure(slots));
+                CK(cudaMemsetAsync(h->d_htkeys.p, 0xFF, slots * 8, st));
+                CK(cudaMemsetAsync(h->d_htvals.p, 0, slots * 4, st));
+                in.read_keep = h->d_readbits.p;
+                const unsigned gt = n_tiles(cd.n_pos);
+                if (H.kind == TWOBIT) k_norm_overlay_add<TWOBIT, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, h->d_htkeys.p, h->d_htvals.p, slots - 1);
+                else k_norm_overlay_add<MURMUR, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, h->d_htkeys.p, h->d_htvals.p, slots - 1);
+#define NORM_COUNTS(KIND)                                                                                                                  \
+    do {                                                                                                                                   \
+        if (H.kind == TWOBIT) k_norm_counts_overlay<KIND, TWOBIT, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, h->d_htkeys.p, h->d_htvals.p, slots - 1, h->d_counts.p); \
+        else k_norm_counts_overlay<KIND, MURMUR, 0><<<gt, THREADS, 0, st>>>(h->dev, H, in, h->d_htkeys.p, h->d_htvals.p, slots - 1, h->d_counts.p);                 \
+    } while (0)
+                if (h->kind == BYTE) NORM_COUNTS(BYTE);
+                else if (h->kind == NIBBLE) NORM_COUNTS(NIBBLE);
+                else NORM_COUNTS(BIT);
+#undef NORM_COUNTS
+                k_read_stats<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, nullptr, nullptr, nullptr, h->d_stat_n.p, cutoff, h->d_stat_b.p);
+                h->all_launches += 3;
+                CK(cudaGetLastError());
+                al2.resize(nr);
+                CK(cudaMemcpyAsync(al2.data(), h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                std::vector<uint8_t> sure(nr, 0), unsure(nr, 0);
+                uint64_t n_unsure = 0, up_total = 0;
+                for (uint32_t r = 0; r < nr;) {
+                    const uint32_t e = bundle_end(r);
+                    if (cand[r]) {
+                        bool below = false;
+                        for (uint32_t q = r; q < e; q++) below |= al2[q] == 0;
+                        for (uint32_t q = r; q < e; q++) {
+                            (below ? sure : unsure)[q] = 1;
+                            if (!below) {
+                                n_unsure++;
+                                const uint32_t len = c.offs[q + 1] - c.offs[q];
+                                if (len >= (uint32_t)h->k) up_total += len - h->k + 1;
+                            }
+                        }
+                    }
+                    r = e;
+                }
+                keep = sure;
+                if (n_unsure) {
+                    // 3. in-between bundles, in stream order: the state each of them meets is the window's start + the reads kept
+                    //    for good before it + the in-between bundles kept before it
+                    h->n_norm_unsure += n_unsure;
+                    std::vector<uint32_t> upos;
+                    upos.reserve(up_total);
+                    for (uint32_t r = 0; r < nr; r++) {
+                        if (!unsure[r]) continue;
+                        const uint32_t s = c.offs[r], len = c.offs[r + 1] - s;
+                        if (len < (uint32_t)h->k) continue;
+                        for (uint32_t i = 0; i + h->k <= len; i++) upos.push_back(s + i);
+                    }
+                    const uint32_t n_up = (uint32_t)upos.size();
+                    std::vector<uint64_t> ubins((size_t)n_up * N);
+                    std::vector<uint16_t> uc0((size_t)n_up * N);
+                    std::unordered_map<uint64_t, std::vector<uint32_t>> hits;
+                    if (n_up) {
+                        CKR(h->d_upos.ensure(n_up));
+                        CKR(h->d_ubins.ensure((size_t)n_up * N));
+                        CKR(h->d_uc0.ensure((size_t)n_up * N));
+                        const uint64_t slots2 = pow2_at_least(2 * (uint64_t)n_up * N);
+                        CKR(h->d_evkeys.ensure(slots2));
+                        CK(cudaMemcpyAsync(h->d_upos.p, upos.data(), (size_t)n_up * 4, cudaMemcpyHostToDevice, st));
+                        CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, slots2 * 8, st));
+                        uint64_t* keys2 = reinterpret_cast<uint64_t*>(h->d_evkeys.p);
+                        Input in0 = make_input(cd);
+#define NORM_GATHER(KIND)                                                                                                                                    \
+    do {                                                                                                                                                     \
+        if (H.kind == TWOBIT) k_norm_gather<KIND, TWOBIT><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_ubins.p, h->d_uc0.p, keys2, slots2 - 1); \
+        else k_norm_gather<KIND, MURMUR><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_ubins.p, h->d_uc0.p, keys2, slots2 - 1);               \
+    } while (0)
+                        if (h->kind == BYTE) NORM_GATHER(BYTE);
+                        else if (h->kind == NIBBLE) NORM_GATHER(NIBBLE);
+                        else NORM_GATHER(BIT);
+#undef NORM_GATHER
+                        h->all_launches += 1;
+                        CKR(upload_bits(sure, nr));   // synchronises: upos may go
+                        Input ink = make_input(cd);
+                        ink.read_keep = h->d_readbits.p;
+                        uint64_t hit_cap = std::max<uint64_t>(1u << 20, h->d_hitkey.cap);
+                        while (true) {
+                            CKR(h->d_hitkey.ensure(hit_cap));
+                            CKR(h->d_hitpos.ensure(hit_cap));
+                            CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+                            if (H.kind == TWOBIT) k_norm_hits<TWOBIT, 0><<<gt, THREADS, 0, st>>>(h->dev, H, ink, keys2, slots2 - 1, h->d_hitkey.p, h->d_hitpos.p, hit_cap, h->d_ctrl);
+                            else k_norm_hits<MURMUR, 0><<<gt, THREADS, 0, st>>>(h->dev, H, ink, keys2, slots2 - 1, h->d_hitkey.p, h->d_hitpos.p, hit_cap, h->d_ctrl);
+                            h->all_launches += 1;
+                            CK(cudaGetLastError());
+                            CKR(read_ctrl(h));
+                            if (h->h_ctrl->n_events <= hit_cap) break;
+                            hit_cap = h->h_ctrl->n_events;
+                        }
+                        const uint64_t n_hits = h->h_ctrl->n_events;
+                        std::vector<uint64_t> hk(n_hits);
+                        std::vector<uint32_t> hp(n_hits);
+                        CK(cudaMemcpyAsync(ubins.data(), h->d_ubins.p, ubins.size() * 8, cudaMemcpyDeviceToHost, st));
+                        CK(cudaMemcpyAsync(uc0.data(), h->d_uc0.p, uc0.size() * 2, cudaMemcpyDeviceToHost, st));
+                        if (n_hits) {
+                            CK(cudaMemcpyAsync(hk.data(), h->d_hitkey.p, n_hits * 8, cudaMemcpyDeviceToHost, st));
+                            CK(cudaMemcpyAsync(hp.data(), h->d_hitpos.p, n_hits * 4, cudaMemcpyDeviceToHost, st));
+                        }
+                        CK(cudaStreamSynchronize(st));
+                        for (uint64_t i = 0; i < n_hits; i++) hits[hk[i]].push_back(hp[i]);
+                        for (auto& kv : hits) std::sort(kv.second.begin(), kv.second.end());
+                    }
+                    std::unordered_map<uint64_t, uint32_t> extra;   // touches by the in-between bundles kept so far
+                    size_t up_at = 0;
+                    for (uint32_t r = 0; r < nr;) {
+                        const uint32_t e = bundle_end(r);
+                        if (!unsure[r]) { r = e; continue; }
+                        const uint32_t bundle_start = c.offs[r];
+                        const size_t up_begin = up_at;
+                        bool below = false;
+                        for (uint32_t q = r; q < e; q++) {
+                            const uint32_t len = c.offs[q + 1] - c.offs[q];
+                            if (len < (uint32_t)h->k) continue;
+                            const uint32_t nk = len - h->k + 1;
+                            unsigned n_ge = 0;
+                            for (uint32_t i = 0; i < nk; i++, up_at++) {
+                                uint32_t mn = cap_c;
+                                for (int t = 0; t < N; t++) {
+                                    const uint64_t key = (ubins[up_at * N + t] << 8) | (uint64_t)t;
+                                    uint64_t v = uc0[up_at * N + t];
+                                    auto hi = hits.find(key);
+                                    if (hi != hits.end()) v += (uint64_t)(std::lower_bound(hi->second.begin(), hi->second.end(), bundle_start) - hi->second.begin());
+                                    auto ei = extra.find(key);
+                                    if (ei != extra.end()) v += ei->second;
+                                    if (v < mn) mn = (uint32_t)v;
+                                }
+                                n_ge += mn >= cutoff;
+                            }
+                            if (n_ge < median_min_req(nk)) below = true;
+                        }
+                        if (below) {
+                            for (uint32_t q = r; q < e; q++) keep[q] = 1;
+                            for (size_t u = up_begin; u < up_at; u++)
+                                for (int t = 0; t < N; t++) extra[(ubins[u * N + t] << 8) | (uint64_t)t] += 1;
+                        }
+                        r = e;
+                    }
+                }
+                // 4. the kept reads are consumed in stream order (one ordinary ingest with a read mask)
+                uint64_t nk_reads = 0;
+                for (uint32_t r = 0; r < nr; r++) nk_reads += keep[r];
+                if (nk_reads) {
+                    CKR(upload_bits(keep, nr));
+                    Input ink = make_input(cd);
+                    ink.read_keep = h->d_readbits.p;
+                    ChunkResult res;
+                    CKR(ingest_chunk(h, 0, H, ink, P0, false, nullptr, &res));
+                    kmers_total += res.n_kmers;
+                    kept_total += nk_reads;
+                }
+            }
+        }
+        memcpy(keep_out + r0, keep.data(), nr);
+        r0 = r1;
+    }
+    if (n_kept_out) *n_kept_out = kept_total;
+    if (n_kmers_out) *n_kmers_out = kmers_total;
     return KMGPU_OK;
 }
 

@@ -164,6 +164,7 @@ __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t
     for (uint32_t r = r_lo + tid; r < r_hi; r += NTHR) {
         uint32_t s = in.offs[r], e = in.offs[r + 1];
         if (e - s < (uint32_t)k) continue;
+        if (in.read_keep && !((in.read_keep[r >> 5] >> (r & 31)) & 1u)) continue;
         uint32_t first = s > t0 ? s : t0;
         uint32_t last = e - k;  // inclusive
         if (last >= t0 + T) last = t0 + T - 1;
@@ -771,6 +772,110 @@ k_bigscan2(const __grid_constant__ SketchDev S, HashCfg H, Input in, const __gri
         e.info = cross | ((uint32_t)allsat << 30);
         unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
         if (at < cap) out[at] = e;
+    }
+}
+
+}  // namespace kmgpu
+
+namespace kmgpu {
+
+// =====================================================================================================================
+// 5. Digital normalization (scripts/normalize-by-median.py:155-179, khmer/utils.py:178-180, Hashtable::median_at_least
+//    src/oxli/hashtable.cc:333-364).  The reference keeps a read bundle iff one of its reads has a median count below
+//    the cutoff in the table AS IT IS when the bundle arrives, and consumes it at once — a serial dependency.  Counts
+//    only grow, so for a window of reads: a bundle at or above the cutoff at the window's start is discarded for good;
+//    a candidate still below the cutoff after EVERY candidate of the window has been added (the overlay below) is kept
+//    for good; the few in between are resolved in stream order on the host from exact per-bin data gathered here.
+// =====================================================================================================================
+
+// overlay: (table, bin) -> touches by the window's candidate reads (open addressing, keys as ht_key)
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_norm_overlay_add(const __grid_constant__ SketchDev S, HashCfg H, Input in, uint64_t* keys, uint32_t* vals, uint64_t mask)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        for (int i = 0; i < S.n_tables; i++) {
+            const uint64_t s = ht_insert(keys, mask, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+            atomicAdd(&vals[s], 1u);
+        }
+    }
+}
+
+// counts of the candidates' k-mers as if every candidate of the window had been consumed: min over tables of
+// min(cap, counter + overlay) (Storage::get_count; a saturated ByteStorage count compares >= any cutoff <= 255)
+template <int KIND, int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_norm_counts_overlay(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                      uint64_t mask, uint16_t* __restrict__ counts)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        uint32_t mn = counter_cap<KIND>();
+        for (int i = 0; i < S.n_tables; i++) {
+            const uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+            uint32_t c = read_counter<KIND>(S.tables[i], bin);
+            const uint64_t s = ht_find(keys, mask, ht_key(bin, i));
+            if (s != ~0ull) c += vals[s];
+            mn = c < mn ? c : mn;
+        }
+        counts[t0 + lp] = (uint16_t)mn;
+    }
+}
+
+// per position of an in-between read (upos[j] = chunk position): its bin and the counter there in every table, and
+// the (table, bin) registered in the set the next kernel probes
+template <int KIND, int HK>
+__global__ void __launch_bounds__(256)
+k_norm_gather(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ upos, uint32_t n_up, uint64_t* __restrict__ out_bins,
+              uint16_t* __restrict__ out_c0, uint64_t* keys2, uint64_t mask2)
+{
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= n_up) return;
+    const uint64_t h = hash_at<HK, 0>(in, H.k, upos[j]);
+    for (int i = 0; i < S.n_tables; i++) {
+        const uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
+        out_bins[(size_t)j * S.n_tables + i] = bin;
+        out_c0[(size_t)j * S.n_tables + i] = (uint16_t)read_counter<KIND>(S.tables[i], bin);
+        ht_insert(keys2, mask2, ht_key(bin, i));
+    }
+}
+
+// touches of registered (table, bin) pairs by the reads kept for good: (key, position) pairs for the host
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_norm_hits(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ keys2, uint64_t mask2, uint64_t* __restrict__ hit_key,
+            uint32_t* __restrict__ hit_pos, unsigned long long cap, Ctrl* ctrl)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        for (int i = 0; i < S.n_tables; i++) {
+            const uint64_t key = ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i);
+            if (ht_find(keys2, mask2, key) == ~0ull) continue;
+            const unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
+            if (at < cap) {
+                hit_key[at] = key;
+                hit_pos[at] = t0 + lp;
+            }
+        }
     }
 }
 

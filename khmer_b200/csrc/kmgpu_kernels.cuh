@@ -38,6 +38,7 @@ struct Input {
     uint32_t n_reads;
     const uint64_t* hashes;  // SRC 1: hash array
     uint32_t n_pos;          // stream positions (bases) or number of hashes
+    const uint32_t* read_keep;  // optional: one bit per read of the chunk; reads whose bit is clear yield no k-mers
 };
 
 struct TileSmem {
@@ -80,6 +81,7 @@ __device__ __forceinline__ void tile_begin(const Input& in, int k, uint32_t t0, 
     for (uint32_t r = r_lo + tid; r < r_hi; r += THREADS) {
         uint32_t s = in.offs[r], e = in.offs[r + 1];
         if (e - s < (uint32_t)k) continue;
+        if (in.read_keep && !((in.read_keep[r >> 5] >> (r & 31)) & 1u)) continue;
         uint32_t first = s > t0 ? s : t0;
         uint32_t last = e - k;  // inclusive
         if (last >= t0 + TILE) last = t0 + TILE - 1;

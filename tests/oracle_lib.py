@@ -78,6 +78,8 @@ def oracle_lib():
                                 C.POINTER(C.c_float)]
         L.ko_median_at_least.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint]
         L.ko_abundance_distribution.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, u64p, C.c_uint64, C.c_int, u64p]
+        L.ko_normalize_reads.restype = C.c_int64
+        L.ko_normalize_reads.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_uint64, C.c_void_p, C.c_uint, C.c_void_p]
         L.ko_update_from.argtypes = [C.c_void_p, C.c_void_p]
         L.ko_save.argtypes = [C.c_void_p, C.c_char_p]
         L.ko_hash_twobit.argtypes = [C.c_char_p, C.c_int, u64p, u64p, u64p]
@@ -224,6 +226,21 @@ class Oracle:
         self.L.ko_abundance_distribution(self.h, tracking.h, seqs, off.ctypes.data_as(u64p), len(off) - 1,
                                          int(clean), dist.ctypes.data_as(u64p))
         return dist
+
+    def normalize_reads(self, reads, cutoff, paired=None):
+        """serial digital normalization (scripts/normalize-by-median.py:155-179): (keep flags, k-mers consumed)"""
+        if isinstance(reads, tuple):
+            buf, off = reads
+            seqs = buf.tobytes() if hasattr(buf, "tobytes") else bytes(buf)
+            off = np.ascontiguousarray(off, dtype=np.uint64)
+        else:
+            seqs, off = pack_reads(reads)
+        n = len(off) - 1
+        keep = np.zeros(max(n, 1), dtype=np.uint8)
+        pw = np.ascontiguousarray(paired, dtype=np.uint8) if paired is not None else None
+        kmers = self.L.ko_normalize_reads(self.h, seqs, off.ctypes.data_as(u64p), n,
+                                          pw.ctypes.data if pw is not None else None, int(cutoff), keep.ctypes.data)
+        return keep[:n], kmers
 
     def update(self, other):
         if self.L.ko_update_from(self.h, other.h):

@@ -224,3 +224,23 @@ def test_oracle_vs_live_reference_random(tmp_path):
         assert ref.n_unique_kmers() == o.n_unique_kmers() and ref.n_occupied() == o.n_occupied()
         for i in range(len(sizes)):
             assert np.array_equal(ref.table(i), o.table(i))
+
+
+def test_diginorm_reproduces_reference_script_md5s(datadir):
+    """tests/test_script_output.py:51-70: normalize-by-median.py -k 21 -M 1e7 on simple-genome-reads.fa writes files with these
+    md5s at -C 20 / -C 15.  The serial loop of the oracle (ko_normalize_reads) driven the way the script drives the table
+    (Countgraph(21, 1e7 / 4, 4); cleaned_seq = upper, N -> A; kept records written as >name\\nsequence\\n) reproduces both."""
+    import hashlib
+    recs, name = [], None
+    for ln in open(os.path.join(datadir, "simple-genome-reads.fa")):
+        ln = ln.rstrip("\n")
+        if ln.startswith(">"):
+            name = ln[1:]
+        else:
+            recs.append((name, ln))
+    cleaned = [s.upper().replace("N", "A") for _, s in recs]
+    for cutoff, want in ((20, "942e9024c25a8d85033d755d86aba4a3"), (15, "0d1b4b9d4c76cb8cdeee5a98f6e70163")):
+        o = ol.Oracle("Countgraph", 21, ol.primes_near_x(4, int(1e7 / 4)))
+        keep, _ = o.normalize_reads(cleaned, cutoff)
+        out = "".join(">%s\n%s\n" % (n, s) for (n, s), k in zip(recs, keep) if k)
+        assert hashlib.md5(out.encode()).hexdigest() == want

@@ -13,6 +13,9 @@ KMGPU_TEST_CLS=Countgraph KMGPU_GROUP_MIN_BUCKETS=0 KMGPU_CHUNK_BASES=16384 KMGP
 echo "== grouped-path tests" | tee -a $OUT/progress.txt
 timeout 1500 python -m pytest -q -x -m gpu tests/test_gpu_parity.py -k "group or golden_C1 or many_buckets or (golden and 25k)" > $OUT/tests_group.log 2>&1; echo "group tests rc=$?" | tee -a $OUT/progress.txt
 tail -5 $OUT/tests_group.log | tee -a $OUT/progress.txt
+echo "== normalize tests" | tee -a $OUT/progress.txt
+timeout 1200 python -m pytest -q -x -s -m gpu tests/test_gpu_normalize.py > $OUT/tests_norm.log 2>&1; echo "normalize tests rc=$?" | tee -a $OUT/progress.txt
+tail -5 $OUT/tests_norm.log | tee -a $OUT/progress.txt
 echo "== bench default" | tee -a $OUT/progress.txt
 timeout 900 python bench.py > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench rc=$?" | tee -a $OUT/progress.txt
 cat $OUT/bench_default.json | cut -c1-600 | tee -a $OUT/progress.txt
