@@ -212,31 +212,36 @@ int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
 int kmgpu_slice_range(uint64_t n_words, int world, int rank, uint64_t* w0, uint64_t* w1);
 
 /* ---- multi-GPU, address-sharded sketches ---------------------------------
- * For tables too large to replicate: bins [r*S_i, (r+1)*S_i) of table i live on rank r (S_i = slice length).
- * Every rank hashes its own reads, then routes each counter update to the owner of its bin by writing the
- * (slice-relative) bin straight into a receive queue in the owner's HBM over NVLink peer memory — the k-mer
- * all-to-all — and every owner applies what it received to its slices with the same delta + fold kernels as
- * the single-GPU path.  Collective protocol per batch of reads (the caller provides the barriers):
- *     kmgpu_shard_route (all ranks)  ->  barrier  ->  kmgpu_shard_apply (all ranks)  ->  barrier
- * Table bytes and n_occupied are exact (the sum of the ranks' slices / counters equals the single sketch);
- * n_unique_kmers and bigcount need an order across ranks and are not maintained in this mode.
- * The saved table is the concatenation of the ranks' slices in rank order (kmgpu_shard_slice + the local
- * sketch's kmgpu_download_table). */
+ * For tables too large to replicate: bins [r*S_i, (r+1)*S_i) of table i live on rank r (S_i = slice length).  Every rank
+ * hashes its own reads and writes each counter update — grouped by the owner's super-bucket (2^27 bins), 64-bit bins —
+ * straight into the owner's record store in HBM over NVLink peer memory: the k-mer all-to-all, fused into the hashing pass.
+ * Every owner then groups what it received by 32 Ki-bin bucket and applies it in shared memory like a local chunk.
+ * Positions are global across the ranks of a round (rank * max_positions + position in the rank's reads, i.e. the stream
+ * order is rank 0's reads, then rank 1's, ...), so the first toucher of a bin is decided across ranks and n_unique_kmers is
+ * exact: it equals one sketch fed the rounds in that order.  Collective protocol per round (the caller provides the barriers):
+ *     kmgpu_shard_route  ->  barrier  ->  kmgpu_shard_apply  ->  barrier  ->  kmgpu_shard_count_new  ->  barrier
+ * Table bytes and n_occupied are exact (concatenated slices / summed counters equal the single sketch); n_unique_kmers is the
+ * sum of the ranks' shares (kmgpu_shard_stats); bigcount is not maintained in this mode.  The saved table is the
+ * concatenation of the ranks' slices in rank order (kmgpu_shard_slice + the local sketch's kmgpu_download_table). */
 typedef struct kmgpu_shard kmgpu_shard_t;
+#define KMGPU_SHARD_IPC_HANDLES 4 /* record store, cursors, overflow word, new-position bitmap */
+#define KMGPU_MAX_WORLD 16
 int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables, const uint64_t* full_sizes, int device,
                        int rank, int world, uint64_t max_positions_per_route, kmgpu_shard_t** out);
 int kmgpu_shard_destroy(kmgpu_shard_t* s);
-/* the local sketch holding this rank's slices (stats, downloads, merges work on it as on any sketch) */
+/* the local sketch holding this rank's slices (downloads, queries by local bin work on it as on any sketch) */
 kmgpu_t* kmgpu_shard_local(kmgpu_shard_t* s);
 int kmgpu_shard_slice(kmgpu_shard_t* s, int table, uint64_t* lo, uint64_t* hi);
-/* peers: CUDA-IPC handles of the receive queues ((n_tables + 1) * 64 bytes per rank), or direct pointers when
- * all ranks live in one process */
+/* n_occupied of this rank's slices, this rank's share of n_unique_kmers, bytes of its receive store */
+int kmgpu_shard_stats(kmgpu_shard_t* s, uint64_t* n_occupied_local, uint64_t* n_unique_share, uint64_t* store_bytes);
+/* peers: CUDA-IPC handles (KMGPU_SHARD_IPC_HANDLES * 64 bytes per rank), or direct pointers when all ranks live in one process */
 int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles);
 int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all_handles);
 int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n);
 int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                       uint64_t* n_kmers_out);
 int kmgpu_shard_apply(kmgpu_shard_t* s);
+int kmgpu_shard_count_new(kmgpu_shard_t* s, uint64_t* n_new_out);
 
 /* ---- measurement -----------------------------------------------------------------------
  * Device time (ms) and launch count of the ingest kernel accumulated since the last reset, measured

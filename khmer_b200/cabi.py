@@ -36,6 +36,7 @@ SYMBOLS = [
     "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
     "kmgpu_shard_create", "kmgpu_shard_destroy", "kmgpu_shard_local", "kmgpu_shard_slice", "kmgpu_shard_ipc_export",
     "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_apply",
+    "kmgpu_shard_count_new", "kmgpu_shard_stats",
 ]
 
 
@@ -128,6 +129,8 @@ def lib():
         L.kmgpu_shard_attach_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.kmgpu_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]
         L.kmgpu_shard_apply.argtypes = [C.c_void_p]
+        L.kmgpu_shard_count_new.argtypes = [C.c_void_p, u64p]
+        L.kmgpu_shard_stats.argtypes = [C.c_void_p, u64p, u64p, u64p]
         _lib = L
     return _lib
 
@@ -421,6 +424,9 @@ class Sketch:
         return ms.value
 
 
+SHARD_IPC_HANDLES = 4
+
+
 class Shard:
     """One rank's part of an address-sharded sketch (kmgpu_shard_*)."""
 
@@ -456,7 +462,7 @@ class Shard:
         return lo.value, hi.value
 
     def ipc_export(self):
-        out = np.zeros(64 * (len(self.full_sizes) + 1), dtype=np.uint8)
+        out = np.zeros(64 * SHARD_IPC_HANDLES, dtype=np.uint8)
         check(lib().kmgpu_shard_ipc_export(self.h, _ptr(out)))
         return out
 
@@ -472,6 +478,18 @@ class Shard:
 
     def apply(self):
         check(lib().kmgpu_shard_apply(self.h))
+
+    def count_new(self):
+        """after every rank has applied the round: how many k-mers of THIS rank's reads were new"""
+        n = C.c_uint64()
+        check(lib().kmgpu_shard_count_new(self.h, C.byref(n)))
+        return n.value
+
+    def stats(self):
+        """(n_occupied of this rank's slices, this rank's share of n_unique_kmers, bytes of the receive store)"""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().kmgpu_shard_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def slice_bytes(self, table):
         """This rank's part of the table image: concatenating the parts of all ranks in rank order gives the

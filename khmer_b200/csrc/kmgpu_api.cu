@@ -2692,21 +2692,35 @@ extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
 
 // ------------------------------------------------------------------------------------------------------
 // multi-GPU: address-sharded sketches (k-mer all-to-all over NVLink peer memory, see include/kmgpu.h)
+//
+// Rank r holds bins [r * slice_i, (r + 1) * slice_i) of table i as an ordinary local sketch.  A round: every rank hashes
+// its own reads and k_part MODE 3 writes each counter update, already grouped by the owner's super-bucket, straight into
+// the owner's record store over peer memory (route); after a barrier every owner groups what it received by bucket and
+// applies it in shared memory like any chunk (apply: k_part MODE 2 + k_apply2 / k_apply_sparse); positions are global
+// (rank * max_positions + position), so "first toucher of a bin" is decided across ranks, and after another barrier every
+// rank counts the positions of ITS reads that some owner marked new (count_new) — n_unique_kmers is exact.
 // ------------------------------------------------------------------------------------------------------
 struct kmgpu_shard {
     kmgpu_sketch* local = nullptr;
     int rank = 0, world = 1, nt = 0;
     uint64_t full_sizes[MAX_TABLES];
     uint64_t slice[MAX_TABLES];
-    SketchDev full;  // full-table sizes and magics: what the k-mers are hashed against
-    uint32_t* rq[MAX_TABLES];
-    unsigned long long* rcur = nullptr;
-    uint64_t qcap = 0, max_positions = 0;
+    SketchDev full;   // full-table sizes and magics: what the k-mers are hashed against
+    GroupPlan G;      // layout of one rank's slices (the same on every rank) and region sizes for max_positions per rank and round
+    uint64_t max_positions = 0;
+    unsigned long long* rec1 = nullptr;    // received records, by super-bucket
+    uint32_t* cur1 = nullptr;
+    unsigned long long* flags = nullptr;   // bit 0: a region of this rank was cut short by a sender
+    uint32_t* newbits = nullptr;           // one bit per global position of a round: marked new by this owner
     struct PeerQ {
-        uint32_t* rq[MAX_TABLES];
-        unsigned long long* rcur;
-    } peers[8];
+        unsigned long long* rec1;
+        uint32_t* cur1;
+        unsigned long long* flags;
+        uint32_t* newbits;
+    } peers[MAX_WORLD];
     bool attached = false, ipc = false;
+    uint64_t n_unique = 0;   // k-mers of this rank's reads that were new
+    uint64_t routed_overflow = 0;
 };
 
 extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s);
@@ -2716,28 +2730,31 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
 {
     if (!out) return fail(KMGPU_EINVAL, "out is NULL");
     *out = nullptr;
-    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
-    if (n_tables < 1 || n_tables > F_MAXT) return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported", n_tables);
-    if (max_positions == 0 || max_positions > chunk_bases()) max_positions = std::min<uint64_t>(chunk_bases(), 8ull << 20);
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d (at most %d ranks)", rank, world, MAX_WORLD);
+    if (n_tables < 1 || n_tables > MAX_TABLES) return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported", n_tables);
+    if (max_positions == 0) max_positions = 8ull << 20;
+    max_positions = ((max_positions + 31) / 32) * 32;
+    if (max_positions > chunk_bases() || (uint64_t)world * max_positions >= (1ull << 32))
+        return fail(KMGPU_EINVAL, "max_positions %llu too large (positions of a round are 32-bit across all ranks)", (unsigned long long)max_positions);
     kmgpu_shard* s = new kmgpu_shard();
     s->rank = rank;
     s->world = world;
     s->nt = n_tables;
     s->max_positions = max_positions;
     memset(&s->full, 0, sizeof s->full);
-    memset(s->rq, 0, sizeof s->rq);
     memset(s->peers, 0, sizeof s->peers);
-    uint64_t local_sizes[MAX_TABLES];
+    uint64_t local_sizes[MAX_TABLES], nominal[MAX_TABLES];
     for (int i = 0; i < n_tables; i++) {
-        if (full_sizes[i] == 0 || full_sizes[i] > 0xFFFFFFFEull - 128) {
+        if (full_sizes[i] == 0 || full_sizes[i] >= (1ull << 55)) {
             delete s;
-            return fail(KMGPU_EUNSUPPORTED, "sharded tables are limited to 2^32 bins per table for now");
+            return fail(KMGPU_EINVAL, "table size %llu out of range", (unsigned long long)full_sizes[i]);
         }
         s->full_sizes[i] = full_sizes[i];
         uint64_t per = (full_sizes[i] + world - 1) / world;
         s->slice[i] = ((per + 127) / 128) * 128;  // slices start on a byte of every storage kind
         uint64_t lo = std::min<uint64_t>(full_sizes[i], s->slice[i] * rank), hi = std::min<uint64_t>(full_sizes[i], s->slice[i] * (rank + 1));
         local_sizes[i] = std::max<uint64_t>(hi - lo, 1);  // a rank past the end of a tiny table keeps a dummy bin
+        nominal[i] = s->slice[i];
         s->full.sizes[i] = full_sizes[i];
         s->full.magic[i] = ~0ull / full_sizes[i];
     }
@@ -2748,14 +2765,37 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
         delete s;
         return rc;
     }
-    s->qcap = (uint64_t)world * max_positions;
-    cudaError_t e = cudaSuccess;
-    for (int i = 0; i < n_tables && e == cudaSuccess; i++) e = cudaMalloc(&s->rq[i], s->qcap * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&s->rcur, MAX_TABLES * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(s->rcur, 0, MAX_TABLES * sizeof(unsigned long long));
+    {
+        // one layout for every rank: buckets and super-buckets of the NOMINAL slice; regions sized for what all ranks together
+        // send an owner in a round when each hashes max_positions positions (= max_positions per owner on average)
+        kmgpu_sketch nominal_shape;
+        nominal_shape.nt = n_tables;
+        nominal_shape.kind = storage;
+        for (int i = 0; i < n_tables; i++) nominal_shape.sizes[i] = nominal[i];
+        const bool ok = plan_group(&nominal_shape, (uint32_t)max_positions, true, &s->G, true);
+        if (!ok || !s->G.L.two_level) {
+            kmgpu_shard_destroy(s);
+            return fail(KMGPU_EUNSUPPORTED, "slices of this size cannot be grouped");
+        }
+        for (int i = 0; i < n_tables; i++)
+            if ((uint64_t)(s->G.L.first_sb[i + 1] - s->G.L.first_sb[i]) * world > (uint64_t)PART_MAXP) {
+                kmgpu_shard_destroy(s);
+                return fail(KMGPU_EUNSUPPORTED, "table %d: %u super-buckets per rank x %d ranks exceed what one routing pass sorts into (%d)", i,
+                            s->G.L.first_sb[i + 1] - s->G.L.first_sb[i], world, PART_MAXP);
+            }
+    }
+    const size_t nb_words = (size_t)world * max_positions / 32;
+    cudaError_t e = cudaMalloc(&s->rec1, (size_t)s->G.n_sb * s->G.L.cap1 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cur1, (size_t)s->G.n_sb * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->cur1, 0, (size_t)s->G.n_sb * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->flags, 8);
+    if (e == cudaSuccess) e = cudaMemset(s->flags, 0, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->newbits, nb_words * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->newbits, 0, nb_words * 4);
     if (e != cudaSuccess) {
+        cudaGetLastError();
         kmgpu_shard_destroy(s);
-        return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "shard queues: %s", cudaGetErrorString(e));
+        return fail(e == cudaErrorMemoryAllocation ? KMGPU_ENOMEM : KMGPU_ECUDA, "shard stores: %s", cudaGetErrorString(e));
     }
     *out = s;
     return KMGPU_OK;
@@ -2768,13 +2808,15 @@ extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s)
     if (s->ipc)
         for (int q = 0; q < s->world; q++) {
             if (q == s->rank) continue;
-            for (int i = 0; i < s->nt; i++)
-                if (s->peers[q].rq[i]) cudaIpcCloseMemHandle(s->peers[q].rq[i]);
-            if (s->peers[q].rcur) cudaIpcCloseMemHandle(s->peers[q].rcur);
+            if (s->peers[q].rec1) cudaIpcCloseMemHandle(s->peers[q].rec1);
+            if (s->peers[q].cur1) cudaIpcCloseMemHandle(s->peers[q].cur1);
+            if (s->peers[q].flags) cudaIpcCloseMemHandle(s->peers[q].flags);
+            if (s->peers[q].newbits) cudaIpcCloseMemHandle(s->peers[q].newbits);
         }
-    for (int i = 0; i < s->nt; i++)
-        if (s->rq[i]) cudaFree(s->rq[i]);
-    if (s->rcur) cudaFree(s->rcur);
+    if (s->rec1) cudaFree(s->rec1);
+    if (s->cur1) cudaFree(s->cur1);
+    if (s->flags) cudaFree(s->flags);
+    if (s->newbits) cudaFree(s->newbits);
     if (s->local) kmgpu_destroy(s->local);
     delete s;
     return KMGPU_OK;
@@ -2790,13 +2832,23 @@ extern "C" int kmgpu_shard_slice(kmgpu_shard_t* s, int table, uint64_t* lo, uint
     return KMGPU_OK;
 }
 
+extern "C" int kmgpu_shard_stats(kmgpu_shard_t* s, uint64_t* n_occupied_local, uint64_t* n_unique_share, uint64_t* store_bytes)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    if (n_occupied_local) *n_occupied_local = s->local->n_occupied;
+    if (n_unique_share) *n_unique_share = s->n_unique;
+    if (store_bytes) *store_bytes = (uint64_t)s->G.n_sb * s->G.L.cap1 * 8;
+    return KMGPU_OK;
+}
+
 extern "C" int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles)
 {
     if (!s || !handles) return fail(KMGPU_EINVAL, "null argument");
     CKR(set_device(s->local->device));
-    for (int i = 0; i <= s->nt; i++) {
+    void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->cur1, s->flags, s->newbits};
+    for (int i = 0; i < KMGPU_SHARD_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t mh;
-        CK(cudaIpcGetMemHandle(&mh, i < s->nt ? (void*)s->rq[i] : (void*)s->rcur));
+        CK(cudaIpcGetMemHandle(&mh, ptrs[i]));
         memcpy(handles + (size_t)i * KMGPU_IPC_HANDLE_BYTES, &mh, KMGPU_IPC_HANDLE_BYTES);
     }
     return KMGPU_OK;
@@ -2807,18 +2859,17 @@ extern "C" int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all)
     if (!s || !all) return fail(KMGPU_EINVAL, "null argument");
     CKR(set_device(s->local->device));
     for (int q = 0; q < s->world; q++) {
-        for (int i = 0; i <= s->nt; i++) {
-            void* p = nullptr;
-            if (q == s->rank) {
-                p = i < s->nt ? (void*)s->rq[i] : (void*)s->rcur;
-            } else {
+        void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->cur1, s->flags, s->newbits};
+        if (q != s->rank)
+            for (int i = 0; i < KMGPU_SHARD_IPC_HANDLES; i++) {
                 cudaIpcMemHandle_t mh;
-                memcpy(&mh, all + ((size_t)q * (s->nt + 1) + i) * KMGPU_IPC_HANDLE_BYTES, KMGPU_IPC_HANDLE_BYTES);
-                CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+                memcpy(&mh, all + ((size_t)q * KMGPU_SHARD_IPC_HANDLES + i) * KMGPU_IPC_HANDLE_BYTES, KMGPU_IPC_HANDLE_BYTES);
+                CK(cudaIpcOpenMemHandle(&ptrs[i], mh, cudaIpcMemLazyEnablePeerAccess));
             }
-            if (i < s->nt) s->peers[q].rq[i] = (uint32_t*)p;
-            else s->peers[q].rcur = (unsigned long long*)p;
-        }
+        s->peers[q].rec1 = (unsigned long long*)ptrs[0];
+        s->peers[q].cur1 = (uint32_t*)ptrs[1];
+        s->peers[q].flags = (unsigned long long*)ptrs[2];
+        s->peers[q].newbits = (uint32_t*)ptrs[3];
     }
     s->attached = true;
     s->ipc = true;
@@ -2827,7 +2878,7 @@ extern "C" int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all)
 
 extern "C" int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n)
 {
-    if (!all || n < 1 || n > 8) return fail(KMGPU_EINVAL, "bad shard list");
+    if (!all || n < 1 || n > MAX_WORLD) return fail(KMGPU_EINVAL, "bad shard list");
     for (int a = 0; a < n; a++) {
         if (!all[a] || all[a]->world != n || all[a]->rank != a) return fail(KMGPU_EINVAL, "shard %d is not rank %d of %d", a, a, n);
         CKR(set_device(all[a]->local->device));
@@ -2840,8 +2891,10 @@ extern "C" int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n)
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
                 cudaGetLastError();
             }
-            for (int i = 0; i < all[a]->nt; i++) all[a]->peers[b].rq[i] = all[b]->rq[i];
-            all[a]->peers[b].rcur = all[b]->rcur;
+            all[a]->peers[b].rec1 = all[b]->rec1;
+            all[a]->peers[b].cur1 = all[b]->cur1;
+            all[a]->peers[b].flags = all[b]->flags;
+            all[a]->peers[b].newbits = all[b]->newbits;
         }
         all[a]->attached = true;
         all[a]->ipc = false;
@@ -2869,29 +2922,52 @@ extern "C" int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint6
     ChunkDev cd;
     CKR(stage_range(h, seqs, offsets, n_reads, first, last, flags, &cd, needs_acgt_check(h, flags), 0, st));
     Input in = make_input(cd);
-    const uint64_t stride = ((uint64_t)in.n_pos + 7) & ~7ull;
-    CKR(h->d_bins.ensure((size_t)s->nt * stride));
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
-    HashCfg H{h->hash, h->k};
-    Pred P;
-    memset(&P, 0, sizeof P);
-    unsigned gt = n_tiles(in.n_pos);
-    if (H.kind == TWOBIT) launch_hashbins<TWOBIT, 0>(false, gt, st, s->full, s->full, H, P, in, h->d_bins.p, stride, h->d_ctrl);
-    else launch_hashbins<MURMUR, 0>(false, gt, st, s->full, s->full, H, P, in, h->d_bins.p, stride, h->d_ctrl);
-    for (int i = 0; i < s->nt; i++) {
-        RouteDst dst;
-        dst.world = s->world;
-        for (int q = 0; q < 8; q++) {
-            dst.queue[q] = q < s->world ? s->peers[q].rq[i] : nullptr;
-            dst.cursor[q] = q < s->world ? s->peers[q].rcur + i : nullptr;
-        }
-        k_route<<<(in.n_pos + 2047) / 2048, 256, 0, st>>>(h->d_bins.p + (size_t)i * stride, in.n_pos, (uint32_t)s->slice[i], dst,
-                                                         (unsigned long long)s->qcap, h->d_ctrl);
+    CK(cudaEventRecord(h->ev0, st));
+    const HashCfg H{h->hash, h->k};
+    int srck = 0;
+    if (H.kind == MURMUR) {
+        CKR(h->d_hash64.ensure(in.n_pos));
+        k_hash64<MURMUR><<<n_tiles(in.n_pos), THREADS, 0, st>>>(H, in, h->d_hash64.p);
+        in.hashes = h->d_hash64.p;
+        srck = 1;
+        h->all_launches += 1;
     }
-    h->all_launches += 1 + s->nt;
+    ShardRoute R;
+    memset(&R, 0, sizeof R);
+    R.world = s->world;
+    for (int q = 0; q < s->world; q++) {
+        R.rec[q] = s->peers[q].rec1;
+        R.cursor[q] = s->peers[q].cur1;
+        R.flags[q] = s->peers[q].flags;
+    }
+    for (int i = 0; i < s->nt; i++) {
+        R.slice[i] = s->slice[i];
+        R.slice_magic[i] = ~0ull / s->slice[i];
+    }
+    PartArgs A;
+    memset(&A, 0, sizeof A);
+    A.S = s->full;
+    A.H = H;
+    A.in = in;
+    A.pos_base = (uint32_t)((uint64_t)s->rank * s->max_positions);
+    A.have_valid = 1;
+    A.table0 = 0;
+    A.count_kmers = 1;
+    A.L = s->G.L;
+    A.ctrl = h->d_ctrl;
+    Pred P0;
+    memset(&P0, 0, sizeof P0);
+    const dim3 grid((in.n_pos + 8191) / 8192, s->nt);
+    if (srck) CKR((launch_part_inst<8192, 512, 3, 1, false, false>(grid, st, A, s->full, P0, R)));
+    else CKR((launch_part_inst<8192, 512, 3, 0, false, false>(grid, st, A, s->full, P0, R)));
+    h->all_launches += 1;
+    CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
-    if (h->h_ctrl->non_acgt) return fail(KMGPU_ECUDA, "a receive queue overflowed (%llu updates dropped)", (unsigned long long)h->h_ctrl->non_acgt);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ingest_ms += ms;
     if (n_kmers_out) *n_kmers_out = h->h_ctrl->n_kmers;
     return KMGPU_OK;
 }
@@ -2904,42 +2980,82 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
     CKR(set_device(h->device));
     if (h->kind == BYTE && h->use_bigcount) return fail(KMGPU_EUNSUPPORTED, "bigcount is not maintained by sharded sketches");
     cudaStream_t st = h->stream;
-    std::vector<DeltaPass> passes;
-    if (!plan_delta(h, passes)) return fail(KMGPU_EUNSUPPORTED, "slices of this size are not supported by the sharded path yet");
-    unsigned long long cur[MAX_TABLES];
-    CK(cudaMemcpyAsync(cur, s->rcur, sizeof cur, cudaMemcpyDeviceToHost, st));
+    unsigned long long fl = 0;
+    CK(cudaMemcpyAsync(&fl, s->flags, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    uint64_t max_span = 0;
-    for (const DeltaPass& p : passes) max_span = std::max<uint64_t>(max_span, p.hi - p.lo);
-    size_t need_lanes = h->kind == BIT ? ((max_span + 127) / 128) * 8 + 8 : ((max_span + 7) & ~7ull) + 8;
-    if (h->d_delta.cap < need_lanes) h->delta_zeroed = 0;
-    CKR(h->d_delta.ensure(need_lanes));
-    if (h->delta_zeroed < h->d_delta.cap) {
-        CK(cudaMemsetAsync(h->d_delta.p, 0, h->d_delta.cap * 2, st));
-        h->delta_zeroed = h->d_delta.cap;
+    if (fl) {
+        CK(cudaMemsetAsync(s->flags, 0, 8, st));
+        CK(cudaMemsetAsync(s->cur1, 0, (size_t)s->G.n_sb * 4, st));
+        return fail(KMGPU_ENOMEM, "a receive region of rank %d overflowed (heavily repeated k-mers): the round was not applied; create the shards with a "
+                                  "smaller max_positions_per_route", s->rank);
     }
+    const GroupPlan& G = s->G;
+    const uint32_t n_pos_all = (uint32_t)((uint64_t)s->world * s->max_positions);
+    CKR(h->d_cursors.ensure(G.n_buckets));
+    if (!try_ensure(h->d_records, std::max<uint64_t>((uint64_t)G.n_buckets * G.L.cap, 2)))
+        return fail(KMGPU_ENOMEM, "no room for the bucket store of a sharded round");
+    CKR(h->d_binlist.ensure(1));
+    CK(cudaMemsetAsync(s->newbits, 0, (size_t)n_pos_all / 8, st));
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
-    for (const DeltaPass& p : passes) {
-        uint64_t n = cur[p.table];
-        if (n > s->qcap) return fail(KMGPU_ECUDA, "receive queue overflow");
-        if (n == 0) continue;
-        unsigned gs = (unsigned)((n + 2047) / 2048);
-        if (h->kind == BIT) {
-            k_scatter<true><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
-            unsigned gb = (unsigned)(((uint64_t)(p.hi - p.lo) + 128 * 256 - 1) / (128 * 256));
-            k_fold_bits<<<gb, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, -1);
-        } else {
-            k_scatter<false><<<gs, 256, 0, st>>>(s->rq[p.table], (uint32_t)n, p.lo, p.hi, h->d_delta.p);
-            unsigned gf = (unsigned)(((uint64_t)(p.hi - p.lo) + 2047) / 2048);
-            if (h->kind == BYTE) k_fold<BYTE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr, -1);
-            else k_fold<NIBBLE><<<gf, 256, 0, st>>>(h->dev.tables[p.table], p.table, p.lo, p.hi, h->d_delta.p, nullptr, 0ull, h->d_ctrl, 0, nullptr, -1);
-        }
-        h->all_launches += 2;
+    CK(cudaEventRecord(h->ev0, st));
+    const GroupTurn tn{0, h->nt, 0, G.n_buckets, 0, G.n_sb};
+    const Store s1{s->rec1, nullptr, s->cur1, G.L.cap1, 0};
+    SatBitsG sb;
+    memset(&sb, 0, sizeof sb);
+    Pred P0;
+    memset(&P0, 0, sizeof P0);
+    const HashCfg H{h->hash, h->k};
+    const std::vector<Part> none;
+    CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, 0u, n_pos_all, 1, 0, sb, &s1, s->newbits));
+    CK(cudaEventRecord(h->ev1, st));
+    CKR(read_ctrl(h));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ingest_ms += ms;
+    if (h->h_ctrl->overflow) {
+        const unsigned bits = (unsigned)(h->h_ctrl->overflow & 3ull);
+        CK(cudaMemsetAsync(&h->d_ctrl->overflow, 0, sizeof(unsigned long long), st));
+        h->n_regroups++;
+        CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, bits, n_pos_all, 1, 0, sb, &s1, s->newbits));
+        CKR(read_ctrl(h));
+        if (h->h_ctrl->overflow) return fail(KMGPU_ECUDA, "internal: regrouping run overflowed");
     }
-    CK(cudaMemsetAsync(s->rcur, 0, MAX_TABLES * sizeof(unsigned long long), st));
+    h->n_occupied += h->h_ctrl->n_z0;
+    CK(cudaMemsetAsync(s->cur1, 0, (size_t)s->G.n_sb * 4, st));
+    CK(cudaStreamSynchronize(st));
+    h->satbits_valid = false;
+    return KMGPU_OK;
+}
+
+// after every rank has applied the round: the positions of THIS rank's reads that any owner marked new (a k-mer is new iff
+// one of its bins was empty when it arrived, whichever rank owns that bin)
+extern "C" int kmgpu_shard_count_new(kmgpu_shard_t* s, uint64_t* n_new_out)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    kmgpu_sketch* h = s->local;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    const size_t words = (size_t)s->max_positions / 32, w0 = (size_t)s->rank * words;
+    CKR(h->d_newbits.ensure(words));
+    CK(cudaMemcpyAsync(h->d_newbits.p, s->newbits + w0, words * 4, cudaMemcpyDeviceToDevice, st));
+    PeerPtrs pp;
+    pp.n = 0;
+    for (int q = 0; q < s->world; q++) {   // OR of the peers' bitmaps over NVLink, eight peers per pass
+        if (q != s->rank) pp.p[pp.n++] = s->peers[q].newbits + w0;
+        if (pp.n == 8 || (q == s->world - 1 && pp.n)) {
+            unsigned gsz = (unsigned)std::min<uint64_t>((words + 255) / 256, 148 * 16);
+            k_merge_peers<<<gsz, 256, 0, st>>>(BIT, h->d_newbits.p, pp, 0, words);
+            h->all_launches += 1;
+            pp.n = 0;
+        }
+    }
+    CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+    k_popc<<<(unsigned)std::min<size_t>((words + 255) / 256, 148 * 8), 256, 0, st>>>(h->d_newbits.p, words, &h->d_ctrl->n_unique);
+    h->all_launches += 1;
     CK(cudaGetLastError());
     CKR(read_ctrl(h));
-    h->n_occupied += h->h_ctrl->n_z0;
-    h->satbits_valid = false;
+    s->n_unique += h->h_ctrl->n_unique;
+    if (n_new_out) *n_new_out = h->h_ctrl->n_unique;
     return KMGPU_OK;
 }

@@ -53,6 +53,17 @@ struct Store {
     __device__ __forceinline__ uint32_t room(uint32_t p) const { return off ? (uint32_t)(off[p - p0 + 1] - off[p - p0]) : cap; }
 };
 
+// address-sharded sketches: where rank r's super-bucket regions live (peer memory over NVLink), see k_part MODE 3
+constexpr int MAX_WORLD = 16;
+struct ShardRoute {
+    unsigned long long* rec[MAX_WORLD];      // super-bucket store of every rank
+    uint32_t* cursor[MAX_WORLD];             // its cursors
+    unsigned long long* flags[MAX_WORLD];    // its overflow word
+    uint64_t slice[G_MAXT];                  // bins of table i held by every rank (the last rank may use fewer)
+    uint64_t slice_magic[G_MAXT];
+    int world;
+};
+
 // ---- bulk asynchronous copies + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
@@ -101,6 +112,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   MODE 0  stream -> buckets            partition = bin >> 15            record = position << 15 | bin & 0x7FFF
 //   MODE 1  stream -> super-buckets      partition = bin >> 27            record = position << 27 | bin & 0x7FFFFFF
 //   MODE 2  super-bucket -> its buckets  partition = (rec >> 15) & 0xFFF  record = position << 15 | bin & 0x7FFF
+//   MODE 3  stream -> the super-buckets of the rank that owns the bin (address-sharded sketches): partition = owner *
+//           super-buckets per rank + (bin within the owner's slice >> 27); the runs are written straight into the owner's
+//           store over NVLink peer memory, one remote atomicAdd per (CTA, partition) reserves them — the k-mer all-to-all
 //
 //   SRC 0: the k-mers are hashed here from the 2-bit stream (TwoBit);  SRC 1: 64-bit hashes precomputed by k_hash64
 //   (Murmur: hashing 2 x k letters per table would dominate) or supplied by the caller (kmgpu_add_hashes).
@@ -181,13 +195,14 @@ __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t
 }
 
 template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP>
-__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
-k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P)
+__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || MODE == 3 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
+k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P, const __grid_constant__ ShardRoute R)
 {
-    constexpr bool WIDE = MODE == 1 || WIDEP;
+    constexpr bool WIDE = MODE == 1 || MODE == 3 || WIDEP;
     constexpr int PER = T / NTHR;
     constexpr int BPT = (PART_MAXP + NTHR - 1) / NTHR;
-    constexpr int PB = MODE == 1 ? SB_BIN_SHIFT : BKT_SHIFT;   // payload bits of the records written
+    constexpr bool SBMODE = MODE == 1 || MODE == 3;            // partitions are super-buckets
+    constexpr int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;      // payload bits of the records written
     extern __shared__ __align__(16) unsigned char pt_raw[];
     uint2* stage = reinterpret_cast<uint2*>(pt_raw);                          // T slots, grouped by partition
     uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // PART_MAXP: count, then run start | cursor base << 16
@@ -228,6 +243,7 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         } else {
             np = A.L.first_sb[t + 1] - A.L.first_sb[t];
             cur0 = A.L.first_sb[t];
+            if (MODE == 3) np *= (uint32_t)R.world;
         }
         if (p0 >= A.in.n_pos) return;
     }
@@ -254,17 +270,27 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         for (int j = 0; j < PER; j++) {
             const uint32_t lp = j * NTHR + tid;
             key[j] = NONE;
-            if (MODE == 1) {
+            if (SBMODE) {
                 if (j & 1) pid1[j >> 1] |= 0xFFFF0000u; else pid1[j >> 1] = 0xFFFFu;
             }
             if (p0 + lp < A.in.n_pos && ((tile.valid[lp >> 5] >> (lp & 31)) & 1u)) {
                 const uint64_t h = SRC == 1 ? __ldcs(A.in.hashes + p0 + lp) : hash_twobit(tile.words, lp, A.H.k);
                 if (!PRED || pred_pass(P, M, h)) {
-                    const uint64_t bin = mod_magic(h, size, magic);
+                    uint64_t bin = mod_magic(h, size, magic);
                     n_k++;
-                    if (MODE == 1) {
+                    if (SBMODE) {
+                        uint32_t pid;
+                        if (MODE == 3) {
+                            // owner = bin / slice (same reciprocal trick as mod_magic), then the bin within the owner's slice
+                            uint64_t q = __umul64hi(bin, R.slice_magic[t]);
+                            uint64_t rem = bin - q * R.slice[t];
+                            if (rem >= R.slice[t]) { rem -= R.slice[t]; q++; }
+                            bin = rem;
+                            pid = (uint32_t)q * (A.L.first_sb[t + 1] - A.L.first_sb[t]) + (uint32_t)(bin >> SB_BIN_SHIFT);
+                        } else {
+                            pid = (uint32_t)(bin >> SB_BIN_SHIFT);
+                        }
                         key[j] = (uint32_t)bin & ((1u << SB_BIN_SHIFT) - 1);
-                        const uint32_t pid = (uint32_t)(bin >> SB_BIN_SHIFT);
                         if (j & 1) pid1[j >> 1] = (pid1[j >> 1] & 0xFFFFu) | (pid << 16); else pid1[j >> 1] = (pid1[j >> 1] & 0xFFFF0000u) | pid;
                     } else {
                         key[j] = (uint32_t)bin;   // MODE 0 tables have at most PART_MAXP << 15 < 2^28 bins
@@ -277,7 +303,7 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     for (int j = 0; j < PER; j++) {
         uint32_t r = 0;
         if (key[j] != NONE) {
-            const uint32_t pid = MODE == 1 ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
+            const uint32_t pid = SBMODE ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
             r = atomicAdd(&hist[pid], 1u);
         }
         if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
@@ -321,7 +347,13 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     for (int q = 0; q < BPT; q++) {
         const uint32_t b = tid * BPT + q;
         if (b < np) hist[b] = at;   // run start (the count has been read by its only reader, this thread)
-        gbase[q] = c[q] ? atomicAdd(&A.dst.cursor[cur0 + b], c[q]) : 0u;   // in flight while the records are placed
+        if (MODE == 3) {
+            const uint32_t nsb = A.L.first_sb[t + 1] - A.L.first_sb[t];
+            const uint32_t owner = b / nsb;
+            gbase[q] = c[q] ? atomicAdd(R.cursor[owner] + cur0 + (b - owner * nsb), c[q]) : 0u;   // remote (NVLink) for other ranks
+        } else {
+            gbase[q] = c[q] ? atomicAdd(&A.dst.cursor[cur0 + b], c[q]) : 0u;   // in flight while the records are placed
+        }
         at += c[q];
     }
     __syncthreads();
@@ -330,14 +362,14 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
 #pragma unroll
     for (int j = 0; j < PER; j++) {
         if (key[j] == NONE) continue;
-        const uint32_t pid = MODE == 1 ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
+        const uint32_t pid = SBMODE ? ((j & 1) ? pid1[j >> 1] >> 16 : pid1[j >> 1] & 0xFFFFu) : key[j] >> BKT_SHIFT;
         const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
         const uint32_t slot = (hist[pid] & 0xFFFFu) + r;
         if (MODE == 2) {
             // the position travels with the record: fetch it again (L1/L2 hit) rather than hold 16 more registers
             const unsigned long long v = __ldcs(srec + p0 + j * NTHR + tid);
             stage[slot] = make_uint2((uint32_t)(v >> SB_BIN_SHIFT), key[j]);
-        } else if (MODE == 1) {
+        } else if (SBMODE) {
             stage[slot] = make_uint2(key[j], (pid << 14) | (uint32_t)(j * NTHR + tid));
         } else {
             stage[slot] = make_uint2(key[j] & (BKT_BINS - 1), (pid << 14) | (uint32_t)(j * NTHR + tid));
@@ -367,8 +399,15 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         unsigned long long rec;
         if (MODE == 2) rec = ((unsigned long long)m.x << BKT_SHIFT) | (m.y & (BKT_BINS - 1));
         else rec = ((unsigned long long)(A.pos_base + p0 + (m.y & 0x3FFFu)) << PB) | m.x;
-        if (idx < A.dst.room(cur0 + pid)) A.dst.rec[A.dst.base(cur0 + pid) + idx] = rec;
-        else over = true;
+        if (MODE == 3) {
+            const uint32_t nsb = A.L.first_sb[t + 1] - A.L.first_sb[t];
+            const uint32_t owner = pid / nsb;
+            if (idx < A.L.cap1) R.rec[owner][(unsigned long long)(cur0 + (pid - owner * nsb)) * A.L.cap1 + idx] = rec;
+            else atomicOr(R.flags[owner], 1ull);   // the owner refuses to apply a round with a region cut short
+        } else {
+            if (idx < A.dst.room(cur0 + pid)) A.dst.rec[A.dst.base(cur0 + pid) + idx] = rec;
+            else over = true;
+        }
     }
     if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
 }

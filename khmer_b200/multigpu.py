@@ -126,7 +126,9 @@ class ShardedGroup:
             if i < len(runs):
                 r0, r1 = runs[i]
                 kmers += self.shard.route((buf, off[r0:r1 + 1]), clean=clean)
-            self.barrier()          # every update of this round sits in its owner's queue
+            self.barrier()          # every update of this round sits in its owner's store
             self.shard.apply()
-            self.barrier()          # queues are empty again before anyone routes the next round
+            self.barrier()          # every owner has marked the new positions of the round
+            self.shard.count_new()
+            self.barrier()          # nobody reads a peer's bitmap or store any more: the next round may start
         return kmers

@@ -37,21 +37,27 @@ def test_sharded_equals_single_sketch(cls, k, world):
         buf, off = cabi.as_reads(reads[lo:hi])
         parts.append((buf, off, split_by_bases(buf, off, 20000)))
     rounds = max(len(p[2]) for p in parts)
-    kmers = 0
+    kmers = okmers = 0
+    o = ol.Oracle(cls, k, sizes)
     for i in range(rounds):
-        for r in range(world):                       # "all ranks route", then "all ranks apply"
+        for r in range(world):                       # "all ranks route", then "all ranks apply", then "all ranks count"
             buf, off, runs = parts[r]
             if i < len(runs):
                 a, b = runs[i]
                 kmers += shards[r].route((buf, off[a:b + 1]))
+                # the stream order of a round is rank 0's reads, then rank 1's, ...: what the single sketch is fed
+                lo, _ = shard_range(len(reads), r, world)
+                okmers += o.consume_reads(reads[lo + a: lo + b])
         for r in range(world):
             shards[r].apply()
-    o = ol.Oracle(cls, k, sizes)
-    assert kmers == o.consume_reads(reads)
+        for r in range(world):
+            shards[r].count_new()
+    assert kmers == okmers
     tables = _assemble(shards, 4)
     for i in range(4):
         assert np.array_equal(tables[i], o.table(i)), "table %d" % i
     assert sum(s.local.n_occupied() for s in shards) == o.n_occupied()
+    assert sum(s.stats()[1] for s in shards) == o.n_unique_kmers()
     for s in shards:
         s.close()
 
@@ -61,7 +67,7 @@ import os, sys
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
 import numpy as np, torch, torch.distributed as dist
 from khmer_b200 import cabi
-from khmer_b200.multigpu import ShardedGroup, shard_range
+from khmer_b200.multigpu import ShardedGroup, shard_range, split_by_bases
 import oracle_lib as ol
 from common import synth_reads
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -77,11 +83,21 @@ for cls, k in (("Countgraph", 20), ("SmallCountgraph", 31), ("Nodegraph", 32), (
     g.attach()
     lo, hi = shard_range(len(reads), rank, world)
     mine = g.consume_reads(reads[lo:hi])
+    # the single sketch is fed the rounds in their stream order: round i = run i of rank 0, of rank 1, ...
     o = ol.Oracle(cls, k, sizes)
-    total = o.consume_reads(reads)
-    t = torch.tensor([mine, sh.local.n_occupied()], dtype=torch.int64, device=dev)
+    runs = []
+    for r in range(world):
+        a, b = shard_range(len(reads), r, world)
+        buf, off = cabi.as_reads(reads[a:b])
+        runs.append([(a + x, a + y) for x, y in split_by_bases(buf, off, 200000)])
+    total = 0
+    for i in range(max(len(x) for x in runs)):
+        for r in range(world):
+            if i < len(runs[r]):
+                total += o.consume_reads(reads[runs[r][i][0]:runs[r][i][1]])
+    t = torch.tensor([mine, sh.stats()[0], sh.stats()[1]], dtype=torch.int64, device=dev)
     dist.all_reduce(t)
-    assert int(t[0]) == total and int(t[1]) == o.n_occupied(), (cls, t.tolist(), total, o.n_occupied())
+    assert int(t[0]) == total and int(t[1]) == o.n_occupied() and int(t[2]) == o.n_unique_kmers(), (cls, t.tolist(), total, o.n_occupied(), o.n_unique_kmers())
     for i in range(4):
         lo_b, hi_b = sh.slice(i)
         want = o.table(i)
