@@ -107,6 +107,13 @@ int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, u
                         uint32_t flags, const kmgpu_band_t* band, const kmgpu_mask_t* mask,
                         uint64_t* n_kmers_out);
 
+/* kmgpu_consume_reads that also returns, per base of [offsets[0], offsets[n_reads]), whether the k-mer starting there was NEW —
+ * the bool Storage::add / test_and_set_bits returns for it in stream order (storage.hh:172-199, :564-569, :571-624).  Replaces the
+ * per-k-mer `store->test_and_set_bits(kmer)` of Hashgraph::consume_sequence_and_tag (src/oxli/hashgraph.cc:200-271): the tag scan over
+ * these bits stays on the host.  newbits_out holds ceil((offsets[n_reads] - offsets[0]) / 32) words, bit b of word w = base 32 w + b. */
+int kmgpu_consume_reads_new(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                            uint32_t* newbits_out, uint64_t* n_kmers_out, uint64_t* n_new_out);
+
 /* Same, from 2-bit packed host buffers as produced by the host read feed: 64-bit words, 32 bases per
  * word, first base in the two most significant bits, code A=0 T=1 C=2 G=3
  * (include/oxli/kmer_hash.hh:70-72); reads are concatenated without padding, offsets in bases. */
@@ -197,7 +204,10 @@ int kmgpu_recount_occupied(kmgpu_t* h);
  * IPC handles of its tables, the caller exchanges them (any transport), every rank attaches its
  * peers, then:  reduce_scatter (rank r folds slice r of every peer into its own tables with the
  * saturating add / OR above, reading peers over NVLink)  ->  caller barrier  ->  all_gather (rank r
- * pulls every other slice from its owner)  ->  caller barrier. */
+ * pulls every other slice from its owner)  ->  caller barrier.
+ * The merge folds table bytes only; n_occupied is recounted.  A ByteStorage with bigcount on is refused (KMGPU_EUNSUPPORTED): which
+ * replica saw a counter's 255th touch is lost, so neither the bigcount map nor counts above 255 could be exact.  n_unique_kmers stays
+ * each replica's own count unless the first-touch log is used (below). */
 #define KMGPU_IPC_HANDLE_BYTES 64
 int kmgpu_ipc_export(kmgpu_t* h, uint8_t* handles /* n_tables * 64 bytes */);
 int kmgpu_ipc_attach(kmgpu_t* h, int rank, int world, const uint8_t* all_handles /* world * n_tables * 64 */);
@@ -207,9 +217,24 @@ int kmgpu_all_gather_peers(kmgpu_t* h);
 /* single-process variant: fold sketches living on different GPUs of this process into replicas[0..n)
  * (peer access enabled internally). */
 int kmgpu_reduce_replicas(kmgpu_t** replicas, int n);
+/* the attach step of kmgpu_reduce_replicas alone (replica r becomes rank r of n; kmgpu_ipc_detach undoes it): lets a single process
+ * call kmgpu_first_touch_resolve on every replica before it merges them */
+int kmgpu_attach_replicas(kmgpu_t** replicas, int n);
 /* the 32-bit-word range [*w0, *w1) of a table of n_words words that rank `rank` of `world` owns in the
  * reduce-scatter / all-gather above (pure arithmetic, no device needed) */
 int kmgpu_slice_range(uint64_t n_words, int world, int rank, uint64_t* w0, uint64_t* w1);
+
+/* Replicated sketches, exact n_unique_kmers and abundance_distribution across ranks ("a bin's global first toucher
+ * lives on the lowest rank that touched it").  With the first-touch log on, a sketch records, per newly occupied bin, which k-mer
+ * occurrence occupied it (and, when it is the tracking filter of kmgpu_abundance_distribution, that k-mer's count).
+ * kmgpu_first_touch_resolve — called on every rank of an attached group after all ranks have ingested and BEFORE the tables are
+ * merged — returns how many of this rank's occurrences are new when the ranks' read shards are taken in rank order (an occurrence
+ * is dropped when every bin it was first to occupy locally is occupied on a lower rank), accumulates their counts into hist
+ * (nullable), returns the rank-local number for comparison, and empties the log.  The sum over ranks equals the n_unique_kmers
+ * (the histogram) of ONE sketch fed rank 0's reads, then rank 1's, ...  All replicas must start the epoch from the same state
+ * (freshly reset, or just merged).  Sketches with the log on always take the grouped path. */
+int kmgpu_first_touch_log(kmgpu_t* h, int on);
+int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64_t* n_local_out, uint64_t* hist);
 
 /* ---- multi-GPU, address-sharded sketches ---------------------------------
  * For tables too large to replicate: bins [r*S_i, (r+1)*S_i) of table i live on rank r (S_i = slice length).  Every rank

@@ -28,11 +28,12 @@ SYMBOLS = [
     "kmgpu_set_use_bigcount", "kmgpu_get_use_bigcount", "kmgpu_consume_reads", "kmgpu_consume_packed",
     "kmgpu_batch_create", "kmgpu_batch_destroy", "kmgpu_batch_info", "kmgpu_consume_batch", "kmgpu_add_hashes",
     "kmgpu_get_counts", "kmgpu_kmer_counts", "kmgpu_kmer_hashes", "kmgpu_read_medians", "kmgpu_median_at_least",
-    "kmgpu_abundance_distribution", "kmgpu_normalize_batch", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
+    "kmgpu_abundance_distribution", "kmgpu_normalize_batch", "kmgpu_consume_reads_new", "kmgpu_first_touch_log",
+    "kmgpu_first_touch_resolve", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
     "kmgpu_table_nbytes", "kmgpu_download_table", "kmgpu_upload_table", "kmgpu_bigcount_size",
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
     "kmgpu_ipc_attach", "kmgpu_ipc_detach", "kmgpu_reduce_scatter_peers", "kmgpu_all_gather_peers",
-    "kmgpu_reduce_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
+    "kmgpu_reduce_replicas", "kmgpu_attach_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
     "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
     "kmgpu_shard_create", "kmgpu_shard_destroy", "kmgpu_shard_local", "kmgpu_shard_slice", "kmgpu_shard_ipc_export",
     "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_apply",
@@ -91,6 +92,9 @@ def lib():
                                                    C.c_uint32, C.c_void_p]
         L.kmgpu_normalize_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
                                             C.c_void_p, u64p, u64p]
+        L.kmgpu_consume_reads_new.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, u64p, u64p]
+        L.kmgpu_first_touch_log.argtypes = [C.c_void_p, C.c_int]
+        L.kmgpu_first_touch_resolve.argtypes = [C.c_void_p, u64p, u64p, C.c_void_p]
         L.kmgpu_stats.argtypes = [C.c_void_p, u64p, u64p]
         L.kmgpu_set_stats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.kmgpu_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -110,6 +114,7 @@ def lib():
         L.kmgpu_reduce_scatter_peers.argtypes = [C.c_void_p]
         L.kmgpu_all_gather_peers.argtypes = [C.c_void_p]
         L.kmgpu_reduce_replicas.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.kmgpu_attach_replicas.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.kmgpu_profile_reset.argtypes = [C.c_void_p]
         L.kmgpu_profile_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), u64p, u64p]
         L.kmgpu_sync.argtypes = [C.c_void_p]
@@ -316,6 +321,27 @@ class Sketch:
                                                  CLEAN if clean else 0, _ptr(hist)))
         return hist
 
+    def consume_reads_new(self, reads, clean=True):
+        """consume + one flag per base: 1 where the k-mer starting there was new in stream order (Storage::add's bool).
+        Returns (n_kmers, n_new, flags uint8[n_bases])."""
+        buf, off = as_reads(reads)
+        nb = int(off[-1] - off[0]) if len(off) > 1 else 0
+        bits = np.zeros((nb + 31) // 32 + 1, dtype=np.uint32)
+        n, nn = C.c_uint64(), C.c_uint64()
+        check(lib().kmgpu_consume_reads_new(self.h, _ptr(buf), _ptr(off), len(off) - 1, CLEAN if clean else 0, _ptr(bits),
+                                            C.byref(n), C.byref(nn)))
+        flags = np.unpackbits(bits.view(np.uint8), bitorder="little")[:nb]
+        return n.value, nn.value, flags
+
+    def first_touch_log(self, on=True):
+        check(lib().kmgpu_first_touch_log(self.h, int(on)))
+
+    def first_touch_resolve(self, hist=None):
+        """(globally new occurrences of this rank, its rank-local count); hist (uint64[65536]) is accumulated when given"""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib().kmgpu_first_touch_resolve(self.h, C.byref(a), C.byref(b), _ptr(hist) if hist is not None else None))
+        return a.value, b.value
+
     def normalize_batch(self, reads, cutoff, paired=None, clean=False):
         """Digital normalization of a batch in stream order (scripts/normalize-by-median.py:155-179): returns the keep flags
         (uint8 per read) and the number of k-mers consumed.  `paired`: optional uint8 per read, 1 = forms a pair with the next."""
@@ -515,6 +541,11 @@ def slice_range(n_words, world, rank):
     a, b = C.c_uint64(), C.c_uint64()
     check(lib().kmgpu_slice_range(n_words, world, rank, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def attach_replicas(sketches):
+    arr = (C.c_void_p * len(sketches))(*[s.h for s in sketches])
+    check(lib().kmgpu_attach_replicas(arr, len(sketches)))
 
 
 def reduce_replicas(sketches):

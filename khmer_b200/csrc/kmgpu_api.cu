@@ -134,6 +134,7 @@ struct ChunkDev {
     const uint64_t* words = nullptr;
     const uint32_t* offs = nullptr;
     const uint32_t* tfr = nullptr;
+    const uint32_t* valid = nullptr;   // bitmap of k-mer starts (k_valid_bits)
     uint32_t n_reads = 0;
     uint32_t n_pos = 0;
 };
@@ -147,6 +148,7 @@ struct kmgpu_batch {
         uint32_t* offs;
         uint32_t* tfr;
         uint32_t n_reads, n_pos;
+        uint32_t* valid;
     };
     std::vector<Piece> pieces;
 };
@@ -184,6 +186,7 @@ struct kmgpu_sketch {
         DevBuf<uint32_t> offs;
         DevBuf<uint64_t> offs64;
         DevBuf<uint32_t> tfr;
+        DevBuf<uint32_t> valid;
         PinBuf<uint32_t> h_offs;
         PinBuf<uint64_t> h_offs64;
         cudaEvent_t ready = nullptr;
@@ -202,11 +205,18 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_cur1;
     DevBuf<unsigned long long> d_off1, d_off2;   // exact region offsets of a regrouping run
     DevBuf<uint64_t> d_hash64;              // Murmur: 64-bit hash of every position of the chunk
+    DevBuf<uint16_t> d_fill;                // grouped path, persistent grouping: records in every sub-region
     DevBuf<uint32_t> d_readbits;            // one bit per read of a window (normalization: candidates / kept)
     DevBuf<uint32_t> d_upos, d_hitpos;      // normalization: positions of in-between reads; hits of their bins
     DevBuf<uint64_t> d_ubins, d_hitkey;
     DevBuf<uint16_t> d_uc0;
     uint64_t n_norm_unsure = 0;
+    // first-touch log (replicated sketches: exact n_unique_kmers / abundance_distribution across ranks)
+    bool ft_on = false, ft_defer = false;
+    DevBuf<uint32_t> d_newmask;
+    std::vector<std::pair<void*, uint64_t>> ft_segs;   // one segment of FtEntry per chunk
+    uint64_t ft_pending = 0, ft_epoch_unique = 0;
+    uint32_t ft_chunk = 0;
     uint64_t n_regroups = 0;
     bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
@@ -261,6 +271,7 @@ static Input make_input(const ChunkDev& c)
     in.hashes = nullptr;
     in.n_pos = c.n_pos;
     in.read_keep = nullptr;
+    in.valid = c.valid;
     return in;
 }
 static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
@@ -273,6 +284,7 @@ static Input make_hash_input(const uint64_t* d_hashes, uint32_t n)
     in.hashes = d_hashes;
     in.n_pos = n;
     in.read_keep = nullptr;
+    in.valid = nullptr;
     return in;
 }
 
@@ -483,14 +495,14 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
         if (h->dev.tables[i]) cudaFree(h->dev.tables[i]);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (int sl = 0; sl < kmgpu_sketch::N_STAGE; sl++) {
-        h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].offs64.release(); h->stage[sl].tfr.release();
+        h->stage[sl].ascii.release(); h->stage[sl].words.release(); h->stage[sl].offs.release(); h->stage[sl].offs64.release(); h->stage[sl].tfr.release(); h->stage[sl].valid.release();
         h->stage[sl].h_offs.release(); h->stage[sl].h_offs64.release();
         if (h->stage[sl].ready) cudaEventDestroy(h->stage[sl].ready);
     }
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_fill.release(); h->d_newmask.release(); for (auto& sg : h->ft_segs) cudaFree(sg.first); h->ft_segs.clear(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -605,6 +617,14 @@ extern "C" int kmgpu_reset(kmgpu_t* h)
     h->big.clear();
     h->big_dirty = true;
     h->satbits_valid = false;
+    if (h->ft_on) {   // a new epoch of the first-touch log
+        CK(cudaStreamSynchronize(h->stream));
+        for (auto& sg : h->ft_segs) cudaFree(sg.first);
+        h->ft_segs.clear();
+        h->ft_pending = 0;
+        h->ft_epoch_unique = 0;
+        h->ft_chunk = 0;
+    }
     return KMGPU_OK;
 }
 extern "C" int kmgpu_timer_start(kmgpu_t* h)
@@ -1364,7 +1384,7 @@ static int ingest_chunk(kmgpu_sketch* h, int src, HashCfg H, const Input& in, co
     if (in.n_pos == 0) return between ? between() : KMGPU_OK;
     {
         GroupPlan G;
-        if (plan_group(h, in.n_pos, h->nt > F_MAXT, &G))
+        if (plan_group(h, in.n_pos, h->nt > F_MAXT || h->ft_on, &G))
             return ingest_chunk_grouped(h, G, src, H, std::vector<Part>(1, Part{in, 0u, nullptr}), P, pred, M, res, between);
         if (h->nt > F_MAXT) return fail(KMGPU_EUNSUPPORTED, "sketches with more than %d tables need the grouped path, which this shape cannot take", F_MAXT);
         std::vector<DeltaPass> dp;
@@ -1493,7 +1513,10 @@ static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, ui
                                                              (uint32_t)n_words, h->d_ctrl_copy);
     CKR(S.tfr.ensure(n_tiles(n_pos) + 1));
     k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(S.offs.p, n_reads, n_tiles(n_pos), S.tfr.p);
-    h->all_launches += 2;
+    CKR(S.valid.ensure((size_t)n_pos / 32 + 2));
+    CK(cudaMemsetAsync(S.valid.p, 0, ((size_t)n_pos / 32 + 2) * 4, st));
+    if (n_reads) k_valid_bits<<<(n_reads + 255) / 256, 256, 0, st>>>(S.offs.p, n_reads, h->k, S.valid.p);
+    h->all_launches += 3;
     CK(cudaGetLastError());
     if (need_acgt_check) {
         CK(cudaMemcpyAsync(h->h_ctrl_copy, h->d_ctrl_copy, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -1505,6 +1528,7 @@ static int stage_chunk(kmgpu_sketch* h, const char* seqs, const ChunkPlan& c, ui
     out->words = S.words.p;
     out->offs = S.offs.p;
     out->tfr = S.tfr.p;
+    out->valid = S.valid.p;
     out->n_reads = n_reads;
     out->n_pos = n_pos;
     return KMGPU_OK;
@@ -1550,8 +1574,11 @@ static bool needs_acgt_check(const kmgpu_sketch* h, uint32_t flags) { return h->
 
 // upload the base range [b0, b1) of the caller's buffer with the reads overlapping it; offsets are clipped and
 // rebased on the device, so the host does O(log n_reads) work per chunk
+// `packed` != nullptr: the caller's buffer is the 2-bit stream itself (32 bases per word, b0 a multiple of 32): the words covering
+// [b0, b1) are uploaded as they are (a quarter of the bytes, no packing kernel)
 static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint64_t b0, uint64_t b1,
-                       uint32_t flags, ChunkDev* out, bool need_acgt_check, int slot, cudaStream_t st)
+                       uint32_t flags, ChunkDev* out, bool need_acgt_check, int slot, cudaStream_t st, const uint64_t* packed = nullptr,
+                       uint64_t packed_words = 0)
 {
     kmgpu_sketch::Stage& S = h->stage[slot];
     // r_lo = last read starting at or before b0; r_hi = first index whose offset is >= b1
@@ -1564,12 +1591,18 @@ static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offset
     uint32_t n_pos = (uint32_t)(b1 - b0);
     uint32_t nr = (uint32_t)(r_hi - r_lo);
     size_t n_words = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
-    CKR(S.ascii.ensure(std::max<size_t>(n_pos, 1)));
+    if (!packed) CKR(S.ascii.ensure(std::max<size_t>(n_pos, 1)));
     CKR(S.words.ensure(n_words));
     CKR(S.offs.ensure(nr + 1));
     CKR(S.offs64.ensure(nr + 1));
     CKR(S.tfr.ensure(n_tiles(n_pos) + 1));
-    if (n_pos) CK(cudaMemcpyAsync(S.ascii.p, seqs + b0, n_pos, cudaMemcpyHostToDevice, st));
+    if (packed) {
+        const uint64_t w0 = b0 / 32, w1 = std::min<uint64_t>(packed_words, w0 + n_words);
+        if (w1 - w0 < n_words) CK(cudaMemsetAsync(S.words.p + (w1 - w0), 0, (n_words - (w1 - w0)) * 8, st));
+        if (w1 > w0) CK(cudaMemcpyAsync(S.words.p, packed + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, st));
+    } else if (n_pos) {
+        CK(cudaMemcpyAsync(S.ascii.p, seqs + b0, n_pos, cudaMemcpyHostToDevice, st));
+    }
     // the caller's offsets may be pageable: a copy from pageable memory would block this thread until everything queued
     // before it on the stream (the sequence bytes just above) has gone over the bus; go through a pinned slice instead
     {
@@ -1585,11 +1618,16 @@ static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offset
         CK(cudaMemcpyAsync(S.offs64.p, src, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, st));
     }
     k_clip_offsets<<<(nr + 1 + 255) / 256, 256, 0, st>>>(S.offs64.p, nr + 1, b0, b1, S.offs.p);
+    if (packed) need_acgt_check = false;
     if (need_acgt_check) CK(cudaMemsetAsync(h->d_ctrl_copy, 0, sizeof(Ctrl), st));
-    k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(S.ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, S.words.p,
-                                                             (uint32_t)n_words, h->d_ctrl_copy);
+    if (!packed)
+        k_pack<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(S.ascii.p, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, S.words.p,
+                                                                 (uint32_t)n_words, h->d_ctrl_copy);
     k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(S.offs.p, nr, n_tiles(n_pos), S.tfr.p);
-    h->all_launches += 3;
+    CKR(S.valid.ensure((size_t)n_pos / 32 + 2));
+    CK(cudaMemsetAsync(S.valid.p, 0, ((size_t)n_pos / 32 + 2) * 4, st));
+    k_valid_bits<<<(nr + 255) / 256, 256, 0, st>>>(S.offs.p, nr, h->k, S.valid.p);
+    h->all_launches += packed ? 3 : 4;
     CK(cudaGetLastError());
     if (need_acgt_check) {
         CK(cudaMemcpyAsync(h->h_ctrl_copy, h->d_ctrl_copy, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -1601,18 +1639,19 @@ static int stage_range(kmgpu_sketch* h, const char* seqs, const uint64_t* offset
     out->words = S.words.p;
     out->offs = S.offs.p;
     out->tfr = S.tfr.p;
+    out->valid = S.valid.p;
     out->n_reads = nr;
     out->n_pos = n_pos;
     return KMGPU_OK;
 }
 
-extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
-                                   const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out)
+// host input, ASCII (seqs) or 2-bit packed (packed, packed_words): chunked, uploaded in parts on the copy stream, ingested
+// newbits_out (optional): one bit per base of [offsets[0], offsets[n_reads]), set iff the k-mer starting there was new
+// (Storage::add / test_and_set_bits returned true for it in stream order); n_new_out: their number
+static int consume_host(kmgpu_t* h, const char* seqs, const uint64_t* packed, uint64_t packed_words, const uint64_t* offsets, uint64_t n_reads,
+                        uint32_t flags, const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out, uint32_t* newbits_out = nullptr,
+                        uint64_t* n_new_out = nullptr)
 {
-    if (!h) return fail(KMGPU_EINVAL, "null handle");
-    if (n_kmers_out) *n_kmers_out = 0;
-    if (n_reads == 0) return KMGPU_OK;
-    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
     std::lock_guard<std::mutex> g(h->mu);
     CKR(set_device(h->device));
     Pred P;
@@ -1638,11 +1677,12 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
         const uint64_t total = last - first, cap = chunk_bases();
         const uint64_t n_chunks = (total + cap - 1) / cap;
         const uint64_t per_chunk = (((total + n_chunks - 1) / n_chunks) + 31) & ~31ull;
-        const uint64_t part_cap = std::max<uint64_t>(std::min<uint64_t>(env_u64("KMGPU_PART_BASES", 24ull << 20), per_chunk),
-                                                     (per_chunk + kmgpu_sketch::MAX_PARTS - 1) / kmgpu_sketch::MAX_PARTS);
+        // parts start on word boundaries of the stream (packed input is uploaded word-wise)
+        const uint64_t part_cap = (std::max<uint64_t>(std::min<uint64_t>(env_u64("KMGPU_PART_BASES", 24ull << 20), per_chunk),
+                                                      (per_chunk + kmgpu_sketch::MAX_PARTS - 1) / kmgpu_sketch::MAX_PARTS) + 31) & ~31ull;
         const uint64_t worst_pos = per_chunk + (uint64_t)kmgpu_sketch::MAX_PARTS * h->k;
         GroupPlan GP;
-        const bool grouped = worst_pos < (1ull << 31) && plan_group(h, (uint32_t)worst_pos, h->nt > F_MAXT, &GP);
+        const bool grouped = worst_pos < (1ull << 31) && plan_group(h, (uint32_t)worst_pos, h->nt > F_MAXT || h->ft_on, &GP);
         if (env_u64("KMGPU_PARTS", 1) && total > part_cap && worst_pos < (1ull << 31) &&
             (grouped || (h->nt <= F_MAXT && plan_delta(h, dp) && plan_buckets(h, (uint32_t)worst_pos, &BL)))) {
             struct Staged { std::vector<Part> parts; };
@@ -1660,10 +1700,12 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
                     const uint64_t b0 = cuts[pi];
                     const uint64_t b1 = std::min(last, cuts[pi + 1] + (uint64_t)(h->k - 1));
                     ChunkDev cd;
-                    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd, chk, slot, h->copy_stream));
+                    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd, chk, slot, h->copy_stream, packed, packed_words));
                     CK(cudaEventRecord(h->stage[slot].ready, h->copy_stream));
                     out->parts.push_back(Part{make_input(cd), pos, h->stage[slot].ready});
-                    pos += cd.n_pos;
+                    // a position is the base's offset within the chunk: the k-1 positions a part shares with the next one hold
+                    // no k-mer start in this part (the reads are clipped to it), they are the next part's first positions
+                    pos = (uint32_t)(cuts[pi + 1] - c0);
                 }
                 return KMGPU_OK;
             };
@@ -1671,17 +1713,26 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
             for (uint64_t ci = 0; ci < n_chunks; ci++) {
                 if (set[ci & 1].parts.empty()) break;
                 const Between next = [&]() -> int { return ci + 1 < n_chunks ? stage_chunk_parts(ci + 1, &set[(ci + 1) & 1]) : KMGPU_OK; };
+                ChunkResult cr;
                 if (grouped) {
                     uint32_t np = 0;
                     for (const Part& pt : set[ci & 1].parts) np = std::max(np, pt.pos_off + pt.in.n_pos);
                     GroupPlan G;   // the regions are sized for this chunk's positions
                     if (!plan_group(h, np, true, &G)) return fail(KMGPU_ECUDA, "internal: grouped plan changed between chunks");
-                    CKR(ingest_chunk_grouped(h, G, 0, H, set[ci & 1].parts, P, pred, M, &res, next));
+                    CKR(ingest_chunk_grouped(h, G, 0, H, set[ci & 1].parts, P, pred, M, &cr, next));
                 } else {
-                    CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &res, next));
+                    CKR(ingest_chunk_delta(h, dp, 0, H, set[ci & 1].parts, P, pred, M, &cr, next));
+                }
+                res.n_kmers += cr.n_kmers;
+                res.n_new += cr.n_new;
+                if (newbits_out && cr.have_newbits) {
+                    // chunk ci starts on a word of the output (per_chunk is a multiple of 32); its k-1 bases of overlap hold no k-mer start
+                    const uint64_t c0 = ci * per_chunk, c1 = std::min(last - first, c0 + per_chunk);
+                    CK(cudaMemcpy(newbits_out + c0 / 32, h->d_newbits.p, ((c1 - c0 + 31) / 32) * 4, cudaMemcpyDeviceToHost));
                 }
             }
             if (n_kmers_out) *n_kmers_out = res.n_kmers;
+            if (n_new_out) *n_new_out = res.n_new;
             return KMGPU_OK;
         }
     }
@@ -1689,7 +1740,9 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     // as few chunks as the cap allows; nothing can start before chunk 0 has crossed PCIe, so chunk 0 is the short one
     // (half of the others when the cap leaves that freedom) and the copy of chunk i+1 hides behind the ingest of chunk i.
     std::vector<uint64_t> starts(1, 0);
-    {
+    if (packed || newbits_out) {
+        balanced_chunks(last - first, chunk_bases(), starts);   // packed input / per-base result bits: chunks cut on word boundaries
+    } else {
         // one chunk more than a device-resident batch would get as soon as that leaves chunk 0 at most half of the others
         const uint64_t total = last - first, cap = chunk_bases(), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
         bool ramp = false;
@@ -1725,80 +1778,53 @@ extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t*
     ChunkDev cd[2];
     uint64_t b0, b1;
     range(0, &b0, &b1);
-    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd[0], chk, 0, h->copy_stream));
+    CKR(stage_range(h, seqs, offsets, n_reads, b0, b1, flags, &cd[0], chk, 0, h->copy_stream, packed, packed_words));
     CK(cudaEventRecord(h->stage[0].ready, h->copy_stream));
     for (uint64_t i = 0; i < n_chunks; i++) {
         CK(cudaStreamWaitEvent(h->stream, h->stage[i & 1].ready, 0));
-        CKR(ingest_chunk(h, 0, H, make_input(cd[i & 1]), P, pred, M, &res, [&]() -> int {
+        ChunkResult cr;
+        CKR(ingest_chunk(h, 0, H, make_input(cd[i & 1]), P, pred, M, &cr, [&]() -> int {
             if (i + 1 < n_chunks) {
                 int ns = (int)((i + 1) & 1);
                 uint64_t c0, c1;
                 range(i + 1, &c0, &c1);
-                CKR(stage_range(h, seqs, offsets, n_reads, c0, c1, flags, &cd[ns], chk, ns, h->copy_stream));
+                CKR(stage_range(h, seqs, offsets, n_reads, c0, c1, flags, &cd[ns], chk, ns, h->copy_stream, packed, packed_words));
                 CK(cudaEventRecord(h->stage[ns].ready, h->copy_stream));
             }
             return KMGPU_OK;
         }));
+        res.n_kmers += cr.n_kmers;
+        res.n_new += cr.n_new;
+        if (newbits_out && cr.have_newbits)
+            CK(cudaMemcpy(newbits_out + starts[i] / 32, h->d_newbits.p, ((starts[i + 1] - starts[i] + 31) / 32) * 4, cudaMemcpyDeviceToHost));
     }
     if (n_kmers_out) *n_kmers_out = res.n_kmers;
+    if (n_new_out) *n_new_out = res.n_new;
     return KMGPU_OK;
 }
 
-// clipped, chunk-relative offsets of the reads overlapping [b0, b1); r0 is advanced past finished reads
-static void clip_offsets(const uint64_t* offsets, uint64_t n_reads, uint64_t b0, uint64_t b1, uint64_t* r0, std::vector<uint32_t>& out)
+extern "C" int kmgpu_consume_reads(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                                   const kmgpu_band_t* band, const kmgpu_mask_t* mask, uint64_t* n_kmers_out)
 {
-    out.clear();
-    while (*r0 < n_reads && offsets[*r0 + 1] <= b0) (*r0)++;
-    out.push_back(0);
-    for (uint64_t r = *r0; r < n_reads && offsets[r] < b1; r++) {
-        uint64_t e = std::min(offsets[r + 1], b1);
-        out.push_back((uint32_t)(e - b0));
-    }
-    // leading gap (possible only before the first read) and trailing part are covered by the first/last piece
-    if (out.size() == 1) out.push_back((uint32_t)(b1 - b0));
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    return consume_host(h, seqs, nullptr, 0, offsets, n_reads, flags, band, mask, n_kmers_out);
 }
 
-// Packed input is consumed in place: chunk i covers bases [i*cap, i*cap + cap + k-1) of the caller's stream
-// (cap a multiple of 32, so every chunk starts on a word of the caller's buffer).  Reads are clipped to
-// the chunk; a clipped piece inside the k-1 overlap is shorter than k and yields nothing, the piece that
-// continues past it starts exactly at the first k-mer the previous chunk could not hold.
-template <class Fn>
-static int for_each_packed_chunk(kmgpu_sketch* h, const uint64_t* words, uint64_t n_words, const uint64_t* offsets, uint64_t n_reads,
-                                 bool device_src, Fn fn)
+// consume + per-k-mer "was new" bits, for consumers that act on them in stream order (tagging: Hashgraph::consume_sequence_and_tag,
+// src/oxli/hashgraph.cc:200-271, tests the bool of store->test_and_set_bits for every k-mer)
+extern "C" int kmgpu_consume_reads_new(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags, uint32_t* newbits_out,
+                                       uint64_t* n_kmers_out, uint64_t* n_new_out)
 {
-    cudaStream_t st = h->stream;
-    const uint64_t n_bases = offsets[n_reads];
-    std::vector<uint64_t> starts;
-    balanced_chunks(n_bases, chunk_bases(), starts);
-    uint64_t r0 = 0;
-    std::vector<uint32_t> offs;
-    for (size_t ci = 0; ci + 1 < starts.size(); ci++) {
-        const uint64_t b0 = starts[ci];
-        uint64_t b1 = std::min(n_bases, starts[ci + 1] + (uint64_t)(h->k - 1));
-        clip_offsets(offsets, n_reads, b0, b1, &r0, offs);
-        uint32_t n_pos = (uint32_t)(b1 - b0);
-        size_t nw = (size_t)n_tiles(n_pos) * (TILE / 32) + TILE_PAD_WORDS;
-        uint64_t w0 = b0 / 32, w1 = std::min<uint64_t>(n_words, w0 + nw);
-        kmgpu_sketch::Stage& SG = h->stage[0];
-        CKR(SG.words.ensure(nw));
-        if (w1 - w0 < nw) CK(cudaMemsetAsync(SG.words.p + (w1 - w0), 0, (nw - (w1 - w0)) * 8, st));
-        CK(cudaMemcpyAsync(SG.words.p, words + w0, (w1 - w0) * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        CKR(SG.offs.ensure(offs.size()));
-        CKR(SG.h_offs.ensure(offs.size()));
-        memcpy(SG.h_offs.p, offs.data(), offs.size() * 4);
-        CK(cudaMemcpyAsync(SG.offs.p, SG.h_offs.p, offs.size() * 4, cudaMemcpyHostToDevice, st));
-        ChunkDev cd;
-        cd.words = SG.words.p;
-        cd.offs = SG.offs.p;
-        cd.n_reads = (uint32_t)offs.size() - 1;
-        cd.n_pos = n_pos;
-        CKR(SG.tfr.ensure(n_tiles(n_pos) + 1));
-        k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256, 0, st>>>(SG.offs.p, cd.n_reads, n_tiles(n_pos), SG.tfr.p);
-        h->all_launches += 1;
-        cd.tfr = SG.tfr.p;
-        CKR(fn(cd));
-    }
-    return KMGPU_OK;
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_new_out) *n_new_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets || !newbits_out) return fail(KMGPU_EINVAL, "null argument");
+    memset(newbits_out, 0, ((offsets[n_reads] - offsets[0] + 31) / 32) * 4);
+    return consume_host(h, seqs, nullptr, 0, offsets, n_reads, flags, nullptr, nullptr, n_kmers_out, newbits_out, n_new_out);
 }
 
 extern "C" int kmgpu_consume_packed(kmgpu_t* h, const uint64_t* words, uint64_t n_words, const uint64_t* offsets, uint64_t n_reads,
@@ -1809,19 +1835,9 @@ extern "C" int kmgpu_consume_packed(kmgpu_t* h, const uint64_t* words, uint64_t 
     if (n_reads == 0) return KMGPU_OK;
     if (!words || !offsets) return fail(KMGPU_EINVAL, "null input");
     if (n_words * 32 < offsets[n_reads]) return fail(KMGPU_EINVAL, "packed buffer shorter than offsets[n_reads]");
-    std::lock_guard<std::mutex> g(h->mu);
-    CKR(set_device(h->device));
-    Pred P;
-    bool pred;
-    const SketchDev* M;
-    CKR(make_pred(h, band, mask, &P, &pred, &M));
-    HashCfg H{h->hash, h->k};
-    ChunkResult res;
-    CKR(for_each_packed_chunk(h, words, n_words, offsets, n_reads, false, [&](const ChunkDev& cd) {
-        return ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res);
-    }));
-    if (n_kmers_out) *n_kmers_out = res.n_kmers;
-    return KMGPU_OK;
+    if (offsets[0] % 32) return fail(KMGPU_EINVAL, "offsets[0] of a packed buffer must be a multiple of 32 bases");
+    // same pipeline as ASCII input (chunks uploaded in parts on the copy stream while the previous part is grouped), a quarter of the bytes
+    return consume_host(h, nullptr, words, n_words, offsets, n_reads, 0, band, mask, n_kmers_out);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1867,10 +1883,11 @@ extern "C" int kmgpu_batch_create(int device, const char* seqs, const uint64_t* 
             if ((e = cudaMalloc(&d_ascii, n_pos)) != cudaSuccess) { bail(e); break; }
             ascii_cap = n_pos;
         }
-        kmgpu_batch::Piece p{nullptr, nullptr, nullptr, nr, n_pos};
+        kmgpu_batch::Piece p{nullptr, nullptr, nullptr, nr, n_pos, nullptr};
         if ((e = cudaMalloc(&p.words, nw * 8)) != cudaSuccess) { bail(e); break; }
         if ((e = cudaMalloc(&p.offs, (nr + 1) * 4)) != cudaSuccess) { cudaFree(p.words); bail(e); break; }
         if ((e = cudaMalloc(&p.tfr, (n_tiles(n_pos) + 1) * 4)) != cudaSuccess) { cudaFree(p.words); cudaFree(p.offs); bail(e); break; }
+        if ((e = cudaMalloc(&p.valid, ((size_t)n_pos / 32 + 2) * 4)) != cudaSuccess) { cudaFree(p.words); cudaFree(p.offs); cudaFree(p.tfr); bail(e); break; }
         b->pieces.push_back(p);
         b->bytes += nw * 8 + (nr + 1) * 4 + (n_tiles(n_pos) + 1) * 4;
         if (n_pos && (e = cudaMemcpy(d_ascii, seqs + c.base0, n_pos, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e); break; }
@@ -1878,6 +1895,8 @@ extern "C" int kmgpu_batch_create(int device, const char* seqs, const uint64_t* 
         cudaMemset(d_ctrl, 0, sizeof(Ctrl));
         k_pack<<<(unsigned)((nw + 255) / 256), 256>>>(d_ascii, n_pos, (flags & KMGPU_CLEAN) ? 1 : 0, p.words, (uint32_t)nw, d_ctrl);
         k_tile_index<<<(n_tiles(n_pos) + 1 + 255) / 256, 256>>>(p.offs, nr, n_tiles(n_pos), p.tfr);
+        cudaMemset(p.valid, 0, ((size_t)n_pos / 32 + 2) * 4);
+        if (nr) k_valid_bits<<<(nr + 255) / 256, 256>>>(p.offs, nr, ksize, p.valid);
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e); break; }
     }
     if (d_ascii) cudaFree(d_ascii);
@@ -1898,6 +1917,7 @@ extern "C" int kmgpu_batch_destroy(kmgpu_batch_t* b)
         if (p.words) cudaFree(p.words);
         if (p.offs) cudaFree(p.offs);
         if (p.tfr) cudaFree(p.tfr);
+        if (p.valid) cudaFree(p.valid);
     }
     delete b;
     return KMGPU_OK;
@@ -1932,6 +1952,7 @@ extern "C" int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmg
         cd.words = p.words;
         cd.offs = p.offs;
         cd.tfr = p.tfr;
+        cd.valid = p.valid;
         cd.n_reads = p.n_reads;
         cd.n_pos = p.n_pos;
         CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));
@@ -2170,13 +2191,21 @@ extern "C" int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, 
         if (cd.n_pos == 0) continue;
         ChunkResult res;
         Input in = make_input(cd);
-        CKR(ingest_chunk(t, 0, H, in, P, false, nullptr, &res));
-        if (!res.have_newbits || res.n_new == 0) continue;
+        t->ft_defer = t->ft_on;   // first-touch log: the entries of this chunk carry the k-mers' counts, known below
+        int rc = ingest_chunk(t, 0, H, in, P, false, nullptr, &res);
+        t->ft_defer = false;
+        CKR(rc);
+        const std::vector<Part> one(1, Part{in, 0u, nullptr});
+        if (!res.have_newbits || res.n_new == 0) {
+            if (t->ft_on) CKR(ft_emit(t, 0, H, one, nullptr));
+            continue;
+        }
         CKR(t->d_counts.ensure(cd.n_pos));
         launch_counts(0, counts->dev, H, in, counts->big_keys.p, counts->big_vals.p, nb, t->d_counts.p, nullptr, t->d_newbits.p, st);
         k_hist<<<148 * 4, 256, 0, st>>>(t->d_counts.p, t->d_newbits.p, cd.n_pos, t->d_hist.p);
         t->all_launches += 2;
         CK(cudaGetLastError());
+        if (t->ft_on) CKR(ft_emit(t, 0, H, one, t->d_counts.p));
     }
     std::vector<unsigned long long> hh(65536);
     CK(cudaMemcpyAsync(hh.data(), t->d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
@@ -2212,7 +2241,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     const HashCfg H{h->hash, h->k};
     const int N = h->nt;
     const uint32_t cap_c = h->kind == BYTE ? 255u : h->kind == NIBBLE ? 15u : 1u;
-    const uint64_t W = std::max<uint64_t>(2, env_u64("KMGPU_NORM_WINDOW", 65536));
+    // reads per window: fixed by KMGPU_NORM_WINDOW, else adapted so that only a small share of a window's bundles is "in between"
+    // (their number grows with the coverage a window adds; they are resolved one by one on the host)
+    const uint64_t W_fixed = env_u64("KMGPU_NORM_WINDOW", 0);
+    uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 4096;
     const uint64_t max_bases = chunk_bases() / 2;
     Pred P0;
     memset(&P0, 0, sizeof P0);
@@ -2320,6 +2352,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                     r = e;
                 }
                 keep = sure;
+                if (!W_fixed) {
+                    if (n_unsure * 50 > nr) W = std::max<uint64_t>(256, W / 2);          // more than 2 % in between: smaller windows
+                    else if (n_unsure * 200 < nr) W = std::min<uint64_t>(1u << 17, W * 2);   // under 0.5 %: larger ones
+                }
                 if (n_unsure) {
                     // 3. in-between bundles, in stream order: the state each of them meets is the window's start + the reads kept
                     //    for good before it + the in-between bundles kept before it
@@ -2335,7 +2371,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                     const uint32_t n_up = (uint32_t)upos.size();
                     std::vector<uint64_t> ubins((size_t)n_up * N);
                     std::vector<uint16_t> uc0((size_t)n_up * N);
-                    std::unordered_map<uint64_t, std::vector<uint32_t>> hits;
+                    std::vector<std::pair<uint64_t, uint32_t>> hits;   // (key, position) of touches by the reads kept for good, sorted
                     if (n_up) {
                         CKR(h->d_upos.ensure(n_up));
                         CKR(h->d_ubins.ensure((size_t)n_up * N));
@@ -2382,10 +2418,28 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                             CK(cudaMemcpyAsync(hp.data(), h->d_hitpos.p, n_hits * 4, cudaMemcpyDeviceToHost, st));
                         }
                         CK(cudaStreamSynchronize(st));
-                        for (uint64_t i = 0; i < n_hits; i++) hits[hk[i]].push_back(hp[i]);
-                        for (auto& kv : hits) std::sort(kv.second.begin(), kv.second.end());
+                        hits.resize(n_hits);
+                        for (uint64_t i = 0; i < n_hits; i++) hits[i] = std::make_pair(hk[i], hp[i]);
+                        std::sort(hits.begin(), hits.end());
                     }
-                    std::unordered_map<uint64_t, uint32_t> extra;   // touches by the in-between bundles kept so far
+                    // flat tables over the distinct (table, bin) keys of the in-between reads: index of every record's key, the
+                    // key's range in `hits`, and the touches added by the in-between bundles kept so far
+                    std::vector<uint64_t> ukeys((size_t)n_up * N);
+                    for (size_t u = 0; u < (size_t)n_up; u++)
+                        for (int t = 0; t < N; t++) ukeys[u * N + t] = (ubins[u * N + t] << 8) | (uint64_t)t;
+                    std::vector<uint64_t> dkeys(ukeys);
+                    std::sort(dkeys.begin(), dkeys.end());
+                    dkeys.erase(std::unique(dkeys.begin(), dkeys.end()), dkeys.end());
+                    std::vector<uint32_t> uidx(ukeys.size());
+                    for (size_t i = 0; i < ukeys.size(); i++) uidx[i] = (uint32_t)(std::lower_bound(dkeys.begin(), dkeys.end(), ukeys[i]) - dkeys.begin());
+                    std::vector<uint32_t> hit_lo(dkeys.size(), 0), extra(dkeys.size(), 0);
+                    {
+                        size_t hi = 0;   // both lists are sorted by key: one merge pass finds where every key's hits start
+                        for (size_t d = 0; d < dkeys.size(); d++) {
+                            while (hi < hits.size() && hits[hi].first < dkeys[d]) hi++;
+                            hit_lo[d] = (uint32_t)hi;
+                        }
+                    }
                     size_t up_at = 0;
                     for (uint32_t r = 0; r < nr;) {
                         const uint32_t e = bundle_end(r);
@@ -2401,12 +2455,12 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                             for (uint32_t i = 0; i < nk; i++, up_at++) {
                                 uint32_t mn = cap_c;
                                 for (int t = 0; t < N; t++) {
-                                    const uint64_t key = (ubins[up_at * N + t] << 8) | (uint64_t)t;
-                                    uint64_t v = uc0[up_at * N + t];
-                                    auto hi = hits.find(key);
-                                    if (hi != hits.end()) v += (uint64_t)(std::lower_bound(hi->second.begin(), hi->second.end(), bundle_start) - hi->second.begin());
-                                    auto ei = extra.find(key);
-                                    if (ei != extra.end()) v += ei->second;
+                                    const uint32_t d = uidx[up_at * N + t];
+                                    uint64_t v = uc0[up_at * N + t] + extra[d];
+                                    // touches of this bin by the reads kept for good that come before this bundle
+                                    size_t a = hit_lo[d], b2 = a;
+                                    while (b2 < hits.size() && hits[b2].first == dkeys[d] && hits[b2].second < bundle_start) b2++;
+                                    v += b2 - a;
                                     if (v < mn) mn = (uint32_t)v;
                                 }
                                 n_ge += mn >= cutoff;
@@ -2416,7 +2470,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                         if (below) {
                             for (uint32_t q = r; q < e; q++) keep[q] = 1;
                             for (size_t u = up_begin; u < up_at; u++)
-                                for (int t = 0; t < N; t++) extra[(ubins[u * N + t] << 8) | (uint64_t)t] += 1;
+                                for (int t = 0; t < N; t++) extra[uidx[u * N + t]] += 1;
                         }
                         r = e;
                     }
@@ -2529,7 +2583,7 @@ extern "C" int kmgpu_ipc_export(kmgpu_t* h, uint8_t* handles)
 extern "C" int kmgpu_ipc_attach(kmgpu_t* h, int rank, int world, const uint8_t* all_handles)
 {
     if (!h || !all_handles) return fail(KMGPU_EINVAL, "null argument");
-    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d", rank, world);
     kmgpu_ipc_detach(h);
     std::lock_guard<std::mutex> g(h->mu);
     CKR(set_device(h->device));
@@ -2597,11 +2651,15 @@ static int reduce_scatter_locked(kmgpu_sketch* h)
         if (w1 <= w0) continue;
         PeerPtrs pp;
         pp.n = 0;
-        for (int q = 0; q < h->world; q++)
+        for (int q = 0; q < h->world; q++) {   // eight peers per pass
             if (q != h->rank) pp.p[pp.n++] = reinterpret_cast<const uint32_t*>(h->peers[q].tables[i]);
-        unsigned g = (unsigned)std::min<uint64_t>((w1 - w0 + 255) / 256, 148 * 16);
-        k_merge_peers<<<g, 256, 0, h->stream>>>(h->kind, reinterpret_cast<uint32_t*>(h->dev.tables[i]), pp, w0, w1);
-        h->all_launches += 1;
+            if (pp.n == 8 || (q == h->world - 1 && pp.n)) {
+                unsigned g = (unsigned)std::min<uint64_t>((w1 - w0 + 255) / 256, 148 * 16);
+                k_merge_peers<<<g, 256, 0, h->stream>>>(h->kind, reinterpret_cast<uint32_t*>(h->dev.tables[i]), pp, w0, w1);
+                h->all_launches += 1;
+                pp.n = 0;
+            }
+        }
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -2631,6 +2689,9 @@ extern "C" int kmgpu_reduce_scatter_peers(kmgpu_t* h)
     if (!h) return fail(KMGPU_EINVAL, "null handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (h->peers.empty()) return fail(KMGPU_EINVAL, "no peers attached");
+    if (h->kind == BYTE && h->use_bigcount)
+        return fail(KMGPU_EUNSUPPORTED, "replicas cannot be merged with bigcount on: which replica saw a counter's 255th touch is not "
+                                        "recoverable (turn bigcount off, or shard the sketch by address)");
     return reduce_scatter_locked(h);
 }
 
@@ -2642,13 +2703,14 @@ extern "C" int kmgpu_all_gather_peers(kmgpu_t* h)
     return all_gather_locked(h);
 }
 
-extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
+extern "C" int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64_t* n_local_out, uint64_t* hist);
+
+// single-process peers: direct pointers, peer access enabled pairwise; rank r = reps[r]
+extern "C" int kmgpu_attach_replicas(kmgpu_t** reps, int n)
 {
-    if (!reps || n < 1 || n > 8) return fail(KMGPU_EINVAL, "bad replica list");
+    if (!reps || n < 1 || n > MAX_WORLD) return fail(KMGPU_EINVAL, "bad replica list");
     for (int r = 1; r < n; r++)
         if (!same_shape(reps[0], reps[r])) return fail(KMGPU_ESHAPE, "replicas must have the same shape");
-    if (n == 1) return KMGPU_OK;
-    // same-process peers: direct pointers, peer access enabled pairwise
     for (int a = 0; a < n; a++) {
         CKR(set_device(reps[a]->device));
         for (int b = 0; b < n; b++) {
@@ -2673,8 +2735,31 @@ extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
             for (int i = 0; i < reps[r]->nt; i++) reps[r]->peers[q].tables[i] = reps[q]->dev.tables[i];
         reps[r]->peers_ipc = false;
     }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
+{
+    if (!reps || n < 1 || n > MAX_WORLD) return fail(KMGPU_EINVAL, "bad replica list");
+    if (n == 1) return KMGPU_OK;
+    CKR(kmgpu_attach_replicas(reps, n));
+    // exact n_unique_kmers across the replicas (first-touch logs on): resolved before any table changes
+    bool ft = true;
+    for (int r = 0; r < n; r++) ft = ft && reps[r]->ft_on;
+    uint64_t unique_total = 0;
+    if (ft) {
+        unique_total = reps[0]->n_unique - reps[0]->ft_epoch_unique;   // the common state the epoch started from
+        for (int r = 0; r < n; r++) {
+            uint64_t n_new = 0;
+            CKR(kmgpu_first_touch_resolve(reps[r], &n_new, nullptr, nullptr));
+            unique_total += n_new;
+        }
+    }
     for (int r = 0; r < n; r++) {
         std::lock_guard<std::mutex> g(reps[r]->mu);
+        if (reps[r]->kind == BYTE && reps[r]->use_bigcount)
+            return fail(KMGPU_EUNSUPPORTED, "replicas cannot be merged with bigcount on: which replica saw a counter's 255th touch is not "
+                                            "recoverable (turn bigcount off, or shard the sketch by address)");
         CKR(reduce_scatter_locked(reps[r]));
     }
     for (int r = 0; r < n; r++) {
@@ -2686,7 +2771,91 @@ extern "C" int kmgpu_reduce_replicas(kmgpu_t** reps, int n)
         reps[r]->peers.clear();
         reps[r]->rank = 0;
         reps[r]->world = 1;
+        if (ft) reps[r]->n_unique = unique_total;
     }
+    return KMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// multi-GPU, replicated: exact n_unique_kmers / abundance_distribution across ranks (first-touch log, kmgpu_group.cuh §6)
+// ------------------------------------------------------------------------------------------------------
+static void ft_clear(kmgpu_sketch* h)
+{
+    for (auto& sg : h->ft_segs) cudaFree(sg.first);
+    h->ft_segs.clear();
+    h->ft_pending = 0;
+    h->ft_epoch_unique = 0;
+    h->ft_chunk = 0;
+}
+
+extern "C" int kmgpu_first_touch_log(kmgpu_t* h, int on)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    ft_clear(h);
+    h->ft_on = on != 0;
+    h->ft_defer = false;
+    return KMGPU_OK;
+}
+
+// Rank r of an attached replica group (kmgpu_ipc_attach / kmgpu_reduce_replicas): how many k-mer occurrences logged since the
+// log was switched on (or last resolved) are new in the stream order "rank 0's reads, then rank 1's, ..." — to be called on
+// every rank after all ranks have finished ingesting and BEFORE any table is merged.  hist (nullable, 65536 entries) is
+// accumulated with the counts the entries carry (abundance_distribution).  The log is emptied.
+extern "C" int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64_t* n_local_out, uint64_t* hist)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->ft_on) return fail(KMGPU_EINVAL, "the first-touch log of this sketch is off");
+    if (h->world > 1 && h->peers.empty()) return fail(KMGPU_EINVAL, "no peers attached");
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    uint64_t total = 0;
+    for (auto& sg : h->ft_segs) total += sg.second;
+    if (n_local_out) *n_local_out = h->ft_epoch_unique;
+    uint64_t n_new = 0;
+    if (total) {
+        LowerRanks lr;
+        memset(&lr, 0, sizeof lr);
+        lr.n = h->world > 1 ? h->rank : 0;
+        for (int q = 0; q < lr.n; q++)
+            for (int i = 0; i < h->nt; i++) lr.tables[q][i] = h->peers[q].tables[i];
+        LowerRanks* d_lr = nullptr;
+        CK(cudaMalloc(&d_lr, sizeof lr));
+        CK(cudaMemcpyAsync(d_lr, &lr, sizeof lr, cudaMemcpyHostToDevice, st));
+        const uint64_t slots = pow2_at_least(2 * std::max<uint64_t>(h->ft_epoch_unique, 1));
+        CKR(h->d_evkeys.ensure(slots));
+        CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, slots * 8, st));
+        CK(cudaMemsetAsync(&h->d_ctrl->n_unique, 0, sizeof(unsigned long long), st));
+        unsigned long long* d_hist = nullptr;
+        if (hist) {
+            CKR(h->d_hist.ensure(65536));
+            CK(cudaMemsetAsync(h->d_hist.p, 0, 65536 * 8, st));
+            d_hist = h->d_hist.p;
+        }
+        for (auto& sg : h->ft_segs) {
+            const unsigned gsz = (unsigned)std::min<uint64_t>((sg.second + 255) / 256, 148 * 16);
+            const FtEntry* ent = (const FtEntry*)sg.first;
+            if (h->kind == BYTE) k_ft_resolve<BYTE><<<gsz, 256, 0, st>>>(ent, sg.second, d_lr, h->d_evkeys.p, slots - 1, &h->d_ctrl->n_unique, d_hist);
+            else if (h->kind == NIBBLE) k_ft_resolve<NIBBLE><<<gsz, 256, 0, st>>>(ent, sg.second, d_lr, h->d_evkeys.p, slots - 1, &h->d_ctrl->n_unique, d_hist);
+            else k_ft_resolve<BIT><<<gsz, 256, 0, st>>>(ent, sg.second, d_lr, h->d_evkeys.p, slots - 1, &h->d_ctrl->n_unique, d_hist);
+            h->all_launches += 1;
+        }
+        CK(cudaGetLastError());
+        int rc = read_ctrl(h);
+        cudaFree(d_lr);
+        CKR(rc);
+        n_new = h->h_ctrl->n_unique;
+        if (hist) {
+            std::vector<unsigned long long> hh(65536);
+            CK(cudaMemcpy(hh.data(), h->d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 65536; i++) hist[i] += hh[i];
+        }
+    }
+    if (n_new_out) *n_new_out = n_new;
+    ft_clear(h);
     return KMGPU_OK;
 }
 
@@ -2733,7 +2902,7 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
     if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world) return fail(KMGPU_EINVAL, "bad rank/world %d/%d (at most %d ranks)", rank, world, MAX_WORLD);
     if (n_tables < 1 || n_tables > MAX_TABLES) return fail(KMGPU_EUNSUPPORTED, "n_tables %d not supported", n_tables);
     if (max_positions == 0) max_positions = 8ull << 20;
-    max_positions = ((max_positions + 31) / 32) * 32;
+    max_positions = ((max_positions + 127) / 128) * 128;   // every rank's range of the new-position bitmaps starts on 16 bytes
     if (max_positions > chunk_bases() || (uint64_t)world * max_positions >= (1ull << 32))
         return fail(KMGPU_EINVAL, "max_positions %llu too large (positions of a round are 32-bit across all ranks)", (unsigned long long)max_positions);
     kmgpu_shard* s = new kmgpu_shard();
@@ -2959,8 +3128,8 @@ extern "C" int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint6
     Pred P0;
     memset(&P0, 0, sizeof P0);
     const dim3 grid((in.n_pos + 8191) / 8192, s->nt);
-    if (srck) CKR((launch_part_inst<8192, 512, 3, 1, false, false>(grid, st, A, s->full, P0, R)));
-    else CKR((launch_part_inst<8192, 512, 3, 0, false, false>(grid, st, A, s->full, P0, R)));
+    if (srck) CKR((launch_part_inst<8192, 512, 3, 1, false, false, 12>(grid, st, A, s->full, P0, R)));
+    else CKR((launch_part_inst<8192, 512, 3, 0, false, false, 12>(grid, st, A, s->full, P0, R)));
     h->all_launches += 1;
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());

@@ -49,6 +49,10 @@ struct Store {
     uint32_t* cursor;                // records written to (demanded of) every partition (indexed by p)
     uint32_t cap;
     uint32_t p0;                     // first partition held (tables are grouped in turns when memory is short)
+    // sub-region layout (k_part_p): the region of partition p is cut into `subs` equal sub-regions of subcap = cap / subs records,
+    // one per persistent grouping CTA, filled independently (fill[(p - p0) * subs + c] records in sub-region c) — no cursor atomics
+    const uint16_t* fill;
+    uint32_t subs, subcap;
     __device__ __forceinline__ unsigned long long base(uint32_t p) const { return off ? off[p - p0] : (unsigned long long)(p - p0) * cap; }
     __device__ __forceinline__ uint32_t room(uint32_t p) const { return off ? (uint32_t)(off[p - p0 + 1] - off[p - p0]) : cap; }
 };
@@ -153,13 +157,21 @@ template <int T, int NTHR, int SRC>
 __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t t0, int have_valid, PartTile<T>& sm)
 {
     const int tid = threadIdx.x;
-    for (int i = tid; i < T / 32; i += NTHR) sm.valid[i] = 0;
+    const bool pre = in.valid != nullptr && in.read_keep == nullptr && !(SRC == 1 && !have_valid);
+    if (pre) {
+        // the bitmap was computed when the chunk was staged: one more independent load next to the stream words
+        const uint32_t vw = (in.n_pos + 31) >> 5, v0 = t0 >> 5;
+        for (int i = tid; i < T / 32; i += NTHR) sm.valid[i] = v0 + i < vw ? __ldg(in.valid + v0 + i) : 0u;
+    } else {
+        for (int i = tid; i < T / 32; i += NTHR) sm.valid[i] = 0;
+    }
     if (SRC == 0) {
         const uint32_t total_words = ((in.n_pos + TILE - 1) / TILE) * (TILE / 32) + TILE_PAD_WORDS;
         const uint32_t w0 = t0 >> 5;
         for (int i = tid; i < T / 32 + TILE_PAD_WORDS; i += NTHR) sm.words[i] = w0 + i < total_words ? __ldg(in.words + w0 + i) : 0ull;
     }
     __syncthreads();
+    if (pre) return;
     if (SRC == 1 && !have_valid) {
         const uint32_t n = in.n_pos - t0 < (uint32_t)T ? in.n_pos - t0 : (uint32_t)T;
         for (int i = tid; i < T / 32; i += NTHR) {
@@ -194,13 +206,14 @@ __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t
     __syncthreads();
 }
 
-template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP>
+// BPT: consecutive partitions per thread in the scan; the launch picks the smallest instantiation with BPT * NTHR >= the
+// number of partitions, so that every thread has a share (and no registers are held for partitions that do not exist)
+template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP, int BPT>
 __global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || MODE == 3 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
 k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P, const __grid_constant__ ShardRoute R)
 {
     constexpr bool WIDE = MODE == 1 || MODE == 3 || WIDEP;
     constexpr int PER = T / NTHR;
-    constexpr int BPT = (PART_MAXP + NTHR - 1) / NTHR;
     constexpr bool SBMODE = MODE == 1 || MODE == 3;            // partitions are super-buckets
     constexpr int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;      // payload bits of the records written
     extern __shared__ __align__(16) unsigned char pt_raw[];
@@ -209,7 +222,6 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     uint32_t* gb32 = hist + PART_MAXP;                                        // WIDE only: 32-bit cursor bases
     PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(hist + PART_MAXP * (WIDE ? 2 : 1));
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
     const uint32_t tid = threadIdx.x;
     const uint32_t p0 = (MODE == 2 ? blockIdx.x % A.tiles_per_src : blockIdx.x) * (uint32_t)T;
 
@@ -331,18 +343,15 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     }
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t v = lane < NTHR / 32 ? s_warp[lane] : 0, w = v;
+    // every warp adds up the totals of the warps before it itself (NTHR / 32 broadcast reads): no second barrier
+    uint32_t before = 0, total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= (uint32_t)o) w += u;
-        }
-        s_warp[lane] = w - v;
-        if (lane == 31) s_total = w;
+    for (int w = 0; w < NTHR / 32; w++) {
+        const uint32_t v = s_warp[w];
+        before += (uint32_t)w < wid ? v : 0u;
+        total += v;
     }
-    __syncthreads();
-    uint32_t at = s_warp[wid] + incl - mine, gbase[BPT];
+    uint32_t at = before + incl - mine, gbase[BPT];
 #pragma unroll
     for (int q = 0; q < BPT; q++) {
         const uint32_t b = tid * BPT + q;
@@ -389,7 +398,6 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     __syncthreads();
 
     // ---- phase 4: runs of consecutive records leave for their regions ---------------------------------------------------
-    const uint32_t total = s_total;
     bool over = false;
     for (uint32_t s = tid; s < total; s += NTHR) {
         const uint2 m = stage[s];
@@ -410,6 +418,131 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         }
     }
     if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
+}
+
+// =====================================================================================================================
+// 1b. k_part_p: MODE 0 as a PERSISTENT kernel without cursor atomics.  grid = (G, tables): CTA (c, t) groups tiles c, c + G, ...
+//     of table t and owns sub-region c of every bucket of that table (Store::subs == G), so a run's place is known from a
+//     cursor the CTA keeps in shared memory — the one global atomicAdd per (tile, non-empty bucket) of k_part (a third of a
+//     chunk's grouping time, and a barrier's worth of latency per tile) is gone.  The cursors live in `fill` between launches
+//     (host input arrives in parts, one launch each).  A sub-region that runs out of room reports overflow like any region;
+//     the chunk is then regrouped by k_part with exact offsets.
+// =====================================================================================================================
+template <int T, int NTHR, int SRC, bool PRED, int BPT>
+__global__ void __launch_bounds__(NTHR, (2 * (part_smem(T, false) + PART_MAXP * 2) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
+k_part_p(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P, uint16_t* __restrict__ fill)
+{
+    constexpr int PER = T / NTHR;
+    extern __shared__ __align__(16) unsigned char pt_raw[];
+    uint2* stage = reinterpret_cast<uint2*>(pt_raw);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // count, then run start | sub-region cursor << 16
+    uint16_t* lcur = reinterpret_cast<uint16_t*>(hist + PART_MAXP);           // this CTA's cursor in its sub-region of every bucket
+    PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(lcur + PART_MAXP);
+    __shared__ uint32_t s_warp[32];
+    const uint32_t tid = threadIdx.x;
+    const int t = A.table0 + blockIdx.y;
+    const uint32_t np = A.L.first[t + 1] - A.L.first[t], cur0 = A.L.first[t];
+    const uint32_t G = A.dst.subs, cta = blockIdx.x, subcap = A.dst.subcap;   // gridDim.x <= G CTAs run (fewer when the part is short)
+    const uint64_t size = A.S.sizes[t], magic = A.S.magic[t];
+    for (uint32_t b = tid; b < np; b += NTHR) lcur[b] = fill[(size_t)(cur0 - A.dst.p0 + b) * G + cta];
+    unsigned n_k = 0;
+    bool over = false;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    for (uint32_t p0 = cta * (uint32_t)T; p0 < A.in.n_pos; p0 += gridDim.x * (uint32_t)T) {
+        uint32_t key[PER], rk[(PER + 1) / 2];
+        for (uint32_t i = tid; i < np; i += NTHR) hist[i] = 0;
+        part_tile_begin<T, NTHR, SRC>(A.in, A.H.k, p0, A.have_valid, tile);   // ends with __syncthreads()
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const uint32_t lp = j * NTHR + tid;
+            key[j] = NONE;
+            if (p0 + lp < A.in.n_pos && ((tile.valid[lp >> 5] >> (lp & 31)) & 1u)) {
+                const uint64_t h = SRC == 1 ? __ldcs(A.in.hashes + p0 + lp) : hash_twobit(tile.words, lp, A.H.k);
+                if (!PRED || pred_pass(P, M, h)) {
+                    key[j] = (uint32_t)mod_magic(h, size, magic);
+                    n_k++;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            uint32_t r = 0;
+            if (key[j] != NONE) r = atomicAdd(&hist[key[j] >> BKT_SHIFT], 1u);
+            if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
+        }
+        __syncthreads();
+        uint32_t c[BPT], mine = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const uint32_t b = tid * BPT + q;
+            c[q] = b < np ? hist[b] : 0;
+            mine += c[q];
+        }
+        uint32_t incl = mine;
+        const uint32_t lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NTHR / 32; w++) {
+            const uint32_t v = s_warp[w];
+            before += (uint32_t)w < wid ? v : 0u;
+            total += v;
+        }
+        uint32_t at = before + incl - mine;
+#pragma unroll
+        for (int q = 0; q < BPT; q++) {
+            const uint32_t b = tid * BPT + q;
+            if (b < np) {
+                const uint32_t base = lcur[b];
+                hist[b] = at | (base << 16);                 // run start, and where the run goes in this CTA's sub-region
+                const uint32_t nb = base + c[q];
+                lcur[b] = (uint16_t)(nb > 0xFFFFu ? 0xFFFFu : nb);   // keeps counting the demand (a full sub-region is reported below)
+                over |= nb > subcap;
+            }
+            at += c[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            if (key[j] == NONE) continue;
+            const uint32_t pid = key[j] >> BKT_SHIFT;
+            const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
+            stage[(hist[pid] & 0xFFFFu) + r] = make_uint2(key[j] & (BKT_BINS - 1), (pid << 14) | (uint32_t)(j * NTHR + tid));
+        }
+        __syncthreads();
+        for (uint32_t s = tid; s < total; s += NTHR) {
+            const uint2 m = stage[s];
+            const uint32_t pid = m.y >> 14;
+            const uint32_t hv = hist[pid];
+            const uint32_t idx = (hv >> 16) + (s - (hv & 0xFFFFu));
+            if (idx < subcap)
+                A.dst.rec[((unsigned long long)(cur0 - A.dst.p0 + pid) * G + cta) * subcap + idx] =
+                    ((unsigned long long)(A.pos_base + p0 + (m.y & 0x3FFFu)) << BKT_SHIFT) | m.x;
+        }
+        __syncthreads();   // hist and the tile buffers are reused by the next tile
+    }
+    for (uint32_t b = tid; b < np; b += NTHR) fill[(size_t)(cur0 - A.dst.p0 + b) * G + cta] = lcur[b];
+    if (t == 0 && A.count_kmers) {
+        n_k = __reduce_add_sync(0xffffffffu, n_k);
+        if ((tid & 31) == 0 && n_k) atomicAdd(&A.ctrl->n_kmers, (unsigned long long)n_k);
+    }
+    if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
+}
+
+// demand of every bucket = the sum of its sub-region cursors (for a regrouping run after k_part_p reported overflow)
+__global__ void k_fill_sums(const uint16_t* __restrict__ fill, uint32_t n_buckets, uint32_t G, uint32_t* __restrict__ cursor)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t sum = 0;
+    for (uint32_t c = 0; c < G; c++) sum += fill[(size_t)b * G + c];
+    cursor[b] = sum;
 }
 
 // 64-bit hashes of every position (Murmur): one pass, then k_part<SRC 1> per table
@@ -478,7 +611,7 @@ template <int KIND>
 __global__ void __launch_bounds__(1024, 1)
 k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
          uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
-         unsigned long long ovf_mask)
+         unsigned long long ovf_mask, uint32_t* __restrict__ newmask)
 {
     extern __shared__ __align__(128) unsigned char ap_raw[];
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // BKT_BINS / 2 words, two 16-bit lanes each
@@ -487,14 +620,40 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     uint64_t* bar = reinterpret_cast<uint64_t*>(slice + slice_bytes_full<KIND>());
     if (ctrl->overflow & ovf_mask) return;      // a region of this table group ran out of room: the group is regrouped with exact offsets
     const uint32_t b = bucket0 + blockIdx.x;
-    const uint32_t n = st.cursor[b];
+    const uint32_t tid = threadIdx.x;
+    constexpr int MAX_SUBS = 320;
+    __shared__ uint32_t s_pref[MAX_SUBS + 1];   // sub-region layout: records before sub-region c
+    uint32_t n;
+    if (st.fill) {
+        // the bucket's records lie in `subs` sub-regions (one per grouping CTA): prefix sums of their fills, by warp 0
+        if (tid < 32) {
+            const uint32_t per = (st.subs + 31) / 32, c0 = tid * per;
+            uint32_t sum = 0;
+            for (uint32_t c = c0; c < c0 + per && c < st.subs; c++) sum += st.fill[(size_t)(b - st.p0) * st.subs + c];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= (uint32_t)o) incl += v;
+            }
+            uint32_t at = incl - sum;
+            for (uint32_t c = c0; c < c0 + per && c < st.subs; c++) {
+                s_pref[c] = at;
+                at += st.fill[(size_t)(b - st.p0) * st.subs + c];
+            }
+            if (tid == 31) s_pref[st.subs] = incl;
+        }
+        __syncthreads();
+        n = s_pref[st.subs];
+    } else {
+        n = st.cursor[b];
+    }
     if (n == 0) return;
     int t = 0;
 #pragma unroll 1
     for (int i = 1; i < L.n_tables; i++)
         if (b >= L.first[i]) t = i;
     const uint64_t bin0 = (uint64_t)(b - L.first[t]) << BKT_SHIFT;
-    const uint32_t tid = threadIdx.x;
     const uint64_t size = S.sizes[t];
     int changed = 0;
     uint8_t* table = S.tables[t];
@@ -513,45 +672,77 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     {
         uint4* f = reinterpret_cast<uint4*>(minpos);
         for (uint32_t i = tid; i < BKT_BINS / 4; i += 1024) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (KIND != BIT) {
-            uint4* z = reinterpret_cast<uint4*>(cnt);
-            for (uint32_t i = tid; i < BKT_BINS / 8; i += 1024) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    mbar_wait(bar, 0);
+    constexpr int GPT = BKT_BINS / 8 / 1024;
+    if (KIND != BIT) {
+        // touch lanes start at 0, with bit 15 set for bins that hold a count already: the value atomicAdd returns then tells
+        // every record, at no extra cost, whether its bin was empty before the chunk — only those records can be a new k-mer's
+        // first toucher and pay the atomicMin below
+#pragma unroll
+        for (int q = 0; q < GPT; q++) {
+            const uint32_t g = q * 1024 + tid;
+            uint32_t w[4] = {0, 0, 0, 0};
+            if ((uint64_t)g * (KIND == BYTE ? 8 : 4) < sbytes) {
+                if (KIND == BYTE) {
+                    const uint64_t old64 = *reinterpret_cast<const uint64_t*>(slice + (size_t)g * 8);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w[j >> 1] |= ((old64 >> (8 * j)) & 255u) ? (0x8000u << ((j & 1) * 16)) : 0u;
+                } else {
+                    const uint32_t old32 = *reinterpret_cast<const uint32_t*>(slice + (size_t)g * 4);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) w[j >> 1] |= ((old32 >> ((j >> 1) * 8 + ((j & 1) ? 0 : 4))) & 15u) ? (0x8000u << ((j & 1) * 16)) : 0u;
+                }
+            }
+            reinterpret_cast<uint4*>(cnt)[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
     __syncthreads();
-    mbar_wait(bar, 0);
     const unsigned long long* src = st.rec + st.base(b);
+    const uint32_t sub_avg = st.fill ? (n / st.subs > 0 ? n / st.subs : 1u) : 1u;
     constexpr int RIF = 16;   // records in flight per thread
     for (uint32_t e0 = 0; e0 < n; e0 += RIF * 1024) {
         unsigned long long v[RIF];
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
             uint32_t e = e0 + j * 1024 + tid;
-            v[j] = e < n ? __ldcs(src + e) : ~0ull;
+            if (st.fill && e < n) {
+                // which sub-region holds the e-th record: they are nearly equally full, so the guess e / average is a step or two off
+                uint32_t c = e / sub_avg;
+                if (c >= st.subs) c = st.subs - 1;
+                while (e < s_pref[c]) c--;
+                while (e >= s_pref[c + 1]) c++;
+                v[j] = __ldcs(src + (size_t)c * st.subcap + (e - s_pref[c]));
+            } else {
+                v[j] = e < n ? __ldcs(src + e) : ~0ull;
+            }
         }
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
             if (v[j] == ~0ull) continue;
             const uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
-            if (KIND != BIT) atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
-            // only a bin that was empty before the chunk can make its first toucher a new k-mer
-            if (slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+            if (KIND == BIT) {
+                // a Bloom bit that is set already changes nothing
+                if (slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+            } else {
+                const uint32_t was = atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+                if (!((lb & 1) ? was >> 31 : (was >> 15) & 1u)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+            }
         }
-        if (KIND != BIT && n > 65535u && ((e0 / (RIF * 1024)) & 1u)) {
-            // more records than a 16-bit lane can count: clamp every lane to 0x7FFF after each 32 Ki records (any value
-            // >= the counter's cap saturates it just the same), so the next 32 Ki cannot wrap a lane into its neighbour
+        if (KIND != BIT && n > 32767u) {
+            // more records than a 15-bit lane can count: clamp every lane to 0x3FFF after each 16 Ki records (any value >= the
+            // counter's cap saturates it just the same), so the next 16 Ki cannot carry into the flag bit or the neighbour
             __syncthreads();
             for (uint32_t i = tid; i < BKT_BINS / 2; i += 1024) {
                 const uint32_t w = cnt[i];
-                const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
-                cnt[i] = (lo > 0x7FFFu ? 0x7FFFu : lo) | ((hi > 0x7FFFu ? 0x7FFFu : hi) << 16);
+                const uint32_t lo = w & 0x7FFFu, hi = (w >> 16) & 0x7FFFu;
+                cnt[i] = (w & 0x80008000u) | (lo > 0x3FFFu ? 0x3FFFu : lo) | ((hi > 0x3FFFu ? 0x3FFFu : hi) << 16);
             }
             __syncthreads();
         }
     }
     __syncthreads();
     unsigned n_new = 0, n_sat = 0, n_cross = 0;
-    constexpr int GPT = BKT_BINS / 8 / 1024;
 #pragma unroll
     for (int q = 0; q < GPT; q++) {
         const uint32_t g = q * 1024 + tid;
@@ -568,10 +759,14 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             n_new += __popc(newm);
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if ((newm >> j) & 1u) atomicOr(&newbits[mp[j] >> 5], 1u << (mp[j] & 31));
+                if ((newm >> j) & 1u) {
+                    atomicOr(&newbits[mp[j] >> 5], 1u << (mp[j] & 31));
+                    if (newmask) atomicOr(&newmask[mp[j]], 1u << t);   // first-touch log: which tables made the position new
+                }
             continue;
         }
-        const uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
+        uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
+        c4.x &= 0x7FFF7FFFu; c4.y &= 0x7FFF7FFFu; c4.z &= 0x7FFF7FFFu; c4.w &= 0x7FFF7FFFu;   // touches without the "was occupied" flags
         if (!(c4.x | c4.y | c4.z | c4.w)) continue;
         const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
         unsigned crossm = 0;
@@ -627,6 +822,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             if (!((newm >> j) & 1u)) continue;
             const uint32_t p = minpos[g * 8 + j];
             atomicOr(&newbits[p >> 5], 1u << (p & 31));
+            if (newmask) atomicOr(&newmask[p], 1u << t);
         }
     }
     // the slice goes back in one bulk copy (generic-proxy writes made visible to the async proxy first)
@@ -670,7 +866,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128)
 k_apply_sparse(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
                uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
-               unsigned long long ovf_mask)
+               unsigned long long ovf_mask, uint32_t* __restrict__ newmask)
 {
     extern __shared__ __align__(16) uint32_t sp_raw[];
     if (ctrl->overflow & ovf_mask) return;
@@ -759,6 +955,7 @@ k_apply_sparse(const __grid_constant__ SketchDev S, const __grid_constant__ Grou
             n_new++;
             const uint32_t p = hp[s];
             atomicOr(&newbits[p >> 5], 1u << (p & 31));
+            if (newmask) atomicOr(&newmask[p], 1u << t);
         }
     }
     n_new = __reduce_add_sync(0xffffffffu, n_new);
@@ -914,6 +1111,94 @@ k_norm_hits(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint
                 hit_key[at] = key;
                 hit_pos[at] = t0 + lp;
             }
+        }
+    }
+}
+
+}  // namespace kmgpu
+
+namespace kmgpu {
+
+// =====================================================================================================================
+// 6. First-touch log (replicated sketches): n_unique_kmers and abundance_distribution count a k-mer
+//    occurrence iff one of its bins was empty when it arrived IN STREAM ORDER.  With one replica per rank and the ranks'
+//    read shards taken in rank order, an occurrence on rank r is globally new iff, for some table, it was the first
+//    toucher of an empty bin locally AND no rank below r touched that bin.  Every rank therefore logs, per chunk, one
+//    entry per newly occupied bin: (table, bin), position, chunk — and, for abundance_distribution, the k-mer's count.
+//    At merge time (before any table is modified) rank r drops the entries whose bin is occupied on a lower rank and
+//    counts the distinct positions that are left.
+// =====================================================================================================================
+struct FtEntry {
+    uint64_t key;      // ht_key(bin, table)
+    uint32_t pos;      // position within its chunk
+    uint16_t chunk;    // chunk number within the epoch (mod 2^16: (chunk, pos) pairs only need to be distinct per position)
+    uint16_t count;    // abundance_distribution: the k-mer's count in the counting sketch
+};
+
+// entries of one chunk: for every position marked new, one entry per table whose bin it occupied (newmask[p])
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_ft_emit(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ newbits, const uint32_t* __restrict__ newmask,
+          uint32_t pos_base, uint32_t chunk, const uint16_t* __restrict__ counts, FtEntry* __restrict__ out, unsigned long long cap,
+          unsigned long long* cursor)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint32_t p = pos_base + t0 + lp;
+        if (!((newbits[p >> 5] >> (p & 31)) & 1u)) continue;
+        uint32_t m = newmask[p];
+        if (!m) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        const uint16_t c = counts ? counts[p] : (uint16_t)0;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            FtEntry e;
+            e.key = ht_key(mod_magic(h, S.sizes[t], S.magic[t]), t);
+            e.pos = p;
+            e.chunk = (uint16_t)chunk;
+            e.count = c;
+            const unsigned long long at = atomicAdd(cursor, 1ull);
+            if (at < cap) out[at] = e;
+        }
+    }
+}
+
+struct LowerRanks {
+    const uint8_t* tables[MAX_WORLD][G_MAXT];   // the tables of the ranks below this one (peer memory)
+    int n;
+};
+
+// entries whose bin no lower rank occupies survive; the distinct (chunk, position) pairs among the survivors are the
+// globally new k-mer occurrences of this rank: counted, and histogrammed by their count
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_ft_resolve(const FtEntry* __restrict__ ent, unsigned long long n, const LowerRanks* __restrict__ lower, unsigned long long* seen, uint64_t mask,
+             unsigned long long* n_new, unsigned long long* hist)
+{
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256ull) {
+        const FtEntry e = ent[i];
+        const int t = (int)(e.key & 255u);
+        const uint64_t bin = e.key >> 8;
+        bool alive = true;
+        for (int q = 0; q < lower->n && alive; q++) alive = read_counter<KIND>(lower->tables[q][t], bin) == 0;
+        if (!alive) continue;
+        const unsigned long long id = ((unsigned long long)e.chunk << 32) | e.pos;
+        uint64_t s = fmix64(id) & mask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&seen[s], ~0ull, id);
+            if (prev == ~0ull) {
+                atomicAdd(n_new, 1ull);
+                if (hist) atomicAdd(&hist[e.count], 1ull);
+                break;
+            }
+            if (prev == id) break;
+            s = (s + 1) & mask;
         }
     }
 }

@@ -39,6 +39,7 @@ struct Input {
     const uint64_t* hashes;  // SRC 1: hash array
     uint32_t n_pos;          // stream positions (bases) or number of hashes
     const uint32_t* read_keep;  // optional: one bit per read of the chunk; reads whose bit is clear yield no k-mers
+    const uint32_t* valid;      // optional: precomputed bitmap of the positions where a k-mer starts (k_valid_bits); ignores read_keep
 };
 
 struct TileSmem {
@@ -162,6 +163,25 @@ __global__ void k_tile_index(const uint32_t* __restrict__ offs, uint32_t n_reads
         if ((uint64_t)offs[mid] <= start) lo = mid; else hi = mid - 1;
     }
     tfr[t] = lo;
+}
+
+// bitmap of the positions where a k-mer starts (start + k <= end of its read), one thread per read; `out` zeroed before.
+// Computed once per staged chunk so that the grouping kernel's CTAs load it instead of rebuilding it from the read offsets
+// (a dependent chain of three global loads per tile and table).
+__global__ void k_valid_bits(const uint32_t* __restrict__ offs, uint32_t n_reads, int k, uint32_t* __restrict__ out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t s = offs[r], e = offs[r + 1];
+    if (e - s < (uint32_t)k) return;
+    const uint32_t a = s, b = e - k;   // inclusive
+    for (uint32_t wd = a >> 5; wd <= (b >> 5); wd++) {
+        const uint32_t lo = wd == (a >> 5) ? (a & 31) : 0;
+        const uint32_t hi = wd == (b >> 5) ? (b & 31) : 31;
+        const uint32_t m = (hi == 31 ? ~0u : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+        if (m == ~0u) out[wd] = m;   // a word wholly inside one read is nobody else's
+        else atomicOr(&out[wd], m);
+    }
 }
 
 // ---- ingest --------------------------------------------------------------------------------------

@@ -723,6 +723,23 @@ void Hashtable::median_at_least_batch(const std::vector<std::string>& seqs, unsi
     if (!seqs.empty()) check(kmgpu_median_at_least(store->handle(), buf.data(), offs.data(), seqs.size(), 0, cutoff, out.data()));
 }
 
+// The loop of scripts/normalize-by-median.py:155-179 (Normalizer.__call__ + ReadBundle.coverages_at_least, khmer/utils.py:178-180)
+// over a batch of cleaned sequences in stream order, resolved on the device: keep[i] = 1 iff read i's bundle was kept (and consumed).
+unsigned long long Hashtable::normalize_batch(const std::vector<std::string>& seqs, unsigned int cutoff, const std::vector<uint8_t>& pair_with_next,
+                                              std::vector<uint8_t>& keep)
+{
+    std::string buf;
+    std::vector<uint64_t> offs;
+    pack_strings(seqs, buf, offs);
+    keep.assign(seqs.size(), 0);
+    if (seqs.empty()) return 0;
+    if (!pair_with_next.empty() && pair_with_next.size() != seqs.size()) throw oxli_value_exception("pair flags: one per read");
+    uint64_t kept = 0, kmers = 0;
+    check(kmgpu_normalize_batch(store->handle(), buf.data(), offs.data(), seqs.size(), 0, pair_with_next.empty() ? nullptr : pair_with_next.data(), cutoff,
+                                keep.data(), &kept, &kmers));
+    return kmers;
+}
+
 BoundedCounterType Hashtable::get_min_count(const std::string& s)
 {
     std::vector<BoundedCounterType> counts;
@@ -823,7 +840,11 @@ void Hashtable::bulk_consume(ReadParserPtr<SeqIO>& parser, const uint64_t* band,
         m.consume_masked = consume_masked ? 1 : 0;
     }
     // two pinned batches: the next one is parsed (by the reader's threads) while the device ingests the current one
+    // the parser threads clean and 2-bit pack the reads as they copy them (KMGPU_FEED_PACKED=0: ASCII batches, cleaned and
+    // packed on the device)
+    static const bool packed = [] { const char* e = getenv("KMGPU_FEED_PACKED"); return !(e && *e == '0'); }();
     ReadBatch batch[2];
+    batch[0].pack = batch[1].pack = packed;
     auto fetch = [&](int slot) -> size_t {
         batch[slot].clear();
         return parser->io().read_batch(feed_bases(), batch[slot]);
@@ -833,8 +854,10 @@ void Hashtable::bulk_consume(ReadParserPtr<SeqIO>& parser, const uint64_t* band,
     while (got) {
         std::future<size_t> next = std::async(std::launch::async, fetch, cur ^ 1);
         uint64_t n = 0;
-        int rc = kmgpu_consume_reads(store->handle(), batch[cur].seqs, batch[cur].offsets.data(), got, KMGPU_CLEAN, band ? &b : nullptr,
-                                     mask ? &m : nullptr, &n);
+        int rc = packed ? kmgpu_consume_packed(store->handle(), batch[cur].words(), batch[cur].n_words(), batch[cur].offsets.data(), got,
+                                               band ? &b : nullptr, mask ? &m : nullptr, &n)
+                        : kmgpu_consume_reads(store->handle(), batch[cur].seqs, batch[cur].offsets.data(), got, KMGPU_CLEAN, band ? &b : nullptr,
+                                              mask ? &m : nullptr, &n);
         __sync_add_and_fetch(&n_consumed, n);
         __sync_add_and_fetch(&total_reads, (unsigned int)got);
         size_t got_next = 0;

@@ -99,10 +99,16 @@ typedef std::pair<Read, Read> ReadPair;
 // memory obtained through the C ABI (kmgpu_alloc_pinned) so that uploads are asynchronous and run at PCIe speed;
 // it is reused from batch to batch.
 struct ReadBatch {
-    char* seqs = nullptr;
-    size_t n_bases = 0, cap = 0;
+    char* seqs = nullptr;            // ASCII bases — or, when `pack` is set, the 2-bit stream (see words())
+    size_t n_bases = 0, cap = 0;     // cap in bytes
     std::vector<uint64_t> offsets;   // n_reads + 1 entries once filled
     bool pinned = false;
+    // pack: the parser threads write the CLEANED reads (Read::set_clean_seq, read_parsers.hh:128-133) straight into the
+    // device's stream format — 64-bit words, 32 bases per word, first base in the top two bits, A0 T1 C2 G3
+    // (kmer_hash.hh:70-72) — so a batch crosses PCIe at 2 bits per base (kmgpu_consume_packed)
+    bool pack = false;
+    uint64_t* words() const { return reinterpret_cast<uint64_t*>(seqs); }
+    size_t n_words() const { return (n_bases + 31) / 32; }
     ReadBatch() {}
     ~ReadBatch();
     ReadBatch(const ReadBatch&) = delete;
@@ -330,6 +336,9 @@ public:
     uint64_t* abundance_distribution(std::string filename, Hashtable* tracking);
 
     // abundance trimming helpers (src/oxli/hashtable.cc:504-612)
+    // digital normalization of a batch in stream order (scripts/normalize-by-median.py:155-179); returns the k-mers consumed
+    unsigned long long normalize_batch(const std::vector<std::string>& seqs, unsigned int cutoff, const std::vector<uint8_t>& pair_with_next,
+                                       std::vector<uint8_t>& keep);
     unsigned long trim_on_abundance(std::string seq, BoundedCounterType min_abund) const;
     unsigned long trim_below_abundance(std::string seq, BoundedCounterType max_abund) const;
     std::vector<unsigned int> find_spectral_error_positions(std::string seq, BoundedCounterType min_abund) const;

@@ -245,6 +245,15 @@ PYBIND11_MODULE(_oxli, m)
             }
             return out;
         })
+        .def("normalize_batch", [](Hashtable& h, const std::vector<std::string>& seqs, unsigned cutoff, const std::vector<uint8_t>& paired) {
+            std::vector<uint8_t> keep;
+            unsigned long long kmers;
+            {
+                py::gil_scoped_release nogil;
+                kmers = h.normalize_batch(seqs, cutoff, paired, keep);
+            }
+            return py::make_tuple(keep, kmers);
+        }, py::arg("seqs"), py::arg("cutoff"), py::arg("paired") = std::vector<uint8_t>())
         .def("n_unique_kmers", &Hashtable::n_unique_kmers)
         .def("n_occupied", &Hashtable::n_occupied)
         .def("n_tables", &Hashtable::n_tables)

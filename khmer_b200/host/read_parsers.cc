@@ -10,6 +10,9 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <thread>
 
 #include <algorithm>
@@ -57,15 +60,16 @@ ReadBatch::~ReadBatch()
     }
 }
 
-void ReadBatch::reserve(size_t n)
+void ReadBatch::reserve(size_t n_want_bases)
 {
+    const size_t n = pack ? (n_want_bases + 31) / 32 * 8 + 16 : n_want_bases;   // bytes
     if (n <= cap) return;
     size_t want = std::max(n, cap + cap / 2);
     void* np = nullptr;
     bool np_pinned = kmgpu_alloc_pinned(want, &np) == 0 && np;   // no device: plain memory still parses
     if (!np_pinned) np = malloc(want);
     if (!np) throw std::bad_alloc();
-    if (n_bases) memcpy(np, seqs, n_bases);
+    if (n_bases) memcpy(np, seqs, pack ? (n_bases + 31) / 32 * 8 : n_bases);
     if (seqs) {
         if (pinned) kmgpu_free_pinned(seqs);
         else free(seqs);
@@ -107,6 +111,120 @@ Bz2& bz2()
 }  // namespace
 
 namespace {
+
+// cleaned 2-bit code of a sequence byte: Read::set_clean_seq (ACGT kept, acgt upper-cased, anything else 'A') followed by
+// twobit_repr (kmer_hash.hh:70-72)
+struct PackLut {
+    uint8_t v[256];
+    PackLut()
+    {
+        memset(v, 0, sizeof v);
+        v[(unsigned char)'T'] = v[(unsigned char)'t'] = 1;
+        v[(unsigned char)'C'] = v[(unsigned char)'c'] = 2;
+        v[(unsigned char)'G'] = v[(unsigned char)'g'] = 3;
+    }
+};
+const PackLut g_pack_lut;
+
+// Appends bases to a 2-bit stream at base position `at`.  Several packers may work on disjoint base ranges of one stream:
+// words that a range shares with its neighbours (the first and the last one it touches) are OR-ed in atomically — they
+// are zeroed, or hold an earlier range's bits, before the packers start — all others are plain stores.
+struct Packer {
+    uint64_t* words;
+    size_t at, first_word;
+    uint64_t acc = 0;
+    Packer(uint64_t* w, size_t start) : words(w), at(start), first_word(start >> 5) {}
+    inline void flush_word(size_t w, bool shared)
+    {
+        if (shared) __atomic_fetch_or(&words[w], acc, __ATOMIC_RELAXED);
+        else words[w] = acc;
+        acc = 0;
+    }
+    inline void add(const char* p, size_t n)
+    {
+        const uint8_t* lut = g_pack_lut.v;
+        for (size_t i = 0; i < n; i++) {
+            const unsigned sh = 62 - 2 * (unsigned)(at & 31);
+            acc |= (uint64_t)lut[(unsigned char)p[i]] << sh;
+            at++;
+            if ((at & 31) == 0) flush_word((at >> 5) - 1, (at >> 5) - 1 == first_word);
+        }
+    }
+    inline void finish()
+    {
+        if (at & 31) flush_word(at >> 5, true);
+    }
+};
+
+// a few long-lived worker threads: a batch is parsed by all of them twice (locate, then copy / pack), and a thread start per
+// slice and pass costs as much as the work on small batches
+class Workers {
+public:
+    explicit Workers(unsigned n) : n_(n)
+    {
+        for (unsigned t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~Workers()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& x : th_) x.join();
+    }
+    // runs fn(0) .. fn(n - 1), fn(0) on the calling thread
+    void run(const std::function<void(unsigned)>& fn)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn;
+            left_ = n_ - 1;
+            gen_++;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [this] { return left_ == 0; });
+        fn_ = nullptr;
+    }
+    unsigned size() const { return n_; }
+
+private:
+    void loop(unsigned t)
+    {
+        uint64_t seen = 0;
+        while (true) {
+            const std::function<void(unsigned)>* fn;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(t);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                left_--;
+            }
+            done_.notify_one();
+        }
+    }
+    unsigned n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned)>* fn_ = nullptr;
+    unsigned left_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace
+
+namespace {
 struct Seg {            // a piece of sequence inside the mapping
     const char* p;
     uint32_t n;
@@ -140,6 +258,7 @@ struct FastxReader::Impl {
     size_t num_reads = 0;
     bool have_qualities = false;
     std::mutex mu;
+    std::unique_ptr<Workers> workers;   // parser threads of the parallel batch path (created on first use)
     std::string pending_error;  // InvalidRead message raised by a batch after its good reads were returned
     int pending_kind = 0;       // 1 InvalidRead, 2 StreamReadError
 
@@ -510,13 +629,13 @@ size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
         for (unsigned t = 1; t < T; t++) cut[t] = find_record(b, w0 + (uint64_t)(w1 - w0) * t / T, w1, m.kind);
         for (unsigned t = 1; t <= T; t++)
             if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
-        std::vector<std::thread> th;
+        if (!m.workers || m.workers->size() != T) m.workers.reset(new Workers(T));
         for (unsigned t = 0; t < T; t++) {
             sl[t].a = cut[t];
             sl[t].b = cut[t + 1];
-            th.emplace_back(parse_slice, std::ref(sl[t]), m.kind);
         }
-        for (auto& x : th) x.join();
+        const char kind = m.kind;
+        m.workers->run([&sl, kind](unsigned t) { parse_slice(sl[t], kind); });
         bool ok = true;
         size_t total = 0, nreads = 0;
         for (auto& x : sl) {
@@ -540,9 +659,25 @@ size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
             }
             char* dst = out.seqs;
             uint64_t* offp = out.offsets.data();
-            th.clear();
-            for (unsigned t = 0; t < T; t++)
-                th.emplace_back([&, t]() {
+            if (out.pack) {
+                // words shared by two slices (and the tail word) start from zero — except the one the batch already ends in
+                uint64_t* w = out.words();
+                const size_t keep = base0 & 31 ? base0 >> 5 : (size_t)-1;
+                for (unsigned t = 0; t <= T; t++) {
+                    const size_t wi = (t < T ? sb[t] : base0 + total) >> 5;
+                    if (wi != keep) w[wi] = 0;
+                }
+                m.workers->run([&](unsigned t) {
+                    size_t r = rb[t];
+                    Packer pk(w, sb[t]);
+                    for (const Seg& sg : sl[t].segs) {
+                        pk.add(sg.p, sg.n);
+                        if (sg.last) offp[r++] = pk.at;
+                    }
+                    pk.finish();
+                });
+            } else {
+                m.workers->run([&](unsigned t) {
                     size_t o = sb[t], r = rb[t];
                     for (const Seg& sg : sl[t].segs) {
                         memcpy(dst + o, sg.p, sg.n);
@@ -550,7 +685,7 @@ size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
                         if (sg.last) offp[r++] = o;
                     }
                 });
-            for (auto& x : th) x.join();
+            }
             out.n_bases = base0 + total;
             m.pos = (size_t)(w1 - b);
             m.num_reads += nreads;
@@ -585,8 +720,20 @@ size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
             break;
         }
         m.num_reads++;
-        out.reserve(out.n_bases + seq.size());
-        memcpy(out.seqs + out.n_bases, seq.data(), seq.size());
+        out.reserve(out.n_bases + seq.size() + 32);
+        if (out.pack) {
+            // serial: the word the batch ends in keeps its bits, the words this read reaches for the first time start from zero
+            uint64_t* w = out.words();
+            const size_t w_first = (out.n_bases + 31) >> 5, w_last = (out.n_bases + seq.size()) >> 5;
+            for (size_t wi = w_first; wi <= w_last; wi++) w[wi] = 0;
+            const uint8_t* lut = g_pack_lut.v;
+            for (size_t i = 0; i < seq.size(); i++) {
+                const size_t at = out.n_bases + i;
+                w[at >> 5] |= (uint64_t)lut[(unsigned char)seq[i]] << (62 - 2 * (unsigned)(at & 31));
+            }
+        } else {
+            memcpy(out.seqs + out.n_bases, seq.data(), seq.size());
+        }
         out.n_bases += seq.size();
         out.offsets.push_back(out.n_bases);
         n++;

@@ -101,3 +101,33 @@ def test_shard_range():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _socket_worker(rank, world, port, log, out):
+    from khmer_b200.multigpu import ReplicaGroup, SocketComm
+    comm = SocketComm(rank=rank, world=world, addr="127.0.0.1", port=port)
+    assert comm.all_gather_bytes(bytes([rank + 7]) * (rank + 1)) == [bytes([7]), bytes([8, 8])][:world]
+    assert comm.all_reduce_sum(10 + rank) == sum(10 + r for r in range(world))
+    comm.barrier()
+    sk = StubSketch(rank, log)
+    g = ReplicaGroup(sk, comm)
+    g.attach()
+    r, w, h = sk.attached
+    assert (r, w) == (rank, world) and h.shape == (world * 64 * 3,)
+    for q in range(world):
+        assert (h[q * 192:(q + 1) * 192] == q + 1).all()
+    g.merge()
+    g.detach()
+    comm.close()
+    if rank == 0:
+        open(out, "w").write("ok")
+
+
+def test_replica_group_socket_rendezvous_world2(tmp_path):
+    """the dependency-free rendezvous (no torch.distributed): same handle order and barrier placement"""
+    log, out = str(tmp_path / "log"), str(tmp_path / "out")
+    port = 31500 + (os.getpid() % 500)
+    mp.spawn(_socket_worker, args=(2, port, log, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+    ops = [ln.split()[1] for ln in open(log).read().split("\n") if ln]
+    assert ops[:2] == ["rs", "rs"] and ops[2:4] == ["ag", "ag"] and ops[4:] == ["detach", "detach"]

@@ -7,8 +7,8 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
 echo "== smoke" | tee $OUT/progress.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/progress.txt
-echo "== sanitizer (small grouped case)" | tee -a $OUT/progress.txt
-KMGPU_TEST_CLS=Countgraph KMGPU_GROUP_MIN_BUCKETS=0 KMGPU_CHUNK_BASES=16384 KMGPU_PART_BASES=1000 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 \
+echo "== small grouped case" | tee -a $OUT/progress.txt
+KMGPU_TEST_CLS=Countgraph KMGPU_GROUP_MIN_BUCKETS=0 KMGPU_CHUNK_BASES=16384 KMGPU_PART_BASES=1000 timeout 300 \
    python -m pytest -q -x -m gpu tests/test_gpu_parity.py -k test_gpu_vs_oracle_random_inner > $OUT/sanitizer.log 2>&1; echo "sanitizer rc=$?" | tee -a $OUT/progress.txt
 echo "== grouped-path tests" | tee -a $OUT/progress.txt
 timeout 1500 python -m pytest -q -x -m gpu tests/test_gpu_parity.py -k "group or golden_C1 or many_buckets or (golden and 25k)" > $OUT/tests_group.log 2>&1; echo "group tests rc=$?" | tee -a $OUT/progress.txt
