@@ -281,6 +281,70 @@ def parity_check(cabi, local_rank, n_reads, seed=31337):
             "mismatch": None if ok else {"got": got, "want": want}}
 
 
+def file_leg(args, local_rank, repeats=3):
+    """k-mers/s of khmer_b200.Countgraph(20, 1e8, 4).consume_seqfile(fasta) — wall clock around the call (it returns when the table
+    is final), best of `repeats`, file in the page cache like the reference arm's."""
+    import khmer_b200
+    os.environ.setdefault("KMGPU_DEVICE", str(local_rank))
+    n_reads = args.reads
+    buf, off, _ = synth_batch(777, n_reads)
+    td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    path = os.path.join(td, "reads.fa")
+    try:
+        rows = buf.reshape(n_reads, READ_LEN)
+        block = np.empty((n_reads, READ_LEN + 4), dtype=np.uint8)
+        block[:, :3] = np.frombuffer(b">r\n", dtype=np.uint8)
+        block[:, 3:3 + READ_LEN] = rows
+        block[:, -1] = ord("\n")
+        with open(path, "wb") as fh:
+            fh.write(block.tobytes())
+        del block
+        best = None
+        for _ in range(repeats + 1):          # first pass is the warm-up (buffers, pinned batches)
+            t = khmer_b200.Countgraph(K, TABLE_X, N_TABLES)
+            t0 = time.perf_counter()
+            reads, kmers = t.consume_seqfile(path)
+            dt = time.perf_counter() - t0
+            assert reads == n_reads and kmers == n_reads * KMERS_PER_READ
+            best = dt if best is None or _ == 1 else min(best, dt)
+            del t
+        return {"value": kmers / best, "unit": "k-mers/s", "api": "khmer_b200.Countgraph.consume_seqfile(path)", "reads": n_reads,
+                "file_bytes": os.path.getsize(path), "format": "FASTA, uncompressed", "parser_threads": min(16, os.cpu_count() or 1),
+                "seconds": best, "timing": "wall clock (perf_counter) around the call, best of %d after one warm-up" % repeats}
+    finally:
+        try:
+            os.unlink(path)
+            os.rmdir(td)
+        except OSError:
+            pass
+
+
+def secondary_legs(cabi, sk, host, dev, local_rank, n_query=400_000):
+    """The read-side queries on the table the timed legs left behind (not the headline metric): per-read medians
+    (Hashtable::get_median_count, hashtable.cc:299-328) and the abundance histogram (hashtable.cc:451-493), wall clock around the
+    C-ABI calls with host buffers."""
+    buf, off, _ = host[0]
+    sk.reset()
+    sk.consume_batch(dev[0])
+    q = (buf[: n_query * READ_LEN], off[: n_query + 1])
+    sk.read_medians((buf[: 1000 * READ_LEN], off[: 1001]))          # warm-up
+    t0 = time.perf_counter()
+    med, _, _, nk = sk.read_medians(q)
+    t_med = time.perf_counter() - t0
+    sizes = primes_near_x(N_TABLES, TABLE_X)
+    tracking = cabi.Sketch(cabi.BIT, cabi.TWOBIT, K, sizes, device=local_rank)
+    t0 = time.perf_counter()
+    hist = sk.abundance_distribution((buf, off), tracking)
+    t_ab = time.perf_counter() - t0
+    n_all = (len(off) - 1) * KMERS_PER_READ
+    out = {"medians": {"reads_per_s": n_query / t_med, "kmers_per_s": n_query * KMERS_PER_READ / t_med, "reads": n_query,
+                       "median_of_medians": float(np.median(med))},
+           "abundance_distribution": {"kmers_per_s": n_all / t_ab, "kmers": n_all, "distinct": int(hist.sum())},
+           "timing": "wall clock around kmgpu_read_medians / kmgpu_abundance_distribution, host ASCII in, results out"}
+    tracking.close()
+    return out
+
+
 def merge_check(cabi, dist, torch, group_cls, rank, world, local_rank, n_reads=125_000):
     """N > 1: every rank ingests its own fixed batch into a fresh replica, the replicas are merged over NVLink exactly as in
     the timed region; all ranks must then hold identical tables, and rank 0 compares them with ONE sketch fed every rank's
@@ -437,6 +501,15 @@ def run_ours(args):
         sk.set_use_bigcount(True)
         sk.reset()
 
+    # end to end from a FILE through the host layer's reference-named call, khmer_b200.Countgraph.consume_seqfile(path): mmap + parser
+    # threads (clean + 2-bit pack) + pinned batches + H2D + ingest, all inside the timed region — what the reference arm's
+    # consume_seqfile<FastxReader> does on the CPU
+    e2e_file = None
+    secondary = None
+    if world == 1 and not args.no_file:
+        e2e_file = file_leg(args, local_rank)
+        secondary = secondary_legs(cabi, sk, host, dev, local_rank)
+
     checks = {}
     if not args.no_check:
         if rank == 0:
@@ -493,6 +566,10 @@ def run_ours(args):
         }
         if value_nobig is not None:
             line["value_bigcount_off"] = value_nobig
+        if e2e_file is not None:
+            line["e2e_file"] = e2e_file
+        if secondary is not None:
+            line["secondary"] = secondary
         line.update(checks)
         emit(line)
     if world > 1:
@@ -532,6 +609,7 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=250_000, help="reads per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip parity_check / merge_check")
+    ap.add_argument("--no-file", action="store_true", help="skip the e2e_file and secondary legs")
     ap.add_argument("--check-reads", type=int, default=250_000, help="reads of the parity_check batch")
     args = ap.parse_args()
     if args.impl == "reference":

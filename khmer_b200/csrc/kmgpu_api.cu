@@ -205,7 +205,6 @@ struct kmgpu_sketch {
     DevBuf<uint32_t> d_cur1;
     DevBuf<unsigned long long> d_off1, d_off2;   // exact region offsets of a regrouping run
     DevBuf<uint64_t> d_hash64;              // Murmur: 64-bit hash of every position of the chunk
-    DevBuf<uint16_t> d_fill;                // grouped path, persistent grouping: records in every sub-region
     DevBuf<uint32_t> d_readbits;            // one bit per read of a window (normalization: candidates / kept)
     DevBuf<uint32_t> d_upos, d_hitpos;      // normalization: positions of in-between reads; hits of their bins
     DevBuf<uint64_t> d_ubins, d_hitkey;
@@ -502,7 +501,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_fill.release(); h->d_newmask.release(); for (auto& sg : h->ft_segs) cudaFree(sg.first); h->ft_segs.clear(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_newmask.release(); for (auto& sg : h->ft_segs) cudaFree(sg.first); h->ft_segs.clear(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -1023,9 +1022,12 @@ static int resolve_bigcount_delta(kmgpu_sketch* h, int src, HashCfg H, const std
     SatBits sb;
     memset(&sb, 0, sizeof sb);
     for (int i = 0; i < h->nt && i < F_MAXT; i++) sb.t[i] = h->d_satbits[i].p;
-    for (const Part& pt : parts) {
-        const Input& in = pt.in;
+    for (size_t pi = 0; pi < parts.size(); pi++) {
+        const Part& pt = parts[pi];
+        Input in = pt.in;
         if (in.n_pos == 0 || rehash) continue;
+        // a part's last k-1 positions are the next part's first ones (their bins[] entries are the next part's by now): scan its own only
+        if (pi + 1 < parts.size()) in.n_pos = std::min<uint32_t>(in.n_pos, parts[pi + 1].pos_off - pt.pos_off);
         const uint32_t* bins = h->d_bins.p + pt.pos_off;
         unsigned gb = (in.n_pos + 255) / 256;
         if (src == 1) k_bigscan<TWOBIT, 1><<<gb, 256, 0, st>>>(h->nt, H, in, bins, stride, sb, h->d_htkeys.p, slots - 1, n_cross ? 1 : 0,

@@ -49,10 +49,6 @@ struct Store {
     uint32_t* cursor;                // records written to (demanded of) every partition (indexed by p)
     uint32_t cap;
     uint32_t p0;                     // first partition held (tables are grouped in turns when memory is short)
-    // sub-region layout (k_part_p): the region of partition p is cut into `subs` equal sub-regions of subcap = cap / subs records,
-    // one per persistent grouping CTA, filled independently (fill[(p - p0) * subs + c] records in sub-region c) — no cursor atomics
-    const uint16_t* fill;
-    uint32_t subs, subcap;
     __device__ __forceinline__ unsigned long long base(uint32_t p) const { return off ? off[p - p0] : (unsigned long long)(p - p0) * cap; }
     __device__ __forceinline__ uint32_t room(uint32_t p) const { return off ? (uint32_t)(off[p - p0 + 1] - off[p - p0]) : cap; }
 };
@@ -420,131 +416,6 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
 }
 
-// =====================================================================================================================
-// 1b. k_part_p: MODE 0 as a PERSISTENT kernel without cursor atomics.  grid = (G, tables): CTA (c, t) groups tiles c, c + G, ...
-//     of table t and owns sub-region c of every bucket of that table (Store::subs == G), so a run's place is known from a
-//     cursor the CTA keeps in shared memory — the one global atomicAdd per (tile, non-empty bucket) of k_part (a third of a
-//     chunk's grouping time, and a barrier's worth of latency per tile) is gone.  The cursors live in `fill` between launches
-//     (host input arrives in parts, one launch each).  A sub-region that runs out of room reports overflow like any region;
-//     the chunk is then regrouped by k_part with exact offsets.
-// =====================================================================================================================
-template <int T, int NTHR, int SRC, bool PRED, int BPT>
-__global__ void __launch_bounds__(NTHR, (2 * (part_smem(T, false) + PART_MAXP * 2) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
-k_part_p(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P, uint16_t* __restrict__ fill)
-{
-    constexpr int PER = T / NTHR;
-    extern __shared__ __align__(16) unsigned char pt_raw[];
-    uint2* stage = reinterpret_cast<uint2*>(pt_raw);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // count, then run start | sub-region cursor << 16
-    uint16_t* lcur = reinterpret_cast<uint16_t*>(hist + PART_MAXP);           // this CTA's cursor in its sub-region of every bucket
-    PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(lcur + PART_MAXP);
-    __shared__ uint32_t s_warp[32];
-    const uint32_t tid = threadIdx.x;
-    const int t = A.table0 + blockIdx.y;
-    const uint32_t np = A.L.first[t + 1] - A.L.first[t], cur0 = A.L.first[t];
-    const uint32_t G = A.dst.subs, cta = blockIdx.x, subcap = A.dst.subcap;   // gridDim.x <= G CTAs run (fewer when the part is short)
-    const uint64_t size = A.S.sizes[t], magic = A.S.magic[t];
-    for (uint32_t b = tid; b < np; b += NTHR) lcur[b] = fill[(size_t)(cur0 - A.dst.p0 + b) * G + cta];
-    unsigned n_k = 0;
-    bool over = false;
-    constexpr uint32_t NONE = 0xFFFFFFFFu;
-    for (uint32_t p0 = cta * (uint32_t)T; p0 < A.in.n_pos; p0 += gridDim.x * (uint32_t)T) {
-        uint32_t key[PER], rk[(PER + 1) / 2];
-        for (uint32_t i = tid; i < np; i += NTHR) hist[i] = 0;
-        part_tile_begin<T, NTHR, SRC>(A.in, A.H.k, p0, A.have_valid, tile);   // ends with __syncthreads()
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            const uint32_t lp = j * NTHR + tid;
-            key[j] = NONE;
-            if (p0 + lp < A.in.n_pos && ((tile.valid[lp >> 5] >> (lp & 31)) & 1u)) {
-                const uint64_t h = SRC == 1 ? __ldcs(A.in.hashes + p0 + lp) : hash_twobit(tile.words, lp, A.H.k);
-                if (!PRED || pred_pass(P, M, h)) {
-                    key[j] = (uint32_t)mod_magic(h, size, magic);
-                    n_k++;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            uint32_t r = 0;
-            if (key[j] != NONE) r = atomicAdd(&hist[key[j] >> BKT_SHIFT], 1u);
-            if (j & 1) rk[j >> 1] |= r << 16; else rk[j >> 1] = r;
-        }
-        __syncthreads();
-        uint32_t c[BPT], mine = 0;
-#pragma unroll
-        for (int q = 0; q < BPT; q++) {
-            const uint32_t b = tid * BPT + q;
-            c[q] = b < np ? hist[b] : 0;
-            mine += c[q];
-        }
-        uint32_t incl = mine;
-        const uint32_t lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < NTHR / 32; w++) {
-            const uint32_t v = s_warp[w];
-            before += (uint32_t)w < wid ? v : 0u;
-            total += v;
-        }
-        uint32_t at = before + incl - mine;
-#pragma unroll
-        for (int q = 0; q < BPT; q++) {
-            const uint32_t b = tid * BPT + q;
-            if (b < np) {
-                const uint32_t base = lcur[b];
-                hist[b] = at | (base << 16);                 // run start, and where the run goes in this CTA's sub-region
-                const uint32_t nb = base + c[q];
-                lcur[b] = (uint16_t)(nb > 0xFFFFu ? 0xFFFFu : nb);   // keeps counting the demand (a full sub-region is reported below)
-                over |= nb > subcap;
-            }
-            at += c[q];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            if (key[j] == NONE) continue;
-            const uint32_t pid = key[j] >> BKT_SHIFT;
-            const uint32_t r = (j & 1) ? rk[j >> 1] >> 16 : rk[j >> 1] & 0xFFFFu;
-            stage[(hist[pid] & 0xFFFFu) + r] = make_uint2(key[j] & (BKT_BINS - 1), (pid << 14) | (uint32_t)(j * NTHR + tid));
-        }
-        __syncthreads();
-        for (uint32_t s = tid; s < total; s += NTHR) {
-            const uint2 m = stage[s];
-            const uint32_t pid = m.y >> 14;
-            const uint32_t hv = hist[pid];
-            const uint32_t idx = (hv >> 16) + (s - (hv & 0xFFFFu));
-            if (idx < subcap)
-                A.dst.rec[((unsigned long long)(cur0 - A.dst.p0 + pid) * G + cta) * subcap + idx] =
-                    ((unsigned long long)(A.pos_base + p0 + (m.y & 0x3FFFu)) << BKT_SHIFT) | m.x;
-        }
-        __syncthreads();   // hist and the tile buffers are reused by the next tile
-    }
-    for (uint32_t b = tid; b < np; b += NTHR) fill[(size_t)(cur0 - A.dst.p0 + b) * G + cta] = lcur[b];
-    if (t == 0 && A.count_kmers) {
-        n_k = __reduce_add_sync(0xffffffffu, n_k);
-        if ((tid & 31) == 0 && n_k) atomicAdd(&A.ctrl->n_kmers, (unsigned long long)n_k);
-    }
-    if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
-}
-
-// demand of every bucket = the sum of its sub-region cursors (for a regrouping run after k_part_p reported overflow)
-__global__ void k_fill_sums(const uint16_t* __restrict__ fill, uint32_t n_buckets, uint32_t G, uint32_t* __restrict__ cursor)
-{
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    uint32_t sum = 0;
-    for (uint32_t c = 0; c < G; c++) sum += fill[(size_t)b * G + c];
-    cursor[b] = sum;
-}
-
 // 64-bit hashes of every position (Murmur): one pass, then k_part<SRC 1> per table
 template <int HK>
 __global__ void __launch_bounds__(THREADS)
@@ -611,7 +482,7 @@ template <int KIND>
 __global__ void __launch_bounds__(1024, 1)
 k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
          uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
-         unsigned long long ovf_mask, uint32_t* __restrict__ newmask)
+         unsigned long long ovf_mask, uint32_t* __restrict__ newmask, int gate)
 {
     extern __shared__ __align__(128) unsigned char ap_raw[];
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // BKT_BINS / 2 words, two 16-bit lanes each
@@ -621,33 +492,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     if (ctrl->overflow & ovf_mask) return;      // a region of this table group ran out of room: the group is regrouped with exact offsets
     const uint32_t b = bucket0 + blockIdx.x;
     const uint32_t tid = threadIdx.x;
-    constexpr int MAX_SUBS = 320;
-    __shared__ uint32_t s_pref[MAX_SUBS + 1];   // sub-region layout: records before sub-region c
-    uint32_t n;
-    if (st.fill) {
-        // the bucket's records lie in `subs` sub-regions (one per grouping CTA): prefix sums of their fills, by warp 0
-        if (tid < 32) {
-            const uint32_t per = (st.subs + 31) / 32, c0 = tid * per;
-            uint32_t sum = 0;
-            for (uint32_t c = c0; c < c0 + per && c < st.subs; c++) sum += st.fill[(size_t)(b - st.p0) * st.subs + c];
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= (uint32_t)o) incl += v;
-            }
-            uint32_t at = incl - sum;
-            for (uint32_t c = c0; c < c0 + per && c < st.subs; c++) {
-                s_pref[c] = at;
-                at += st.fill[(size_t)(b - st.p0) * st.subs + c];
-            }
-            if (tid == 31) s_pref[st.subs] = incl;
-        }
-        __syncthreads();
-        n = s_pref[st.subs];
-    } else {
-        n = st.cursor[b];
-    }
+    const uint32_t n = st.cursor[b];
     if (n == 0) return;
     int t = 0;
 #pragma unroll 1
@@ -683,7 +528,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
         for (int q = 0; q < GPT; q++) {
             const uint32_t g = q * 1024 + tid;
             uint32_t w[4] = {0, 0, 0, 0};
-            if ((uint64_t)g * (KIND == BYTE ? 8 : 4) < sbytes) {
+            if (gate && (uint64_t)g * (KIND == BYTE ? 8 : 4) < sbytes) {
                 if (KIND == BYTE) {
                     const uint64_t old64 = *reinterpret_cast<const uint64_t*>(slice + (size_t)g * 8);
 #pragma unroll
@@ -699,23 +544,13 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     }
     __syncthreads();
     const unsigned long long* src = st.rec + st.base(b);
-    const uint32_t sub_avg = st.fill ? (n / st.subs > 0 ? n / st.subs : 1u) : 1u;
     constexpr int RIF = 16;   // records in flight per thread
     for (uint32_t e0 = 0; e0 < n; e0 += RIF * 1024) {
         unsigned long long v[RIF];
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
             uint32_t e = e0 + j * 1024 + tid;
-            if (st.fill && e < n) {
-                // which sub-region holds the e-th record: they are nearly equally full, so the guess e / average is a step or two off
-                uint32_t c = e / sub_avg;
-                if (c >= st.subs) c = st.subs - 1;
-                while (e < s_pref[c]) c--;
-                while (e >= s_pref[c + 1]) c++;
-                v[j] = __ldcs(src + (size_t)c * st.subcap + (e - s_pref[c]));
-            } else {
-                v[j] = e < n ? __ldcs(src + e) : ~0ull;
-            }
+            v[j] = e < n ? __ldcs(src + e) : ~0ull;
         }
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
@@ -723,10 +558,14 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             const uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
             if (KIND == BIT) {
                 // a Bloom bit that is set already changes nothing
-                if (slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
-            } else {
+                if (!gate || slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+            } else if (gate) {
                 const uint32_t was = atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
                 if (!((lb & 1) ? was >> 31 : (was >> 15) & 1u)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+            } else {
+                // ungated: both updates leave at once, nothing waits for a result (the sweep ignores positions of bins that were occupied)
+                atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+                atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
             }
         }
         if (KIND != BIT && n > 32767u) {

@@ -930,6 +930,152 @@ void Hashtable::consume_seqfile_banding_with_mask(ReadParserPtr<SeqIO>& parser, 
     bulk_consume<SeqIO>(parser, b, mask, threshold, consume_masked, total_reads, n_consumed);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// tagging
+// ---------------------------------------------------------------------------------------------------------
+void Hashtable::_set_tag_density(unsigned int d)
+{
+    // hashgraph.hh:128-135
+    if (!(d % 2 == 0) || !all_tags.empty()) throw oxli_exception("Invalid tag density: must be even, and the tag set must be empty.");
+    _tag_density = d;
+}
+
+// Hashgraph::consume_sequence_and_tag (hashgraph.cc:200-271) for every read of a batch, with store->test_and_set_bits(kmer)
+// replaced by the bit the device returned for that k-mer.  Reads without a k-mer are skipped (the reference inserts an
+// uninitialised hash value for them: undefined behaviour, consciously not reproduced).
+void Hashtable::tag_batch(const char* seqs, const uint64_t* offsets, size_t n_reads, unsigned long long& n_consumed)
+{
+    if (_hashkind != TWOBIT_HASH) throw oxli_exception("tagging needs a two-bit hash sketch (Countgraph, SmallCountgraph, Nodegraph)");
+    if (n_reads == 0) return;
+    const uint64_t n_bases = offsets[n_reads] - offsets[0];
+    std::vector<uint32_t> bits((n_bases + 31) / 32 + 1);
+    uint64_t n_kmers = 0, n_new = 0;
+    check(kmgpu_consume_reads_new(store->handle(), seqs, offsets, n_reads, KMGPU_CLEAN, bits.data(), &n_kmers, &n_new));
+    n_consumed += n_new;
+    const unsigned k = _ksize;
+    const HashIntoType mask = k == 32 ? ~(HashIntoType)0 : (((HashIntoType)1 << (2 * k)) - 1);
+    std::lock_guard<std::mutex> g(tags_mu);   // the reference takes a spin lock per k-mer; one batch at a time here
+    auto clean = [](char c) -> char {
+        switch (c) {
+        case 'A': case 'C': case 'G': case 'T': return c;
+        case 'a': return 'A';
+        case 'c': return 'C';
+        case 'g': return 'G';
+        case 't': return 'T';
+        default: return 'A';
+        }
+    };
+    for (size_t r = 0; r < n_reads; r++) {
+        const char* s = seqs + offsets[r];
+        const uint64_t len = offsets[r + 1] - offsets[r], base = offsets[r] - offsets[0];
+        if (len < k) continue;
+        // KmerIterator (kmer_hash.cc:278-343) over the cleaned read (Read::set_clean_seq: ACGT kept, acgt upper-cased, else 'A')
+        HashIntoType f = 0, rc = 0;
+        for (unsigned i = 0; i + 1 < k; i++) {
+            const char c = clean(s[i]);
+            f = (f << 2) | code_fwd(c);
+            rc = (rc >> 2) | (code_cmp(c) << (2 * k - 2));
+        }
+        unsigned int since = _tag_density / 2 + 1;
+        HashIntoType kmer = 0;
+        for (uint64_t i = 0; i + k <= len; i++) {
+            const char c = clean(s[i + k - 1]);
+            f = ((f << 2) | code_fwd(c)) & mask;
+            rc = (rc >> 2) | (code_cmp(c) << (2 * k - 2));
+            kmer = f < rc ? f : rc;
+            const uint64_t p = base + i;
+            const bool is_new = (bits[p >> 5] >> (p & 31)) & 1u;
+            if (is_new) {
+                ++since;
+            } else if (all_tags.count(kmer)) {
+                since = 1;
+            } else {
+                ++since;
+            }
+            if (since >= _tag_density) {
+                all_tags.insert(kmer);
+                since = 1;
+            }
+        }
+        if (since >= _tag_density / 2 - 1) all_tags.insert(kmer);   // the last k-mer, too
+    }
+}
+
+void Hashtable::consume_sequence_and_tag(const std::string& cleaned_seq, unsigned long long& n_consumed)
+{
+    const uint64_t offs[2] = {0, cleaned_seq.size()};
+    tag_batch(cleaned_seq.data(), offs, 1, n_consumed);
+}
+
+template <typename SeqIO>
+void Hashtable::consume_seqfile_and_tag(std::string const& filename, unsigned int& total_reads, unsigned long long& n_consumed)
+{
+    ReadParserPtr<SeqIO> parser = get_parser<SeqIO>(filename);
+    consume_seqfile_and_tag<SeqIO>(parser, total_reads, n_consumed);
+}
+template <typename SeqIO>
+void Hashtable::consume_seqfile_and_tag(ReadParserPtr<SeqIO>& parser, unsigned int& total_reads, unsigned long long& n_consumed)
+{
+    total_reads = 0;      // hashgraph.cc:300-301
+    n_consumed = 0;
+    ReadBatch batch;      // ASCII: the tag scan hashes the reads on the host
+    while (true) {
+        batch.clear();
+        size_t got = parser->io().read_batch(feed_bases(), batch);
+        if (got == 0) break;
+        unsigned long long n = 0;
+        tag_batch(batch.seqs, batch.offsets.data(), got, n);
+        __sync_add_and_fetch(&n_consumed, n);
+        __sync_add_and_fetch(&total_reads, (unsigned int)got);
+    }
+}
+
+void Hashtable::save_tagset(std::string filename)
+{
+    // hashgraph.cc:55-88: "OXLI", version, SAVED_TAGS, ksize (u32), number of tags (u64), tag density (u32), the tags in set order
+    std::ofstream out(filename.c_str(), std::ios::binary);
+    const size_t n = all_tags.size();
+    unsigned int save_ksize = _ksize;
+    out.write(SAVED_SIGNATURE, 4);
+    unsigned char version = SAVED_FORMAT_VERSION, ht_type = SAVED_TAGS;
+    out.write((const char*)&version, 1);
+    out.write((const char*)&ht_type, 1);
+    out.write((const char*)&save_ksize, sizeof save_ksize);
+    out.write((const char*)&n, sizeof n);
+    out.write((const char*)&_tag_density, sizeof _tag_density);
+    std::vector<HashIntoType> buf(all_tags.begin(), all_tags.end());
+    out.write((const char*)buf.data(), sizeof(HashIntoType) * n);
+    if (out.fail()) throw oxli_file_exception(strerror(errno));
+    out.close();
+}
+
+void Hashtable::load_tagset(std::string filename, bool clear)
+{
+    // hashgraph.cc:90-175
+    std::ifstream in(filename.c_str(), std::ios::binary);
+    if (!in.is_open()) throw oxli_file_exception("Cannot open tagset file: " + filename);
+    char sig[4];
+    unsigned char version = 0, ht_type = 0;
+    unsigned int save_ksize = 0, density = 0;
+    size_t n = 0;
+    in.read(sig, 4);
+    in.read((char*)&version, 1);
+    in.read((char*)&ht_type, 1);
+    if (!in || std::string(sig, 4) != SAVED_SIGNATURE) throw oxli_file_exception("Does not start with signature for a oxli file: " + filename);
+    if (version != SAVED_FORMAT_VERSION) throw oxli_file_exception("Incorrect file format version " + std::to_string((int)version) + " while reading tagset from " + filename);
+    if (ht_type != SAVED_TAGS) throw oxli_file_exception("Incorrect file format type " + std::to_string((int)ht_type) + " while reading tagset from " + filename);
+    in.read((char*)&save_ksize, sizeof save_ksize);
+    if (!in || save_ksize != _ksize) throw oxli_file_exception("Incorrect k-mer size " + std::to_string(save_ksize) + " while reading tagset from " + filename);
+    in.read((char*)&n, sizeof n);
+    in.read((char*)&density, sizeof density);
+    std::vector<HashIntoType> buf(n);
+    in.read((char*)buf.data(), sizeof(HashIntoType) * n);
+    if (!in) throw oxli_file_exception("Error reading tagset file: " + filename);
+    if (clear) all_tags.clear();
+    _tag_density = density;
+    all_tags.insert(buf.begin(), buf.end());
+}
+
 template <typename SeqIO>
 uint64_t* Hashtable::abundance_distribution(ReadParserPtr<SeqIO>& parser, Hashtable* tracking)
 {
@@ -977,6 +1123,8 @@ template void Hashtable::consume_seqfile_banding_with_mask<FastxReader>(std::str
 template void Hashtable::consume_seqfile_banding_with_mask<FastxReader>(ReadParserPtr<FastxReader>&, unsigned int, unsigned int,
                                                                         Hashtable*, unsigned int, unsigned int&, unsigned long long&,
                                                                         bool);
+template void Hashtable::consume_seqfile_and_tag<FastxReader>(std::string const&, unsigned int&, unsigned long long&);
+template void Hashtable::consume_seqfile_and_tag<FastxReader>(ReadParserPtr<FastxReader>&, unsigned int&, unsigned long long&);
 template uint64_t* Hashtable::abundance_distribution<FastxReader>(ReadParserPtr<FastxReader>&, Hashtable*);
 template uint64_t* Hashtable::abundance_distribution<FastxReader>(std::string, Hashtable*);
 

@@ -15,6 +15,8 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <set>
+#include <mutex>
 #include <vector>
 
 struct kmgpu_sketch;
@@ -33,6 +35,7 @@ constexpr const char* SAVED_SIGNATURE = "OXLI";
 constexpr unsigned char SAVED_FORMAT_VERSION = 4;
 constexpr unsigned char SAVED_COUNTING_HT = 1;
 constexpr unsigned char SAVED_HASHBITS = 2;
+constexpr unsigned char SAVED_TAGS = 3;
 constexpr unsigned char SAVED_SMALLCOUNT = 7;
 
 // ---- exceptions (include/oxli/oxli_exception.hh) -------------------------------------------------------
@@ -343,10 +346,32 @@ public:
     unsigned long trim_below_abundance(std::string seq, BoundedCounterType max_abund) const;
     std::vector<unsigned int> find_spectral_error_positions(std::string seq, BoundedCounterType min_abund) const;
 
+    // ---- tagging (Hashgraph, include/oxli/hashgraph.hh:88-140, src/oxli/hashgraph.cc:200-320; two-bit hash sketches only) ----
+    // The counting of every k-mer and its "was new" bit come from the device in one call per batch of reads
+    // (kmgpu_consume_reads_new); the tag scan over those bits is the reference's, read by read in stream order, against the
+    // std::set the tag file is written from.  n_consumed counts the NEW k-mers, like the reference's.
+    void consume_sequence_and_tag(const std::string& cleaned_seq, unsigned long long& n_consumed);
+    template <typename SeqIO>
+    void consume_seqfile_and_tag(std::string const& filename, unsigned int& total_reads, unsigned long long& n_consumed);
+    template <typename SeqIO>
+    void consume_seqfile_and_tag(read_parsers::ReadParserPtr<SeqIO>& parser, unsigned int& total_reads, unsigned long long& n_consumed);
+    size_t n_tags() const { return all_tags.size(); }
+    const std::set<HashIntoType>& tags() const { return all_tags; }
+    void add_tag(HashIntoType t) { all_tags.insert(t); }
+    void clear_tags() { all_tags.clear(); }
+    void _set_tag_density(unsigned int d);      // hashgraph.hh:128-135: even, and only while no tag exists
+    unsigned int _get_tag_density() const { return _tag_density; }
+    void save_tagset(std::string filename);     // hashgraph.cc:55-88
+    void load_tagset(std::string filename, bool clear_tags = true);
+
 private:
     template <typename SeqIO>
     void bulk_consume(read_parsers::ReadParserPtr<SeqIO>& parser, const uint64_t* band, Hashtable* mask, unsigned int threshold,
                       bool consume_masked, unsigned int& total_reads, unsigned long long& n_consumed);
+    void tag_batch(const char* seqs, const uint64_t* offsets, size_t n_reads, unsigned long long& n_consumed);
+    std::set<HashIntoType> all_tags;
+    unsigned int _tag_density = 40;   // DEFAULT_TAG_DENSITY (include/oxli/oxli.hh:83)
+    std::mutex tags_mu;
 };
 
 // class shells: (hash function, storage) pairs — hashgraph.hh:273-296, hashtable.hh:591-627

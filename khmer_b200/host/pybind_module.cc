@@ -245,6 +245,33 @@ PYBIND11_MODULE(_oxli, m)
             }
             return out;
         })
+        .def("consume_seqfile_and_tag", [](Hashtable& h, py::object file_or_parser) {
+            // graphs.pyx:588-600: (total_reads, n_consumed) with n_consumed = the NEW k-mers
+            unsigned int total_reads = 0;
+            unsigned long long n_consumed = 0;
+            if (py::isinstance<py::str>(file_or_parser)) {
+                std::string fn = file_or_parser.cast<std::string>();
+                py::gil_scoped_release nogil;
+                h.consume_seqfile_and_tag<FastxReader>(fn, total_reads, n_consumed);
+            } else {
+                PyParser& p = file_or_parser.cast<PyParser&>();
+                py::gil_scoped_release nogil;
+                h.consume_seqfile_and_tag<FastxReader>(p.parser, total_reads, n_consumed);
+            }
+            return py::make_tuple(total_reads, n_consumed);
+        })
+        .def("consume_and_tag", [](Hashtable& h, const std::string& seq) {
+            unsigned long long n = 0;
+            h.consume_sequence_and_tag(seq, n);
+            return n;
+        })
+        .def("n_tags", &Hashtable::n_tags)
+        .def("get_tagset", [](Hashtable& h) { return std::vector<HashIntoType>(h.tags().begin(), h.tags().end()); })
+        .def("add_tag", [](Hashtable& h, py::object kmer) { h.add_tag(sanitize_hash_kmer(h, kmer)); })
+        .def("save_tagset", &Hashtable::save_tagset)
+        .def("load_tagset", &Hashtable::load_tagset, py::arg("filename"), py::arg("clear_tags") = true)
+        .def("_get_tag_density", &Hashtable::_get_tag_density)
+        .def("_set_tag_density", &Hashtable::_set_tag_density)
         .def("normalize_batch", [](Hashtable& h, const std::vector<std::string>& seqs, unsigned cutoff, const std::vector<uint8_t>& paired) {
             std::vector<uint8_t> keep;
             unsigned long long kmers;

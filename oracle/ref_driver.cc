@@ -277,4 +277,38 @@ int64_t ref_parse_clean(const char* fn, char* seq_out, uint64_t seq_cap, uint64_
     REF_CATCH(-1)
 }
 
+// tagging (Hashgraph): khmer/_oxli/graphs.pyx:588-600, :630-637 — only for kinds 0..2 (the *graph classes)
+int ref_consume_seqfile_and_tag(void* h, const char* fn, uint64_t* reads, uint64_t* n_consumed_out)
+{
+    REF_TRY
+    Hashgraph* hg = dynamic_cast<Hashgraph*>((Hashtable*)h);
+    if (!hg) { g_err = "not a Hashgraph"; return -1; }
+    unsigned int total_reads = 0;
+    unsigned long long n_consumed = 0;
+    hg->consume_seqfile_and_tag<FastxReader>(std::string(fn), total_reads, n_consumed);
+    *reads = total_reads;
+    *n_consumed_out = n_consumed;
+    return 0;
+    REF_CATCH(-1)
+}
+
+int64_t ref_n_tags(void* h)
+{
+    REF_TRY
+    Hashgraph* hg = dynamic_cast<Hashgraph*>((Hashtable*)h);
+    if (!hg) { g_err = "not a Hashgraph"; return -1; }
+    return (int64_t)hg->n_tags();
+    REF_CATCH(-1)
+}
+
+int ref_save_tagset(void* h, const char* fn)
+{
+    REF_TRY
+    Hashgraph* hg = dynamic_cast<Hashgraph*>((Hashtable*)h);
+    if (!hg) { g_err = "not a Hashgraph"; return -1; }
+    hg->save_tagset(fn);
+    return 0;
+    REF_CATCH(-1)
+}
+
 }  // extern "C"

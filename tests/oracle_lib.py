@@ -319,6 +319,11 @@ def ref_lib():
         L.ref_hash_twobit.argtypes = [C.c_char_p, C.c_int, u64p, u64p, u64p]
         L.ref_hash_murmur.argtypes = [C.c_char_p, C.c_int, u64p, u64p, u64p]
         L.ref_revhash.argtypes = [C.c_uint64, C.c_int, C.c_char_p]
+        if hasattr(L, "ref_n_tags"):   # a prebuilt library from before the tagging wrappers lacks them
+            L.ref_consume_seqfile_and_tag.argtypes = [C.c_void_p, C.c_char_p, u64p, u64p]
+            L.ref_n_tags.restype = C.c_int64
+            L.ref_n_tags.argtypes = [C.c_void_p]
+            L.ref_save_tagset.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_parse_clean.restype = C.c_int64
         L.ref_parse_clean.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, u64p, C.c_uint64, u64p]
         _ref = L
@@ -359,6 +364,17 @@ class Ref:
         r, k = C.c_uint64(), C.c_uint64()
         self._chk(self.L.ref_consume_seqfile(self.h, _b(path), threads, C.byref(r), C.byref(k)))
         return r.value, k.value
+
+    def consume_seqfile_and_tag(self, path):
+        r, k = C.c_uint64(), C.c_uint64()
+        self._chk(self.L.ref_consume_seqfile_and_tag(self.h, _b(path), C.byref(r), C.byref(k)))
+        return r.value, k.value
+
+    def n_tags(self):
+        return self._chk(self.L.ref_n_tags(self.h))
+
+    def save_tagset(self, path):
+        self._chk(self.L.ref_save_tagset(self.h, _b(path)))
 
     def consume_seqfile_banding(self, path, num_bands, band):
         r, k = C.c_uint64(), C.c_uint64()

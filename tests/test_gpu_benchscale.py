@@ -56,6 +56,17 @@ def _ct_bigcounts(path, sizes):
 
 
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref (compiled reference) not present")
+def test_bench_scale_parity_grouped_path(tmp_path):
+    """the same comparison with the fused grouping kernel (k_part + k_apply2) instead of bins[] + k_bucketize + k_apply"""
+    import subprocess
+    import sys
+    env = dict(os.environ, KMGPU_PREFER_BINS="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_bench_scale_parity_with_compiled_reference"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref (compiled reference) not present")
 def test_bench_scale_parity_with_compiled_reference(tmp_path):
     from khmer_b200 import cabi
     n_reads = 1_000_000

@@ -48,6 +48,16 @@ def test_gpu_golden_cases_cas_single_pass():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_gpu_golden_cases_grouped_path():
+    """The large-table goldens (C1 and the other 25k cases, 1e8-bin tables) through the grouped path (fused hash + grouping); by
+    default these shapes take the bins[] + k_bucketize path."""
+    import subprocess, sys
+    env = dict(os.environ, KMGPU_PREFER_BINS="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_gpu_matches_reference_golden and (C1 or 25k)"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_gpu_golden_cases_delta_many_blocks():
     """All reference goldens through the delta+fold path with ~2k-bin blocks (many blocks per table)."""
     import subprocess, sys

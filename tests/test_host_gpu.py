@@ -328,3 +328,56 @@ def test_trim_functions_against_oracle_counts():
             assert g.trim_below_abundance(q, thr) == (q[:pos], pos)
     seq = "ACGTACGTAAGGTTCCTTTTTTTTTTTTACGTACGT"
     assert g.find_spectral_error_positions(seq, 1) == [16]      # hashtable.cc:565-612 walked by hand
+
+
+@pytest.mark.parametrize("cls,fn,k", [("Nodegraph", "random-20-a.fa", 20), ("Countgraph", "synth-err-n.fa", 21),
+                                      ("SmallCountgraph", "lowcomplexity.fa", 12), ("Nodegraph", "25k.fq.gz", 32)])
+def test_consume_seqfile_and_tag_against_live_reference(datadir, tmp_path, cls, fn, k):
+    """load-graph.py's default path (oxli/functions.py:57-66 -> Hashgraph::consume_seqfile_and_tag, src/oxli/hashgraph.cc:200-320):
+    counters and is-new bits from the device, the tag scan on the host; tag count, n_consumed (= new k-mers) and the saved
+    tagset are the compiled reference's, byte for byte."""
+    if not ol.have_ref() or not hasattr(ol.ref_lib(), "ref_n_tags"):
+        pytest.skip("compiled reference with the tagging wrappers not shipped")
+    kh = _kh()
+    sizes = ol.primes_near_x(4, 2e5 if fn != "25k.fq.gz" else 4e6)
+    path = os.path.join(datadir, fn)
+    g = getattr(kh, cls)(k, 1, 1, primes=sizes)
+    r = ol.Ref(cls, k, sizes)
+    assert g.consume_seqfile_and_tag(path) == r.consume_seqfile_and_tag(path)
+    assert g.n_tags() == r.n_tags() and g.n_tags() > 0
+    assert g.n_unique_kmers() == r.n_unique_kmers() and g.n_occupied() == r.n_occupied()
+    a, b = str(tmp_path / "a.tagset"), str(tmp_path / "b.tagset")
+    g.save_tagset(a)
+    r.save_tagset(b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    g2 = getattr(kh, cls)(k, 1, 1, primes=sizes)
+    g2.load_tagset(a)
+    assert g2.n_tags() == g.n_tags() and g2._get_tag_density() == 40
+    assert [bytes(v) for v in g.get_raw_tables()] == [r.table(i).tobytes() for i in range(4)]
+
+
+def test_normalize_batch_reference_md5(datadir):
+    """scripts/normalize-by-median.py -k 21 -C 20 -M 1e7 on simple-genome-reads.fa (tests/test_script_output.py:51-59) through
+    the host layer's batch entry: the kept records written as the script writes them have the reference's md5."""
+    kh = _kh()
+    recs, name = [], None
+    for ln in open(os.path.join(datadir, "simple-genome-reads.fa")):
+        ln = ln.rstrip("\n")
+        if ln.startswith(">"):
+            name = ln[1:]
+        else:
+            recs.append((name, ln))
+    g = kh.Countgraph(21, 1e7 / 4, 4)
+    keep, kmers = g.normalize_batch([s.upper().replace("N", "A") for _, s in recs], 20)
+    out = "".join(">%s\n%s\n" % (n, s) for (n, s), k in zip(recs, keep) if k)
+    assert hashlib.md5(out.encode()).hexdigest() == "942e9024c25a8d85033d755d86aba4a3"
+    assert kmers == sum(len(s) - 20 for (_, s), k in zip(recs, keep) if k)
+
+
+def test_ascii_feed_still_matches(golden, datadir):
+    """the host feed packs reads to 2 bits on the parser threads by default; KMGPU_FEED_PACKED=0 ships ASCII and packs on the device"""
+    import subprocess, sys
+    env = dict(os.environ, KMGPU_FEED_PACKED="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_consume_seqfile_save_matches_reference and (C1 or syn-ct or ragged)"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
