@@ -156,6 +156,11 @@ int kmgpu_read_medians(kmgpu_t* h, const char* seqs, const uint64_t* offsets, ui
 int kmgpu_median_at_least(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads,
                           uint32_t flags, uint32_t cutoff, uint8_t* out);
 
+/* Hashtable::trim_on_abundance (below == 0: cut at the first k-mer with count < abund) / trim_below_abundance (below != 0: at the
+ * first with count > abund) for a batch (src/oxli/hashtable.cc:504-560): trim_pos_out[r] = the length read r keeps. */
+int kmgpu_trim_batch(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
+                     uint32_t abund, int below, uint32_t* trim_pos_out);
+
 /* Hashtable::abundance_distribution (src/oxli/hashtable.cc:451-493): for every k-mer in stream order,
  * if `tracking` does not hold it, add it there and bump hist[count in `counts`].  hist (65536 entries)
  * is ACCUMULATED into, so a file can be fed in several calls. */

@@ -28,7 +28,7 @@ SYMBOLS = [
     "kmgpu_set_use_bigcount", "kmgpu_get_use_bigcount", "kmgpu_consume_reads", "kmgpu_consume_packed",
     "kmgpu_batch_create", "kmgpu_batch_destroy", "kmgpu_batch_info", "kmgpu_consume_batch", "kmgpu_add_hashes",
     "kmgpu_get_counts", "kmgpu_kmer_counts", "kmgpu_kmer_hashes", "kmgpu_read_medians", "kmgpu_median_at_least",
-    "kmgpu_abundance_distribution", "kmgpu_normalize_batch", "kmgpu_consume_reads_new", "kmgpu_first_touch_log",
+    "kmgpu_abundance_distribution", "kmgpu_trim_batch", "kmgpu_normalize_batch", "kmgpu_consume_reads_new", "kmgpu_first_touch_log",
     "kmgpu_first_touch_resolve", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
     "kmgpu_table_nbytes", "kmgpu_download_table", "kmgpu_upload_table", "kmgpu_bigcount_size",
     "kmgpu_bigcount_export", "kmgpu_bigcount_import", "kmgpu_merge", "kmgpu_recount_occupied", "kmgpu_ipc_export",
@@ -90,6 +90,7 @@ def lib():
                                             C.c_void_p]
         L.kmgpu_abundance_distribution.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                    C.c_uint32, C.c_void_p]
+        L.kmgpu_trim_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
         L.kmgpu_normalize_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
                                             C.c_void_p, u64p, u64p]
         L.kmgpu_consume_reads_new.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, u64p, u64p]
@@ -320,6 +321,14 @@ class Sketch:
         check(lib().kmgpu_abundance_distribution(self.h, tracking.h, _ptr(buf), _ptr(off), len(off) - 1,
                                                  CLEAN if clean else 0, _ptr(hist)))
         return hist
+
+    def trim_batch(self, reads, abund, below=False, clean=False):
+        """trim_on_abundance (below=False) / trim_below_abundance (below=True) per read: the length each read keeps"""
+        buf, off = as_reads(reads)
+        nr = len(off) - 1
+        out = np.zeros(max(nr, 1), dtype=np.uint32)
+        check(lib().kmgpu_trim_batch(self.h, _ptr(buf), _ptr(off), nr, CLEAN if clean else 0, int(abund), int(below), _ptr(out)))
+        return out[:nr]
 
     def consume_reads_new(self, reads, clean=True):
         """consume + one flag per base: 1 where the k-mer starting there was new in stream order (Storage::add's bool).

@@ -217,6 +217,7 @@ struct kmgpu_sketch {
     uint64_t ft_pending = 0, ft_epoch_unique = 0;
     uint32_t ft_chunk = 0;
     uint64_t n_regroups = 0;
+    uint64_t chunk_cap = 0;                 // positions per chunk (sketch_chunk_bases)
     bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
     DevBuf<uint16_t> d_delta;
@@ -1676,7 +1677,7 @@ static int consume_host(kmgpu_t* h, const char* seqs, const uint64_t* packed, ui
         // staging slot per part, two sets of slots: the next chunk's parts are queued while this chunk is being applied).
         std::vector<DeltaPass> dp;
         BucketLayout BL;
-        const uint64_t total = last - first, cap = chunk_bases();
+        const uint64_t total = last - first, cap = sketch_chunk_bases(h);
         const uint64_t n_chunks = (total + cap - 1) / cap;
         const uint64_t per_chunk = (((total + n_chunks - 1) / n_chunks) + 31) & ~31ull;
         // parts start on word boundaries of the stream (packed input is uploaded word-wise)
@@ -1743,10 +1744,10 @@ static int consume_host(kmgpu_t* h, const char* seqs, const uint64_t* packed, ui
     // (half of the others when the cap leaves that freedom) and the copy of chunk i+1 hides behind the ingest of chunk i.
     std::vector<uint64_t> starts(1, 0);
     if (packed || newbits_out) {
-        balanced_chunks(last - first, chunk_bases(), starts);   // packed input / per-base result bits: chunks cut on word boundaries
+        balanced_chunks(last - first, sketch_chunk_bases(h), starts);   // packed input / per-base result bits: chunks cut on word boundaries
     } else {
         // one chunk more than a device-resident batch would get as soon as that leaves chunk 0 at most half of the others
-        const uint64_t total = last - first, cap = chunk_bases(), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
+        const uint64_t total = last - first, cap = sketch_chunk_bases(h), n = (2 * total + cap + 2 * cap - 1) / (2 * cap);
         bool ramp = false;
         if (n >= 2 && 2 * total <= (n + 1) * cap) {
             // sizes 1 : 2 : ... : n — the copy of every chunk still hides behind the ingest of the one before it (PCIe
@@ -1949,15 +1950,32 @@ extern "C" int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmg
     CKR(make_pred(h, band, mask, &P, &pred, &M));
     HashCfg H{h->hash, h->k};
     ChunkResult res;
-    for (const auto& p : b->pieces) {
-        ChunkDev cd;
-        cd.words = p.words;
-        cd.offs = p.offs;
-        cd.tfr = p.tfr;
-        cd.valid = p.valid;
-        cd.n_reads = p.n_reads;
-        cd.n_pos = p.n_pos;
-        CKR(ingest_chunk(h, 0, H, make_input(cd), P, pred, M, &res));
+    const uint64_t cap = sketch_chunk_bases(h);
+    for (size_t i = 0; i < b->pieces.size();) {
+        // a sketch that prefers larger chunks (two-level grouped path) takes several pieces of the batch as the parts of one chunk
+        std::vector<Part> parts;
+        uint64_t pos = 0;
+        size_t j = i;
+        while (j < b->pieces.size() && (j == i || pos + b->pieces[j].n_pos <= cap)) {
+            const auto& p = b->pieces[j];
+            ChunkDev cd;
+            cd.words = p.words;
+            cd.offs = p.offs;
+            cd.tfr = p.tfr;
+            cd.valid = p.valid;
+            cd.n_reads = p.n_reads;
+            cd.n_pos = p.n_pos;
+            parts.push_back(Part{make_input(cd), (uint32_t)pos, nullptr});
+            pos += p.n_pos;
+            j++;
+        }
+        GroupPlan G;
+        if (parts.size() > 1 && pos < (1ull << 31) && plan_group(h, (uint32_t)pos, h->nt > F_MAXT || h->ft_on, &G)) {
+            CKR(ingest_chunk_grouped(h, G, 0, H, parts, P, pred, M, &res, Between()));
+        } else {
+            for (const Part& pt : parts) CKR(ingest_chunk(h, 0, H, pt.in, P, pred, M, &res));
+        }
+        i = j;
     }
     if (n_kmers_out) *n_kmers_out = res.n_kmers;
     return KMGPU_OK;
@@ -2158,6 +2176,41 @@ extern "C" int kmgpu_median_at_least(kmgpu_t* h, const char* seqs, const uint64_
     return per_read_query(h, seqs, offsets, n_reads, flags, nullptr, nullptr, nullptr, nullptr, true, cutoff, out);
 }
 
+extern "C" int kmgpu_trim_batch(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags, uint32_t abund, int below,
+                                uint32_t* trim_pos_out)
+{
+    if (!h) return fail(KMGPU_EINVAL, "null handle");
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets || !trim_pos_out) return fail(KMGPU_EINVAL, "null argument");
+    for (uint64_t r = 0; r < n_reads; r++)
+        if (offsets[r + 1] - offsets[r] > chunk_bases())
+            return fail(KMGPU_EUNSUPPORTED, "read %llu is longer than a device chunk", (unsigned long long)r);
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+    const uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+    const HashCfg H{h->hash, h->k};
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
+    uint64_t r0 = 0;
+    cudaStream_t st = h->stream;
+    for (const ChunkPlan& c : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
+        const uint32_t nr = cd.n_reads;
+        CKR(h->d_counts.ensure(std::max<uint32_t>(cd.n_pos, 1)));
+        if (cd.n_pos) launch_counts(0, h->dev, H, make_input(cd), h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr, st);
+        CKR(h->d_stat_n.ensure(nr));
+        k_trim_scan<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, abund, below, h->d_stat_n.p);
+        h->all_launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(trim_pos_out + r0, h->d_stat_n.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        r0 += nr;
+    }
+    return KMGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // abundance distribution
 // ------------------------------------------------------------------------------------------------------
@@ -2246,7 +2299,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     // reads per window: fixed by KMGPU_NORM_WINDOW, else adapted so that only a small share of a window's bundles is "in between"
     // (their number grows with the coverage a window adds; they are resolved one by one on the host)
     const uint64_t W_fixed = env_u64("KMGPU_NORM_WINDOW", 0);
-    uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 4096;
+    uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 16384;
     const uint64_t max_bases = chunk_bases() / 2;
     Pred P0;
     memset(&P0, 0, sizeof P0);
@@ -2355,8 +2408,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                 }
                 keep = sure;
                 if (!W_fixed) {
-                    if (n_unsure * 50 > nr) W = std::max<uint64_t>(256, W / 2);          // more than 2 % in between: smaller windows
-                    else if (n_unsure * 200 < nr) W = std::min<uint64_t>(1u << 17, W * 2);   // under 0.5 %: larger ones
+                    // a window costs ~1 ms of launches and round trips whatever its size, an in-between read ~10 us of host work:
+                    // aim at a few hundred in-between reads per window
+                    if (n_unsure > 600) W = std::max<uint64_t>(1024, W / 2);
+                    else if (n_unsure < 150) W = std::min<uint64_t>(1u << 18, W * 2);
                 }
                 if (n_unsure) {
                     // 3. in-between bundles, in stream order: the state each of them meets is the window's start + the reads kept
@@ -2943,7 +2998,8 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
         nominal_shape.nt = n_tables;
         nominal_shape.kind = storage;
         for (int i = 0; i < n_tables; i++) nominal_shape.sizes[i] = nominal[i];
-        const bool ok = plan_group(&nominal_shape, (uint32_t)max_positions, true, &s->G, true);
+        const bool ok = plan_group(&nominal_shape, (uint32_t)max_positions, true, &s->G, true, (uint32_t)(PART_MAXP / world),
+                                   (uint64_t)world * max_positions);
         if (!ok || !s->G.L.two_level) {
             kmgpu_shard_destroy(s);
             return fail(KMGPU_EUNSUPPORTED, "slices of this size cannot be grouped");

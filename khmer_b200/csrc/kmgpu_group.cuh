@@ -25,8 +25,7 @@
 namespace kmgpu {
 
 constexpr int G_MAXT = MAX_TABLES;                       // tables per sketch on this path
-constexpr int SB_SHIFT = 12;                             // buckets per super-bucket (two-level grouping)
-constexpr int SB_BIN_SHIFT = BKT_SHIFT + SB_SHIFT;       // 27: bins per super-bucket
+constexpr int SB_SHIFT_MAX = 12;                         // at most 4096 buckets (2^27 bins) per super-bucket (two-level grouping)
 constexpr int PART_MAXP = 6144;                          // partitions one k_part CTA can sort into (shared-memory histogram)
 
 struct GroupLayout {
@@ -36,6 +35,8 @@ struct GroupLayout {
     uint32_t cap1;                   // home region of a super-bucket
     int n_tables;
     int two_level;
+    int sb_shift;                    // log2(buckets per super-bucket): chosen so that both levels sort into about sqrt(buckets)
+                                     // partitions (runs stay long at both levels); records of level 1 carry 15 + sb_shift bin bits
 };
 
 struct SatBitsG {
@@ -211,7 +212,8 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     constexpr bool WIDE = MODE == 1 || MODE == 3 || WIDEP;
     constexpr int PER = T / NTHR;
     constexpr bool SBMODE = MODE == 1 || MODE == 3;            // partitions are super-buckets
-    constexpr int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;      // payload bits of the records written
+    const int SB_SHIFT = A.L.sb_shift, SB_BIN_SHIFT = BKT_SHIFT + SB_SHIFT;
+    const int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;          // payload bits of the records written
     extern __shared__ __align__(16) unsigned char pt_raw[];
     uint2* stage = reinterpret_cast<uint2*>(pt_raw);                          // T slots, grouped by partition
     uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // PART_MAXP: count, then run start | cursor base << 16
@@ -518,7 +520,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
         uint4* f = reinterpret_cast<uint4*>(minpos);
         for (uint32_t i = tid; i < BKT_BINS / 4; i += 1024) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
-    mbar_wait(bar, 0);
+    if (gate) mbar_wait(bar, 0);   // ungated: the slice is first needed by the sweep, its load hides behind the record loop
     constexpr int GPT = BKT_BINS / 8 / 1024;
     if (KIND != BIT) {
         // touch lanes start at 0, with bit 15 set for bins that hold a count already: the value atomicAdd returns then tells
@@ -568,19 +570,23 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
                 atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
             }
         }
-        if (KIND != BIT && n > 32767u) {
-            // more records than a 15-bit lane can count: clamp every lane to 0x3FFF after each 16 Ki records (any value >= the
-            // counter's cap saturates it just the same), so the next 16 Ki cannot carry into the flag bit or the neighbour
+        // More records than a lane can count (15 bits when bit 15 is the "was occupied" flag, else 16): clamp every lane after each
+        // 16 Ki (32 Ki) records to a value the next round cannot push into the flag bit or the neighbouring lane — any value >=
+        // the counter's cap saturates it just the same.
+        const bool clamp_now = gate ? n > 32767u : (n > 65535u && ((e0 / (RIF * 1024)) & 1u));
+        if (KIND != BIT && clamp_now) {
+            const uint32_t lim = gate ? 0x3FFFu : 0x7FFFu, keep = gate ? 0x80008000u : 0u, msk = gate ? 0x7FFFu : 0xFFFFu;
             __syncthreads();
             for (uint32_t i = tid; i < BKT_BINS / 2; i += 1024) {
                 const uint32_t w = cnt[i];
-                const uint32_t lo = w & 0x7FFFu, hi = (w >> 16) & 0x7FFFu;
-                cnt[i] = (w & 0x80008000u) | (lo > 0x3FFFu ? 0x3FFFu : lo) | ((hi > 0x3FFFu ? 0x3FFFu : hi) << 16);
+                const uint32_t lo = w & msk, hi = (w >> 16) & msk;
+                cnt[i] = (w & keep) | (lo > lim ? lim : lo) | ((hi > lim ? lim : hi) << 16);
             }
             __syncthreads();
         }
     }
     __syncthreads();
+    if (!gate) mbar_wait(bar, 0);
     unsigned n_new = 0, n_sat = 0, n_cross = 0;
 #pragma unroll
     for (int q = 0; q < GPT; q++) {
@@ -591,7 +597,8 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             const uint4 m0 = reinterpret_cast<const uint4*>(minpos)[g * 2], m1 = reinterpret_cast<const uint4*>(minpos)[g * 2 + 1];
             const uint32_t mp[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) newm |= (unsigned)(mp[j] != ~0u) << j;   // only bins that were clear carry a position
+            for (int j = 0; j < 8; j++) newm |= (unsigned)(mp[j] != ~0u) << j;   // touched bins ...
+            newm &= ~(unsigned)slice[g];                                         // ... that were clear
             if (!newm) continue;
             changed = 1;
             slice[g] = (uint8_t)(slice[g] | newm);
@@ -605,7 +612,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             continue;
         }
         uint4 c4 = reinterpret_cast<const uint4*>(cnt)[g];
-        c4.x &= 0x7FFF7FFFu; c4.y &= 0x7FFF7FFFu; c4.z &= 0x7FFF7FFFu; c4.w &= 0x7FFF7FFFu;   // touches without the "was occupied" flags
+        if (gate) { c4.x &= 0x7FFF7FFFu; c4.y &= 0x7FFF7FFFu; c4.z &= 0x7FFF7FFFu; c4.w &= 0x7FFF7FFFu; }   // touches without the "was occupied" flags
         if (!(c4.x | c4.y | c4.z | c4.w)) continue;
         const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
         unsigned crossm = 0;

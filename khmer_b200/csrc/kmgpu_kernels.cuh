@@ -645,6 +645,31 @@ k_read_stats(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ o
     }
 }
 
+// Hashtable::trim_on_abundance / trim_below_abundance (src/oxli/hashtable.cc:504-560) for a batch, one warp per read, over the
+// per-position counts: the length the read keeps.  below == 0: a k-mer is bad when count < abund; below != 0: when count > abund.
+// No k-mer, a single k-mer, or a bad first k-mer: 0.  First bad k-mer at index i >= 1: k - 1 + i.  None: the whole read.
+__global__ void __launch_bounds__(256)
+k_trim_scan(const uint16_t* __restrict__ counts, const uint32_t* __restrict__ offs, uint32_t n_reads, int k, uint32_t abund, int below,
+            uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_reads) return;
+    const uint32_t s = offs[r], e = offs[r + 1], len = e - s;
+    const uint32_t n = len >= (uint32_t)k ? len - k + 1 : 0;
+    uint32_t first_bad = 0xFFFFFFFFu;
+    const uint16_t* c = counts + s;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t v = c[i];
+        if (below ? v > abund : v < abund) {
+            first_bad = i;
+            break;
+        }
+    }
+    first_bad = __reduce_min_sync(0xffffffffu, first_bad);
+    if (lane == 0) out[r] = n <= 1 || first_bad == 0 ? 0u : first_bad == 0xFFFFFFFFu ? len : (uint32_t)k - 1 + first_bad;
+}
+
 // ---- host feed: ASCII -> 2-bit stream -----------------------------------------------------------------
 // One thread per output word (32 bases).  clean != 0: Read::set_clean_seq then twobit_repr
 // (read_parsers.cc:53-69, kmer_hash.hh:70-72): A/a 0, T/t 1, C/c 2, G/g 3, anything else 0 ('A').

@@ -818,7 +818,7 @@ std::vector<unsigned int> Hashtable::find_spectral_error_positions(std::string s
 static uint64_t feed_bases()
 {
     const char* e = getenv("KMGPU_FEED_BASES");
-    return e && *e ? strtoull(e, nullptr, 10) : (64ull << 20);
+    return e && *e ? strtoull(e, nullptr, 10) : (144ull << 20);   // about one device chunk per batch (a chunk costs one pass over the sketch)
 }
 
 template <typename SeqIO>

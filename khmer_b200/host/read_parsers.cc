@@ -52,11 +52,51 @@ void Read::set_clean_seq()
     }
 }
 
+// Page-locking memory costs milliseconds per call, a batch buffer is needed per bulk call and thread: released buffers are kept
+// (a handful, the largest ones) and handed out again.
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<char*, size_t>> free_list;
+    ~PinnedPool()
+    {
+        // the CUDA context may be gone at exit: leave the pages to the process teardown
+    }
+    char* take(size_t want, size_t* got)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].second >= want) {
+                char* p = free_list[i].first;
+                *got = free_list[i].second;
+                free_list.erase(free_list.begin() + i);
+                return p;
+            }
+        return nullptr;
+    }
+    bool give(char* p, size_t cap)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.size() >= 8) return false;
+        free_list.push_back(std::make_pair(p, cap));
+        return true;
+    }
+};
+PinnedPool& pinned_pool()
+{
+    static PinnedPool* p = new PinnedPool();   // never destroyed: see ~PinnedPool
+    return *p;
+}
+}  // namespace
+
 ReadBatch::~ReadBatch()
 {
     if (seqs) {
-        if (pinned) kmgpu_free_pinned(seqs);
-        else free(seqs);
+        if (pinned) {
+            if (!pinned_pool().give(seqs, cap)) kmgpu_free_pinned(seqs);
+        } else {
+            free(seqs);
+        }
     }
 }
 
@@ -66,13 +106,24 @@ void ReadBatch::reserve(size_t n_want_bases)
     if (n <= cap) return;
     size_t want = std::max(n, cap + cap / 2);
     void* np = nullptr;
-    bool np_pinned = kmgpu_alloc_pinned(want, &np) == 0 && np;   // no device: plain memory still parses
-    if (!np_pinned) np = malloc(want);
+    size_t got = 0;
+    bool np_pinned = false;
+    if (char* pooled = pinned_pool().take(want, &got)) {
+        np = pooled;
+        want = got;
+        np_pinned = true;
+    } else {
+        np_pinned = kmgpu_alloc_pinned(want, &np) == 0 && np;   // no device: plain memory still parses
+        if (!np_pinned) np = malloc(want);
+    }
     if (!np) throw std::bad_alloc();
     if (n_bases) memcpy(np, seqs, pack ? (n_bases + 31) / 32 * 8 : n_bases);
     if (seqs) {
-        if (pinned) kmgpu_free_pinned(seqs);
-        else free(seqs);
+        if (pinned) {
+            if (!pinned_pool().give(seqs, cap)) kmgpu_free_pinned(seqs);
+        } else {
+            free(seqs);
+        }
     }
     seqs = (char*)np;
     cap = want;

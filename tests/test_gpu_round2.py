@@ -173,3 +173,23 @@ def test_mask_sketch_with_bigcount_counts_above_255():
                     want += 1
         assert n == want
         _same(g, o, 3)
+
+
+def test_trim_batch_matches_reference_semantics():
+    """Hashtable::trim_on_abundance / trim_below_abundance (src/oxli/hashtable.cc:504-560) for a batch, against the oracle's counts"""
+    k, sizes = 17, ol.primes_near_x(3, 50000)
+    g, o = make_gpu("Countgraph", k, sizes), ol.Oracle("Countgraph", k, sizes)
+    reads = synth_reads(3, 800, 90, 1500, err=0.03)
+    g.consume_reads(reads)
+    o.consume_reads(reads)
+    queries = synth_reads(4, 300, 90, 1500, err=0.05) + ["ACGT", "A" * 17, "A" * 18, ""]
+    for abund, below in ((3, False), (8, False), (5, True), (40, True)):
+        got = g.trim_batch(queries, abund, below=below)
+        for q, pos in zip(queries, got):
+            c = o.kmer_counts(q).tolist() if len(q) >= k else []
+            bad = (lambda v: v > abund) if below else (lambda v: v < abund)
+            if len(c) <= 1 or bad(c[0]):
+                want = 0
+            else:
+                want = next((k - 1 + i for i in range(1, len(c)) if bad(c[i])), len(q))
+            assert pos == want, (q, abund, below)

@@ -331,11 +331,12 @@ def test_trim_functions_against_oracle_counts():
 
 
 @pytest.mark.parametrize("cls,fn,k", [("Nodegraph", "random-20-a.fa", 20), ("Countgraph", "synth-err-n.fa", 21),
-                                      ("SmallCountgraph", "lowcomplexity.fa", 12), ("Nodegraph", "25k.fq.gz", 32)])
+                                      ("SmallCountgraph", "lowcomplexity.fa", 12), ("Nodegraph", "25k.fq.gz", 20)])
 def test_consume_seqfile_and_tag_against_live_reference(datadir, tmp_path, cls, fn, k):
     """load-graph.py's default path (oxli/functions.py:57-66 -> Hashgraph::consume_seqfile_and_tag, src/oxli/hashgraph.cc:200-320):
     counters and is-new bits from the device, the tag scan on the host; tag count, n_consumed (= new k-mers) and the saved
-    tagset are the compiled reference's, byte for byte."""
+    tagset are the compiled reference's, byte for byte.  (Inputs without reads shorter than k: for those the reference inserts an
+    uninitialised hash value as a tag, hashgraph.cc:207,263-266 — undefined behaviour this layer does not reproduce.)"""
     if not ol.have_ref() or not hasattr(ol.ref_lib(), "ref_n_tags"):
         pytest.skip("compiled reference with the tagging wrappers not shipped")
     kh = _kh()
