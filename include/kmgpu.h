@@ -128,6 +128,10 @@ int kmgpu_batch_destroy(kmgpu_batch_t* b);
 int kmgpu_batch_info(const kmgpu_batch_t* b, uint64_t* n_reads, uint64_t* n_bases, uint64_t* device_bytes);
 int kmgpu_consume_batch(kmgpu_t* h, const kmgpu_batch_t* b, const kmgpu_band_t* band,
                         const kmgpu_mask_t* mask, uint64_t* n_kmers_out);
+/* kmgpu_read_medians over a device-resident batch (no upload inside the call): one entry per read of the batch in the four
+ * output arrays (each may be NULL).  Fails with KMGPU_EUNSUPPORTED when the batch holds a read longer than a device chunk. */
+int kmgpu_batch_read_medians(kmgpu_t* h, const kmgpu_batch_t* b, uint16_t* median_out, float* average_out, float* stddev_out,
+                             uint32_t* n_kmers_out);
 
 /* Hashtable::add(HashIntoType) / count (hashtable.hh:222-237): add already-hashed k-mers in order;
  * is_new_out[i] (nullable) = the bool Storage::add returns for the i-th hash. */

@@ -26,7 +26,7 @@ f32p = C.POINTER(C.c_float)
 SYMBOLS = [
     "kmgpu_last_error", "kmgpu_abi_version", "kmgpu_device_count", "kmgpu_create", "kmgpu_destroy",
     "kmgpu_set_use_bigcount", "kmgpu_get_use_bigcount", "kmgpu_consume_reads", "kmgpu_consume_packed",
-    "kmgpu_batch_create", "kmgpu_batch_destroy", "kmgpu_batch_info", "kmgpu_consume_batch", "kmgpu_add_hashes",
+    "kmgpu_batch_create", "kmgpu_batch_destroy", "kmgpu_batch_info", "kmgpu_consume_batch", "kmgpu_batch_read_medians", "kmgpu_add_hashes",
     "kmgpu_get_counts", "kmgpu_kmer_counts", "kmgpu_kmer_hashes", "kmgpu_read_medians", "kmgpu_median_at_least",
     "kmgpu_abundance_distribution", "kmgpu_trim_batch", "kmgpu_normalize_batch", "kmgpu_consume_reads_new", "kmgpu_first_touch_log",
     "kmgpu_first_touch_resolve", "kmgpu_stats", "kmgpu_set_stats", "kmgpu_shape", "kmgpu_set_ksize",
@@ -80,6 +80,7 @@ def lib():
         L.kmgpu_batch_destroy.argtypes = [C.c_void_p]
         L.kmgpu_batch_info.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.kmgpu_consume_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Band), C.POINTER(Mask), u64p]
+        L.kmgpu_batch_read_medians.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kmgpu_add_hashes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.kmgpu_get_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.kmgpu_kmer_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, u64p]
@@ -305,6 +306,16 @@ class Sketch:
         nk = np.zeros(nr, dtype=np.uint32)
         check(lib().kmgpu_read_medians(self.h, _ptr(buf), _ptr(off), nr, CLEAN if clean else 0, _ptr(med), _ptr(avg),
                                        _ptr(sd), _ptr(nk)))
+        return med, avg, sd, nk
+
+    def batch_read_medians(self, batch, stats=True):
+        """read_medians over a device-resident Batch (no upload inside the call); stats=False: medians only"""
+        nr = batch.info()[0]
+        med = np.zeros(nr, dtype=np.uint16)
+        avg = np.zeros(nr, dtype=np.float32) if stats else None
+        sd = np.zeros(nr, dtype=np.float32) if stats else None
+        nk = np.zeros(nr, dtype=np.uint32) if stats else None
+        check(lib().kmgpu_batch_read_medians(self.h, batch.h, _ptr(med), _ptr(avg), _ptr(sd), _ptr(nk)))
         return med, avg, sd, nk
 
     def median_at_least(self, reads, cutoff, clean=False):

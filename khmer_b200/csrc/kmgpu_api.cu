@@ -206,8 +206,11 @@ struct kmgpu_sketch {
     DevBuf<unsigned long long> d_off1, d_off2;   // exact region offsets of a regrouping run
     DevBuf<uint64_t> d_hash64;              // Murmur: 64-bit hash of every position of the chunk
     DevBuf<uint32_t> d_readbits;            // one bit per read of a window (normalization: candidates / kept)
-    DevBuf<uint32_t> d_upos, d_hitpos;      // normalization: positions of in-between reads; hits of their bins
-    DevBuf<uint64_t> d_ubins, d_hitkey;
+    DevBuf<uint32_t> d_upos;                // normalization: positions of the in-between reads' k-mers + bundle / read index arrays
+    DevBuf<uint32_t> d_nslot, d_ncnt, d_nfill;   // normalization: in-between resolution (k_norm_resolve)
+    DevBuf<uint2> d_nhits;
+    DevBuf<uint8_t> d_nstate;
+    uint64_t n_norm_rounds = 0;
     DevBuf<uint16_t> d_uc0;
     uint64_t n_norm_unsure = 0;
     // first-touch log (replicated sketches: exact n_unique_kmers / abundance_distribution across ranks)
@@ -217,6 +220,8 @@ struct kmgpu_sketch {
     uint64_t ft_pending = 0, ft_epoch_unique = 0;
     uint32_t ft_chunk = 0;
     uint64_t n_regroups = 0;
+    double group_boost1 = 1.0, group_boost2 = 1.0;   // grouped path: slack factors learnt from regions that overflowed
+    DevBuf<uint32_t> d_biglist;                      // regrouping run: heavily loaded buckets
     uint64_t chunk_cap = 0;                 // positions per chunk (sketch_chunk_bases)
     bool bucket_attr_set = false;
     DevBuf<uint32_t> d_bins;
@@ -502,7 +507,7 @@ extern "C" int kmgpu_destroy(kmgpu_t* h)
     if (h->d_ctrl_copy) cudaFree(h->d_ctrl_copy);
     if (h->h_ctrl_copy) cudaFreeHost(h->h_ctrl_copy);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_newmask.release(); for (auto& sg : h->ft_segs) cudaFree(sg.first); h->ft_segs.clear(); h->d_readbits.release(); h->d_upos.release(); h->d_hitpos.release(); h->d_ubins.release(); h->d_hitkey.release(); h->d_uc0.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
+    h->d_flags.release(); h->d_newbits.release(); h->d_filter.release(); h->d_rank.release(); h->d_records.release(); h->d_cursors.release(); h->d_rec1.release(); h->d_cur1.release(); h->d_off1.release(); h->d_off2.release(); h->d_hash64.release(); h->d_newmask.release(); for (auto& sg : h->ft_segs) cudaFree(sg.first); h->ft_segs.clear(); h->d_readbits.release(); h->d_upos.release(); h->d_uc0.release(); h->d_nslot.release(); h->d_ncnt.release(); h->d_nfill.release(); h->d_nhits.release(); h->d_nstate.release(); h->d_biglist.release(); h->d_bins.release(); h->d_delta.release(); h->d_binlist.release(); h->d_sel.release(); h->d_recslot.release();
     h->d_evkeys.release(); h->d_evvals.release(); h->d_evout.release(); h->h_evout.release();
     for (int i = 0; i < MAX_TABLES; i++) h->d_satbits[i].release();
     h->d_htkeys.release(); h->d_htvals.release(); h->d_events.release(); h->d_counts.release(); h->d_hashes.release();
@@ -2109,6 +2114,40 @@ extern "C" int kmgpu_kmer_hashes(kmgpu_t* h, const char* seqs, const uint64_t* o
     return per_kmer_query(h, seqs, offsets, n_reads, flags, nullptr, hashes_out, n_kmers_out);
 }
 
+// one staged chunk of whole reads: counts per position, then one warp per read (median / mean / stddev, or median_at_least)
+static int read_stats_chunk(kmgpu_sketch* h, const ChunkDev& cd, uint64_t r0, uint32_t nb, uint16_t* median_out, float* average_out,
+                            float* stddev_out, uint32_t* n_kmers_out, bool at_least, uint32_t cutoff, uint8_t* at_least_out)
+{
+    HashCfg H{h->hash, h->k};
+    cudaStream_t st = h->stream;
+    uint32_t nr = cd.n_reads;
+    CKR(h->d_counts.ensure(std::max<uint32_t>(cd.n_pos, 1)));
+    if (cd.n_pos) {
+        launch_counts(0, h->dev, H, make_input(cd), h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr, st);
+        h->all_launches += 1;
+    }
+    CKR(h->d_stat_med.ensure(nr));
+    CKR(h->d_stat_f.ensure(2ull * nr));
+    CKR(h->d_stat_n.ensure(nr));
+    CKR(h->d_stat_b.ensure(nr));
+    bool want_med = !at_least;
+    k_read_stats<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, want_med ? h->d_stat_med.p : nullptr,
+                                              want_med ? h->d_stat_f.p : nullptr, want_med ? h->d_stat_f.p + nr : nullptr,
+                                              h->d_stat_n.p, cutoff, at_least ? h->d_stat_b.p : nullptr);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    if (want_med) {
+        if (median_out) CK(cudaMemcpyAsync(median_out + r0, h->d_stat_med.p, 2ull * nr, cudaMemcpyDeviceToHost, st));
+        if (average_out) CK(cudaMemcpyAsync(average_out + r0, h->d_stat_f.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
+        if (stddev_out) CK(cudaMemcpyAsync(stddev_out + r0, h->d_stat_f.p + nr, 4ull * nr, cudaMemcpyDeviceToHost, st));
+    } else {
+        CK(cudaMemcpyAsync(at_least_out + r0, h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
+    }
+    if (n_kmers_out) CK(cudaMemcpyAsync(n_kmers_out + r0, h->d_stat_n.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return KMGPU_OK;
+}
+
 static int per_read_query(kmgpu_sketch* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                           uint16_t* median_out, float* average_out, float* stddev_out, uint32_t* n_kmers_out, bool at_least,
                           uint32_t cutoff, uint8_t* at_least_out)
@@ -2123,40 +2162,42 @@ static int per_read_query(kmgpu_sketch* h, const char* seqs, const uint64_t* off
     CKR(set_device(h->device));
     if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
     uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
-    HashCfg H{h->hash, h->k};
     std::vector<ChunkPlan> plan;
     plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
     uint64_t r0 = 0;
-    cudaStream_t st = h->stream;
     for (const ChunkPlan& c : plan) {
         ChunkDev cd;
         CKR(stage_chunk(h, seqs, c, flags, &cd, needs_acgt_check(h, flags)));
-        uint32_t nr = cd.n_reads;
-        CKR(h->d_counts.ensure(std::max<uint32_t>(cd.n_pos, 1)));
-        if (cd.n_pos) {
-            launch_counts(0, h->dev, H, make_input(cd), h->big_keys.p, h->big_vals.p, nb, h->d_counts.p, nullptr, nullptr, st);
-            h->all_launches += 1;
-        }
-        CKR(h->d_stat_med.ensure(nr));
-        CKR(h->d_stat_f.ensure(2ull * nr));
-        CKR(h->d_stat_n.ensure(nr));
-        CKR(h->d_stat_b.ensure(nr));
-        bool want_med = !at_least;
-        k_read_stats<<<(nr + 7) / 8, 256, 0, st>>>(h->d_counts.p, cd.offs, nr, h->k, want_med ? h->d_stat_med.p : nullptr,
-                                                  want_med ? h->d_stat_f.p : nullptr, want_med ? h->d_stat_f.p + nr : nullptr,
-                                                  h->d_stat_n.p, cutoff, at_least ? h->d_stat_b.p : nullptr);
-        h->all_launches += 1;
-        CK(cudaGetLastError());
-        if (want_med) {
-            if (median_out) CK(cudaMemcpyAsync(median_out + r0, h->d_stat_med.p, 2ull * nr, cudaMemcpyDeviceToHost, st));
-            if (average_out) CK(cudaMemcpyAsync(average_out + r0, h->d_stat_f.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
-            if (stddev_out) CK(cudaMemcpyAsync(stddev_out + r0, h->d_stat_f.p + nr, 4ull * nr, cudaMemcpyDeviceToHost, st));
-        } else {
-            CK(cudaMemcpyAsync(at_least_out + r0, h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
-        }
-        if (n_kmers_out) CK(cudaMemcpyAsync(n_kmers_out + r0, h->d_stat_n.p, 4ull * nr, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        r0 += nr;
+        CKR(read_stats_chunk(h, cd, r0, nb, median_out, average_out, stddev_out, n_kmers_out, at_least, cutoff, at_least_out));
+        r0 += cd.n_reads;
+    }
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_batch_read_medians(kmgpu_t* h, const kmgpu_batch_t* b, uint16_t* median_out, float* average_out, float* stddev_out,
+                                        uint32_t* n_kmers_out)
+{
+    if (!h || !b) return fail(KMGPU_EINVAL, "null argument");
+    if (b->device != h->device) return fail(KMGPU_EINVAL, "batch lives on another device");
+    if (b->ksize != h->k) return fail(KMGPU_EINVAL, "batch was cut for k=%d, sketch has k=%d", b->ksize, h->k);
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    if (h->kind == BYTE && h->use_bigcount) CKR(sync_big_to_device(h));
+    uint32_t nb = (h->kind == BYTE && h->use_bigcount) ? h->n_big_dev : 0;
+    uint64_t r0 = 0;
+    for (const auto& p : b->pieces) r0 += p.n_reads;
+    if (r0 != b->n_reads) return fail(KMGPU_EUNSUPPORTED, "the batch holds a read longer than a device chunk; per-read statistics need whole reads");
+    r0 = 0;
+    for (const auto& p : b->pieces) {
+        ChunkDev cd;
+        cd.words = p.words;
+        cd.offs = p.offs;
+        cd.tfr = p.tfr;
+        cd.valid = p.valid;
+        cd.n_reads = p.n_reads;
+        cd.n_pos = p.n_pos;
+        CKR(read_stats_chunk(h, cd, r0, nb, median_out, average_out, stddev_out, n_kmers_out, false, 0, nullptr));
+        r0 += p.n_reads;
     }
     return KMGPU_OK;
 }
@@ -2272,9 +2313,6 @@ extern "C" int kmgpu_abundance_distribution(kmgpu_t* counts, kmgpu_t* tracking, 
 // ------------------------------------------------------------------------------------------------------
 // digital normalization
 // ------------------------------------------------------------------------------------------------------
-// Hashtable::median_at_least's threshold (hashtable.cc:337): (unsigned)(0.5 + float(n) / 2)
-static inline unsigned median_min_req(uint32_t n) { return (unsigned)(0.5 + (double)((float)n / 2)); }
-
 extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                                      const uint8_t* pair_with_next, uint32_t cutoff, uint8_t* keep_out, uint64_t* n_kept_out,
                                      uint64_t* n_kmers_out)
@@ -2299,7 +2337,9 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     // reads per window: fixed by KMGPU_NORM_WINDOW, else adapted so that only a small share of a window's bundles is "in between"
     // (their number grows with the coverage a window adds; they are resolved one by one on the host)
     const uint64_t W_fixed = env_u64("KMGPU_NORM_WINDOW", 0);
-    uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 16384;
+    uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 32768;
+    uint64_t n_windows = 0;
+    const uint64_t unsure0 = h->n_norm_unsure, rounds0 = h->n_norm_rounds;
     const uint64_t max_bases = chunk_bases() / 2;
     Pred P0;
     memset(&P0, 0, sizeof P0);
@@ -2322,6 +2362,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
         if (r1 == r0) r1 = r0 + 1;
         while (r1 < n_reads && pair_with_next && pair_with_next[r1 - 1]) r1++;   // do not cut a pair
         const uint32_t nr = (uint32_t)(r1 - r0);
+        n_windows++;
         ChunkPlan c;
         c.base0 = offsets[r0];
         c.base1 = offsets[r1];
@@ -2408,129 +2449,125 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                 }
                 keep = sure;
                 if (!W_fixed) {
-                    // a window costs ~1 ms of launches and round trips whatever its size, an in-between read ~10 us of host work:
-                    // aim at a few hundred in-between reads per window
-                    if (n_unsure > 600) W = std::max<uint64_t>(1024, W / 2);
-                    else if (n_unsure < 150) W = std::min<uint64_t>(1u << 18, W * 2);
+                    // a window costs ~1 ms of launches and round trips whatever its size; the in-between bundles (their number grows
+                    // with the square of the window) cost a few rounds of k_norm_resolve over their k-mers
+                    if (n_unsure > 8192) W = std::max<uint64_t>(2048, W / 2);
+                    else if (n_unsure < 2048) W = std::min<uint64_t>(1u << 17, W * 2);
                 }
                 if (n_unsure) {
-                    // 3. in-between bundles, in stream order: the state each of them meets is the window's start + the reads kept
-                    //    for good before it + the in-between bundles kept before it
+                    // 3. in-between bundles: the state each of them meets is the window's start + the candidates kept before it.
+                    //    Gather, for every k-mer of theirs, the counters at the window's start and the touches of its bins by the
+                    //    window's candidates (position, read); then decide in rounds on the device (k_norm_resolve).
                     h->n_norm_unsure += n_unsure;
-                    std::vector<uint32_t> upos;
+                    std::vector<uint32_t> upos, meta_ub, meta_start, meta_ur, meta_read;
                     upos.reserve(up_total);
-                    for (uint32_t r = 0; r < nr; r++) {
-                        if (!unsure[r]) continue;
-                        const uint32_t s = c.offs[r], len = c.offs[r + 1] - s;
-                        if (len < (uint32_t)h->k) continue;
-                        for (uint32_t i = 0; i + h->k <= len; i++) upos.push_back(s + i);
+                    meta_ur.push_back(0);
+                    for (uint32_t r = 0; r < nr;) {
+                        const uint32_t e = bundle_end(r);
+                        if (unsure[r]) {
+                            meta_ub.push_back((uint32_t)meta_read.size());
+                            meta_start.push_back(c.offs[r]);
+                            for (uint32_t q = r; q < e; q++) {
+                                const uint32_t s0 = c.offs[q], len = c.offs[q + 1] - s0;
+                                for (uint32_t i = 0; i + h->k <= len; i++) upos.push_back(s0 + i);
+                                meta_read.push_back(q);
+                                meta_ur.push_back((uint32_t)upos.size());
+                            }
+                        }
+                        r = e;
                     }
-                    const uint32_t n_up = (uint32_t)upos.size();
-                    std::vector<uint64_t> ubins((size_t)n_up * N);
-                    std::vector<uint16_t> uc0((size_t)n_up * N);
-                    std::vector<std::pair<uint64_t, uint32_t>> hits;   // (key, position) of touches by the reads kept for good, sorted
+                    meta_ub.push_back((uint32_t)meta_read.size());
+                    const uint32_t n_up = (uint32_t)upos.size(), n_ub = (uint32_t)meta_start.size(), n_ur = (uint32_t)meta_read.size();
+                    std::vector<uint8_t> state(nr, 0);
+                    for (uint32_t r = 0; r < nr; r++) state[r] = sure[r] ? 1 : unsure[r] ? 2 : 0;
                     if (n_up) {
-                        CKR(h->d_upos.ensure(n_up));
-                        CKR(h->d_ubins.ensure((size_t)n_up * N));
-                        CKR(h->d_uc0.ensure((size_t)n_up * N));
                         const uint64_t slots2 = pow2_at_least(2 * (uint64_t)n_up * N);
+                        if (slots2 > (1ull << 32)) return fail(KMGPU_EUNSUPPORTED, "normalize_batch: window too large");
+                        // one upload: upos | ub_first | ub_start | ur_first | ur_read
+                        std::vector<uint32_t> pack;
+                        pack.reserve((size_t)n_up + meta_ub.size() + meta_start.size() + meta_ur.size() + meta_read.size());
+                        pack.insert(pack.end(), upos.begin(), upos.end());
+                        const size_t o_ub = pack.size();
+                        pack.insert(pack.end(), meta_ub.begin(), meta_ub.end());
+                        const size_t o_st = pack.size();
+                        pack.insert(pack.end(), meta_start.begin(), meta_start.end());
+                        const size_t o_ur = pack.size();
+                        pack.insert(pack.end(), meta_ur.begin(), meta_ur.end());
+                        const size_t o_rd = pack.size();
+                        pack.insert(pack.end(), meta_read.begin(), meta_read.end());
+                        CKR(h->d_upos.ensure(pack.size()));
+                        CKR(h->d_nslot.ensure((size_t)n_up * N));
+                        CKR(h->d_uc0.ensure((size_t)n_up * N));
                         CKR(h->d_evkeys.ensure(slots2));
-                        CK(cudaMemcpyAsync(h->d_upos.p, upos.data(), (size_t)n_up * 4, cudaMemcpyHostToDevice, st));
+                        CKR(h->d_ncnt.ensure(slots2));
+                        CKR(h->d_nfill.ensure(slots2));
+                        CKR(h->d_nstate.ensure(nr));
+                        CK(cudaMemcpyAsync(h->d_upos.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, st));
+                        CK(cudaMemcpyAsync(h->d_nstate.p, state.data(), nr, cudaMemcpyHostToDevice, st));
                         CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, slots2 * 8, st));
+                        CK(cudaMemsetAsync(h->d_ncnt.p, 0, slots2 * 4, st));
+                        CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
                         uint64_t* keys2 = reinterpret_cast<uint64_t*>(h->d_evkeys.p);
                         Input in0 = make_input(cd);
 #define NORM_GATHER(KIND)                                                                                                                                    \
     do {                                                                                                                                                     \
-        if (H.kind == TWOBIT) k_norm_gather<KIND, TWOBIT><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_ubins.p, h->d_uc0.p, keys2, slots2 - 1); \
-        else k_norm_gather<KIND, MURMUR><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_ubins.p, h->d_uc0.p, keys2, slots2 - 1);               \
+        if (H.kind == TWOBIT) k_norm_gather<KIND, TWOBIT><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_nslot.p, h->d_uc0.p, keys2, slots2 - 1); \
+        else k_norm_gather<KIND, MURMUR><<<(n_up + 255) / 256, 256, 0, st>>>(h->dev, H, in0, h->d_upos.p, n_up, h->d_nslot.p, h->d_uc0.p, keys2, slots2 - 1);               \
     } while (0)
                         if (h->kind == BYTE) NORM_GATHER(BYTE);
                         else if (h->kind == NIBBLE) NORM_GATHER(NIBBLE);
                         else NORM_GATHER(BIT);
 #undef NORM_GATHER
+                        Input inc = make_input(cd);
+                        inc.read_keep = h->d_readbits.p;   // still the candidates' bits (uploaded for the overlay)
+                        if (H.kind == TWOBIT) k_norm_hits<TWOBIT, 0, 0><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_ncnt.p, nullptr);
+                        else k_norm_hits<MURMUR, 0, 0><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_ncnt.p, nullptr);
+                        k_norm_hit_offsets<<<148 * 8, 256, 0, st>>>(h->d_ncnt.p, h->d_nfill.p, slots2, &h->d_ctrl->n_events);
+                        h->all_launches += 3;
+                        CK(cudaGetLastError());
+                        CKR(read_ctrl(h));   // synchronises: the host vectors above may go
+                        const uint64_t n_hits = h->h_ctrl->n_events;
+                        if (n_hits >= (1ull << 32)) return fail(KMGPU_EUNSUPPORTED, "normalize_batch: window too large");
+                        CKR(h->d_nhits.ensure(std::max<uint64_t>(n_hits, 1)));
+                        if (H.kind == TWOBIT) k_norm_hits<TWOBIT, 0, 1><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_nfill.p, h->d_nhits.p);
+                        else k_norm_hits<MURMUR, 0, 1><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_nfill.p, h->d_nhits.p);
                         h->all_launches += 1;
-                        CKR(upload_bits(sure, nr));   // synchronises: upos may go
-                        Input ink = make_input(cd);
-                        ink.read_keep = h->d_readbits.p;
-                        uint64_t hit_cap = std::max<uint64_t>(1u << 20, h->d_hitkey.cap);
-                        while (true) {
-                            CKR(h->d_hitkey.ensure(hit_cap));
-                            CKR(h->d_hitpos.ensure(hit_cap));
+                        NormResolve R;
+                        R.ub_first = h->d_upos.p + o_ub;
+                        R.ub_start = h->d_upos.p + o_st;
+                        R.ur_first = h->d_upos.p + o_ur;
+                        R.ur_read = h->d_upos.p + o_rd;
+                        R.slot = h->d_nslot.p;
+                        R.c0 = h->d_uc0.p;
+                        R.cnt = h->d_ncnt.p;
+                        R.fill = h->d_nfill.p;
+                        R.hits = h->d_nhits.p;
+                        R.state = h->d_nstate.p;
+                        R.n_tables = N;
+                        R.cutoff = cutoff;
+                        R.cap = cap_c;
+                        unsigned int* n_left = reinterpret_cast<unsigned int*>(&h->d_ctrl->n_events);
+                        for (uint64_t round = 0;; round++) {
+                            // two rounds per look at the counter (a round is a few microseconds, the look a round trip)
                             CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
-                            if (H.kind == TWOBIT) k_norm_hits<TWOBIT, 0><<<gt, THREADS, 0, st>>>(h->dev, H, ink, keys2, slots2 - 1, h->d_hitkey.p, h->d_hitpos.p, hit_cap, h->d_ctrl);
-                            else k_norm_hits<MURMUR, 0><<<gt, THREADS, 0, st>>>(h->dev, H, ink, keys2, slots2 - 1, h->d_hitkey.p, h->d_hitpos.p, hit_cap, h->d_ctrl);
-                            h->all_launches += 1;
+                            k_norm_resolve<<<(n_ub + 7) / 8, 256, 0, st>>>(R, n_ub, n_left);
+                            CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+                            k_norm_resolve<<<(n_ub + 7) / 8, 256, 0, st>>>(R, n_ub, n_left);
+                            h->all_launches += 2;
+                            h->n_norm_rounds += 2;
                             CK(cudaGetLastError());
                             CKR(read_ctrl(h));
-                            if (h->h_ctrl->n_events <= hit_cap) break;
-                            hit_cap = h->h_ctrl->n_events;
+                            if (h->h_ctrl->n_events == 0) break;
+                            if (round > n_ub) return fail(KMGPU_ECUDA, "normalize_batch: the in-between resolution does not converge");
                         }
-                        const uint64_t n_hits = h->h_ctrl->n_events;
-                        std::vector<uint64_t> hk(n_hits);
-                        std::vector<uint32_t> hp(n_hits);
-                        CK(cudaMemcpyAsync(ubins.data(), h->d_ubins.p, ubins.size() * 8, cudaMemcpyDeviceToHost, st));
-                        CK(cudaMemcpyAsync(uc0.data(), h->d_uc0.p, uc0.size() * 2, cudaMemcpyDeviceToHost, st));
-                        if (n_hits) {
-                            CK(cudaMemcpyAsync(hk.data(), h->d_hitkey.p, n_hits * 8, cudaMemcpyDeviceToHost, st));
-                            CK(cudaMemcpyAsync(hp.data(), h->d_hitpos.p, n_hits * 4, cudaMemcpyDeviceToHost, st));
-                        }
+                        CK(cudaMemcpyAsync(state.data(), h->d_nstate.p, nr, cudaMemcpyDeviceToHost, st));
                         CK(cudaStreamSynchronize(st));
-                        hits.resize(n_hits);
-                        for (uint64_t i = 0; i < n_hits; i++) hits[i] = std::make_pair(hk[i], hp[i]);
-                        std::sort(hits.begin(), hits.end());
+                    } else {
+                        // in-between bundles without a single k-mer cannot be "below": never kept (they were no candidates at all)
+                        for (uint32_t r = 0; r < nr; r++)
+                            if (state[r] == 2) state[r] = 0;
                     }
-                    // flat tables over the distinct (table, bin) keys of the in-between reads: index of every record's key, the
-                    // key's range in `hits`, and the touches added by the in-between bundles kept so far
-                    std::vector<uint64_t> ukeys((size_t)n_up * N);
-                    for (size_t u = 0; u < (size_t)n_up; u++)
-                        for (int t = 0; t < N; t++) ukeys[u * N + t] = (ubins[u * N + t] << 8) | (uint64_t)t;
-                    std::vector<uint64_t> dkeys(ukeys);
-                    std::sort(dkeys.begin(), dkeys.end());
-                    dkeys.erase(std::unique(dkeys.begin(), dkeys.end()), dkeys.end());
-                    std::vector<uint32_t> uidx(ukeys.size());
-                    for (size_t i = 0; i < ukeys.size(); i++) uidx[i] = (uint32_t)(std::lower_bound(dkeys.begin(), dkeys.end(), ukeys[i]) - dkeys.begin());
-                    std::vector<uint32_t> hit_lo(dkeys.size(), 0), extra(dkeys.size(), 0);
-                    {
-                        size_t hi = 0;   // both lists are sorted by key: one merge pass finds where every key's hits start
-                        for (size_t d = 0; d < dkeys.size(); d++) {
-                            while (hi < hits.size() && hits[hi].first < dkeys[d]) hi++;
-                            hit_lo[d] = (uint32_t)hi;
-                        }
-                    }
-                    size_t up_at = 0;
-                    for (uint32_t r = 0; r < nr;) {
-                        const uint32_t e = bundle_end(r);
-                        if (!unsure[r]) { r = e; continue; }
-                        const uint32_t bundle_start = c.offs[r];
-                        const size_t up_begin = up_at;
-                        bool below = false;
-                        for (uint32_t q = r; q < e; q++) {
-                            const uint32_t len = c.offs[q + 1] - c.offs[q];
-                            if (len < (uint32_t)h->k) continue;
-                            const uint32_t nk = len - h->k + 1;
-                            unsigned n_ge = 0;
-                            for (uint32_t i = 0; i < nk; i++, up_at++) {
-                                uint32_t mn = cap_c;
-                                for (int t = 0; t < N; t++) {
-                                    const uint32_t d = uidx[up_at * N + t];
-                                    uint64_t v = uc0[up_at * N + t] + extra[d];
-                                    // touches of this bin by the reads kept for good that come before this bundle
-                                    size_t a = hit_lo[d], b2 = a;
-                                    while (b2 < hits.size() && hits[b2].first == dkeys[d] && hits[b2].second < bundle_start) b2++;
-                                    v += b2 - a;
-                                    if (v < mn) mn = (uint32_t)v;
-                                }
-                                n_ge += mn >= cutoff;
-                            }
-                            if (n_ge < median_min_req(nk)) below = true;
-                        }
-                        if (below) {
-                            for (uint32_t q = r; q < e; q++) keep[q] = 1;
-                            for (size_t u = up_begin; u < up_at; u++)
-                                for (int t = 0; t < N; t++) extra[uidx[u * N + t]] += 1;
-                        }
-                        r = e;
-                    }
+                    for (uint32_t r = 0; r < nr; r++) keep[r] = state[r] == 1;
                 }
                 // 4. the kept reads are consumed in stream order (one ordinary ingest with a read mask)
                 uint64_t nk_reads = 0;
@@ -2551,6 +2588,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     }
     if (n_kept_out) *n_kept_out = kept_total;
     if (n_kmers_out) *n_kmers_out = kmers_total;
+    if (env_u64("KMGPU_DEBUG", 0))
+        fprintf(stderr, "[kmgpu] normalize_batch: %llu reads in %llu windows (last %llu reads), %llu in-between reads, %llu resolve rounds\n",
+                (unsigned long long)n_reads, (unsigned long long)n_windows, (unsigned long long)W,
+                (unsigned long long)(h->n_norm_unsure - unsure0), (unsigned long long)(h->n_norm_rounds - rounds0));
     return KMGPU_OK;
 }
 
@@ -3246,6 +3287,11 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
         CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, bits, n_pos_all, 1, 0, sb, &s1, s->newbits));
         CKR(read_ctrl(h));
         if (h->h_ctrl->overflow) return fail(KMGPU_ECUDA, "internal: regrouping run overflowed");
+        // bucket regions get more slack from the next round on (the receive regions were sized at creation and stay)
+        const uint32_t cap_now = s->G.L.cap;
+        s->G.L.cap = (uint32_t)std::min<uint64_t>(((uint64_t)cap_now * 3 / 2 + 1) & ~1ull, (uint64_t)n_pos_all + 2);
+        s->G.wide = s->G.L.cap > 65535;
+        s->G.sparse = s->G.sparse && s->G.L.cap <= SPARSE_MAX_RECORDS;
     }
     h->n_occupied += h->h_ctrl->n_z0;
     CK(cudaMemsetAsync(s->cur1, 0, (size_t)s->G.n_sb * 4, st));

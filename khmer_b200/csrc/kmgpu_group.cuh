@@ -463,6 +463,16 @@ __global__ void __launch_bounds__(1024) k_exact_offsets(const uint32_t* __restri
     if (threadIdx.x == 0) off[n] = s_carry;
 }
 
+// buckets whose demand exceeds `thresh` records (regrouping run of a sparse plan): list[0 .. *count)
+__global__ void k_big_buckets(const uint32_t* __restrict__ cursor, uint32_t b_lo, uint32_t n, uint32_t thresh, uint32_t* __restrict__ list, uint32_t list_cap,
+                              unsigned int* count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || cursor[b_lo + i] <= thresh) return;
+    const uint32_t at = atomicAdd(count, 1u);
+    if (at < list_cap) list[at] = b_lo + i;
+}
+
 // =====================================================================================================================
 // 2. k_apply2: one CTA per bucket.  Shared memory: 16-bit touch lanes (64 KB), first-toucher positions (128 KB), the
 //    bucket's slice of the table (32 / 16 / 4 KB).
@@ -484,7 +494,7 @@ template <int KIND>
 __global__ void __launch_bounds__(1024, 1)
 k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
          uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
-         unsigned long long ovf_mask, uint32_t* __restrict__ newmask, int gate)
+         unsigned long long ovf_mask, uint32_t* __restrict__ newmask, int gate, const uint32_t* __restrict__ bucket_list)
 {
     extern __shared__ __align__(128) unsigned char ap_raw[];
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // BKT_BINS / 2 words, two 16-bit lanes each
@@ -492,7 +502,9 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     uint8_t* slice = reinterpret_cast<uint8_t*>(minpos + BKT_BINS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(slice + slice_bytes_full<KIND>());
     if (ctrl->overflow & ovf_mask) return;      // a region of this table group ran out of room: the group is regrouped with exact offsets
-    const uint32_t b = bucket0 + blockIdx.x;
+    // bucket_list: the launch covers only the listed buckets (the heavily loaded ones of a regrouping run whose other buckets
+    // go through k_apply_sparse)
+    const uint32_t b = bucket_list ? bucket_list[blockIdx.x] : bucket0 + blockIdx.x;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = st.cursor[b];
     if (n == 0) return;
@@ -712,14 +724,15 @@ template <int KIND>
 __global__ void __launch_bounds__(128)
 k_apply_sparse(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
                uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
-               unsigned long long ovf_mask, uint32_t* __restrict__ newmask)
+               unsigned long long ovf_mask, uint32_t* __restrict__ newmask, uint32_t max_n)
 {
     extern __shared__ __align__(16) uint32_t sp_raw[];
     if (ctrl->overflow & ovf_mask) return;
     const uint32_t b = bucket0 + blockIdx.x;
     const uint32_t n = st.cursor[b];
     if (n == 0) return;
-    if (n > st.room(b) || n > SPARSE_MAX_RECORDS) return;   // reported by k_part (regions of this launch hold <= SPARSE_MAX_RECORDS)
+    // more than the region holds: reported by k_part; more than max_n (regrouping runs): the bucket is on k_apply2's list
+    if (n > st.room(b) || n > max_n) return;
     uint32_t slots = 64;
     while (slots < 2 * n) slots <<= 1;
     uint32_t* hk = sp_raw;            // bin in bucket + 1, 0 = free
@@ -867,7 +880,7 @@ namespace kmgpu {
 //    the cutoff in the table AS IT IS when the bundle arrives, and consumes it at once — a serial dependency.  Counts
 //    only grow, so for a window of reads: a bundle at or above the cutoff at the window's start is discarded for good;
 //    a candidate still below the cutoff after EVERY candidate of the window has been added (the overlay below) is kept
-//    for good; the few in between are resolved in stream order on the host from exact per-bin data gathered here.
+//    for good; the few in between are resolved on the device in rounds (k_norm_resolve) from exact per-bin data.
 // =====================================================================================================================
 
 // overlay: (table, bin) -> touches by the window's candidate reads (open addressing, keys as ht_key)
@@ -917,11 +930,11 @@ k_norm_counts_overlay(const __grid_constant__ SketchDev S, HashCfg H, Input in, 
     }
 }
 
-// per position of an in-between read (upos[j] = chunk position): its bin and the counter there in every table, and
-// the (table, bin) registered in the set the next kernel probes
+// per position of an in-between read (upos[j] = chunk position): for every table, the counter of its bin at the window's start
+// and the slot of (table, bin) in the set the next kernels probe
 template <int KIND, int HK>
 __global__ void __launch_bounds__(256)
-k_norm_gather(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ upos, uint32_t n_up, uint64_t* __restrict__ out_bins,
+k_norm_gather(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ upos, uint32_t n_up, uint32_t* __restrict__ out_slot,
               uint16_t* __restrict__ out_c0, uint64_t* keys2, uint64_t mask2)
 {
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;
@@ -929,17 +942,18 @@ k_norm_gather(const __grid_constant__ SketchDev S, HashCfg H, Input in, const ui
     const uint64_t h = hash_at<HK, 0>(in, H.k, upos[j]);
     for (int i = 0; i < S.n_tables; i++) {
         const uint64_t bin = mod_magic(h, S.sizes[i], S.magic[i]);
-        out_bins[(size_t)j * S.n_tables + i] = bin;
         out_c0[(size_t)j * S.n_tables + i] = (uint16_t)read_counter<KIND>(S.tables[i], bin);
-        ht_insert(keys2, mask2, ht_key(bin, i));
+        out_slot[(size_t)j * S.n_tables + i] = (uint32_t)ht_insert(keys2, mask2, ht_key(bin, i));
     }
 }
 
-// touches of registered (table, bin) pairs by the reads kept for good: (key, position) pairs for the host
-template <int HK, int SRC>
+// touches of the registered (table, bin) pairs by the window's candidate reads (in.read_keep), as one list per pair.
+// PASS 0 counts them (cnt[slot]); k_norm_hit_offsets gives every pair its range; PASS 1 writes (position, read) into the range
+// (fill[slot] ends at the range's end).
+template <int HK, int SRC, int PASS>
 __global__ void __launch_bounds__(THREADS)
-k_norm_hits(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ keys2, uint64_t mask2, uint64_t* __restrict__ hit_key,
-            uint32_t* __restrict__ hit_pos, unsigned long long cap, Ctrl* ctrl)
+k_norm_hits(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ keys2, uint64_t mask2, uint32_t* cnt_or_fill,
+            uint2* __restrict__ hits)
 {
     __shared__ TileSmem sm;
     const uint32_t t0 = blockIdx.x * TILE;
@@ -949,16 +963,112 @@ k_norm_hits(const __grid_constant__ SketchDev S, HashCfg H, Input in, const uint
         if (t0 + lp >= in.n_pos) break;
         if (!tile_valid<HK, SRC>(sm, lp)) continue;
         const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        uint32_t read = ~0u;
         for (int i = 0; i < S.n_tables; i++) {
-            const uint64_t key = ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i);
-            if (ht_find(keys2, mask2, key) == ~0ull) continue;
-            const unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
-            if (at < cap) {
-                hit_key[at] = key;
-                hit_pos[at] = t0 + lp;
+            const uint64_t sl = ht_find(keys2, mask2, ht_key(mod_magic(h, S.sizes[i], S.magic[i]), i));
+            if (sl == ~0ull) continue;
+            const uint32_t at = atomicAdd(&cnt_or_fill[sl], 1u);
+            if (PASS == 1) {
+                if (read == ~0u) {   // the read this position belongs to: last r with offs[r] <= position
+                    uint32_t lo = in.tfr[blockIdx.x], hi = in.tfr[blockIdx.x + 1];
+                    const uint32_t p = t0 + lp;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi + 1) >> 1;
+                        if (in.offs[mid] <= p) lo = mid; else hi = mid - 1;
+                    }
+                    read = lo;
+                }
+                hits[at] = make_uint2(t0 + lp, read);
             }
         }
     }
+}
+
+__global__ void k_norm_hit_offsets(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ fill, uint64_t n_slots, unsigned long long* total)
+{
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = cnt[s];
+        if (c) fill[s] = (uint32_t)atomicAdd(total, (unsigned long long)c);
+    }
+}
+
+// One round of the in-between resolution, one warp per in-between bundle.  state[read]: 0 discarded, 1 kept, 2 undecided.
+// The reference's decision for a bundle depends on the bundles kept BEFORE it; counts only grow with every kept read, so with
+// lo = (kept so far) and hi = (kept or undecided) every count is bracketed: below the cutoff even under hi => kept; at or
+// above it already under lo => discarded.  The first undecided bundle of the stream always decides (lo = hi before it), every
+// round decides at least that one; rounds repeat until none is left.  Reading a state another warp has just decided only
+// tightens the bracket.
+struct NormResolve {
+    const uint32_t* ub_first;   // [n_ub + 1] first in-between read (index into ur_*) of every in-between bundle
+    const uint32_t* ub_start;   // [n_ub]     chunk position where the bundle starts: only touches before it count
+    const uint32_t* ur_first;   // [n_ur + 1] first entry of every in-between read in slot[] / c0[] (entries = its k-mers)
+    const uint32_t* ur_read;    // [n_ur]     read number within the window
+    const uint32_t* slot;       // [entries x N]
+    const uint16_t* c0;         // [entries x N]
+    const uint32_t* cnt;        // per slot: number of hits; they end at fill[slot]
+    const uint32_t* fill;
+    const uint2* hits;
+    uint8_t* state;
+    int n_tables;
+    uint32_t cutoff, cap;
+};
+
+__global__ void __launch_bounds__(256)
+k_norm_resolve(const __grid_constant__ NormResolve R, uint32_t n_ub, unsigned int* n_left)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (b >= n_ub) return;
+    const uint32_t q0 = R.ub_first[b], q1 = R.ub_first[b + 1];
+    volatile uint8_t* state = R.state;
+    if (state[R.ur_read[q0]] != 2) return;
+    const uint32_t bstart = R.ub_start[b];
+    bool kept = false, all_above = true;
+    for (uint32_t q = q0; q < q1; q++) {
+        const uint32_t e0 = R.ur_first[q], nk = R.ur_first[q + 1] - e0;
+        unsigned ge_lo = 0, ge_hi = 0;
+        for (uint32_t i = lane; i < nk; i += 32) {
+            uint32_t mn_lo = R.cap, mn_hi = R.cap;
+            for (int t = 0; t < R.n_tables; t++) {
+                const size_t at = (size_t)(e0 + i) * R.n_tables + t;
+                const uint32_t sl = R.slot[at];
+                uint32_t v_lo = R.c0[at], v_hi = v_lo;
+                const uint32_t end = R.fill[sl], beg = end - R.cnt[sl];
+                for (uint32_t x = beg; x < end; x++) {
+                    const uint2 hit = R.hits[x];
+                    if (hit.x >= bstart) continue;
+                    const uint32_t st = state[hit.y];
+                    v_lo += st == 1;
+                    v_hi += st >= 1;
+                }
+                mn_lo = v_lo < mn_lo ? v_lo : mn_lo;
+                mn_hi = v_hi < mn_hi ? v_hi : mn_hi;
+            }
+            ge_lo += mn_lo >= R.cutoff;
+            ge_hi += mn_hi >= R.cutoff;
+        }
+        ge_lo = __reduce_add_sync(0xffffffffu, ge_lo);
+        ge_hi = __reduce_add_sync(0xffffffffu, ge_hi);
+        const unsigned req = (unsigned)(0.5 + (double)((float)nk / 2));   // Hashtable::median_at_least (hashtable.cc:337)
+        kept |= ge_hi < req;
+        all_above &= !(ge_lo < req);
+    }
+    if (!kept && !all_above) {
+        if (lane == 0) atomicAdd(n_left, 1u);
+        return;
+    }
+    const uint8_t v = kept ? 1 : 0;
+    for (uint32_t q = q0 + lane; q < q1; q += 32) state[R.ur_read[q]] = v;
+}
+
+// keep bits of a window from the per-read states (1 = kept)
+__global__ void k_norm_keep_bits(const uint8_t* __restrict__ state, uint32_t n_reads, uint32_t* __restrict__ bits)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32u >= n_reads) return;
+    uint32_t m = 0;
+    for (uint32_t j = 0; j < 32 && w * 32u + j < n_reads; j++) m |= (uint32_t)(state[w * 32u + j] == 1) << j;
+    bits[w] = m;
 }
 
 }  // namespace kmgpu

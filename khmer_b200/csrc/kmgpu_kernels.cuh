@@ -517,9 +517,15 @@ k_counts(SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ big_keys
         if (hashes) hashes[p] = h;
         if (!counts) continue;
         uint32_t mn = counter_cap<KIND>();
-        for (int i = 0; i < S.n_tables; i++) {
-            uint32_t c = read_counter<KIND>(S.tables[i], mod_magic(h, S.sizes[i], S.magic[i]));
-            mn = c < mn ? c : mn;
+        for (int i0 = 0; i0 < S.n_tables; i0 += 4) {   // four tables at a time: all four loads in flight before the first is used
+            uint32_t c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = i0 + j < S.n_tables ? i0 + j : i0;
+                c[j] = read_counter<KIND>(S.tables[i], mod_magic(h, S.sizes[i], S.magic[i]));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) mn = c[j] < mn ? c[j] : mn;
         }
         if (KIND == BYTE && mn == 255u && n_big) {
             uint32_t lo = 0, hi = n_big;

@@ -349,7 +349,7 @@ def test_bucket_path_many_buckets(cls):
     g.close()
 
 
-@pytest.mark.parametrize("variant", ["dense", "sparse", "sparse-two", "dense-two", "regroup", "turns", "t16k"])
+@pytest.mark.parametrize("variant", ["dense", "sparse", "sparse-two", "dense-two", "regroup", "sparse-regroup", "sparse-two-regroup", "turns", "t16k"])
 def test_group_path_many_buckets(variant):
     """test_bucket_path_many_buckets (six classes, ~70 buckets per table, state carried across calls, bigcount map) with the
     grouped path forced on and steered into each of its forms."""
@@ -363,6 +363,10 @@ def test_group_path_many_buckets(variant):
         env.update(KMGPU_FORCE_TWO_LEVEL="1")
     elif variant == "regroup":     # regions of 500 records against ~6.7 K expected: exact offsets, dense apply with clamping rounds
         env.update(KMGPU_BUCKET_CAP="500")
+    elif variant == "sparse-regroup":   # sparse plan whose regions overflow: exact offsets, k_apply_sparse + the heavily loaded buckets by list
+        env.update(KMGPU_CHUNK_BASES="16384", KMGPU_BUCKET_CAP="40", KMGPU_REGROUP_SPARSE_MAX="300")
+    elif variant == "sparse-two-regroup":
+        env.update(KMGPU_CHUNK_BASES="16384", KMGPU_FORCE_TWO_LEVEL="1", KMGPU_BUCKET_CAP="40", KMGPU_SB_CAP="3000", KMGPU_REGROUP_SPARSE_MAX="300")
     elif variant == "turns":
         env.update(KMGPU_GROUP_MAX_RECORDS="900000")
     elif variant == "t16k":

@@ -193,3 +193,28 @@ def test_trim_batch_matches_reference_semantics():
             else:
                 want = next((k - 1 + i for i in range(1, len(c)) if bad(c[i])), len(q))
             assert pos == want, (q, abund, below)
+
+
+@pytest.mark.parametrize("cls", ["Countgraph", "SmallCounttable", "Nodegraph"])
+def test_batch_read_medians_equals_host_call(cls):
+    """kmgpu_batch_read_medians (device-resident batch) against kmgpu_read_medians and the oracle, incl. reads without k-mers and
+    a sketch of five tables (the count kernel takes the tables four at a time)"""
+    from khmer_b200 import cabi
+    kind, hk, _ = ol.CLASSES[cls]
+    k = 21 if hk == ol.TWOBIT else 33
+    sizes = ol.primes_near_x(5, 40000)
+    g, o = make_gpu(cls, k, sizes), ol.Oracle(cls, k, sizes)
+    reads = synth_reads(11, 1500, 140, 6000, err=0.01)
+    assert g.consume_reads(reads) == o.consume_reads(reads)
+    q = reads[:400] + ["ACGT", "", "A" * (k - 1), "C" * 300]
+    b = cabi.Batch(q, k, clean=True)
+    med, avg, sd, nk = g.batch_read_medians(b)
+    med2, avg2, sd2, nk2 = g.read_medians(q, clean=True)
+    assert np.array_equal(med, med2) and np.array_equal(nk, nk2)
+    assert avg.tobytes() == avg2.tobytes() and sd.tobytes() == sd2.tobytes()
+    for i in (0, 7, 399, 403):
+        if len(q[i]) >= k:
+            m, a, s = o.median(q[i])
+            assert (int(med[i]), np.float32(avg[i]).tobytes(), np.float32(sd[i]).tobytes()) == (m, np.float32(a).tobytes(), np.float32(s).tobytes())
+    assert g.batch_read_medians(b, stats=False)[0].tolist() == med.tolist()
+    b.close()
