@@ -343,6 +343,8 @@ def secondary_legs(cabi, sk, host, dev, local_rank, n_query=400_000):
     n_res = len(med_r)
     sizes = primes_near_x(N_TABLES, TABLE_X)
     tracking = cabi.Sketch(cabi.BIT, cabi.TWOBIT, K, sizes, device=local_rank)
+    sk.abundance_distribution((buf, off), tracking)                 # warm-up: the tracking filter's workspaces are allocated here
+    tracking.reset()
     t0 = time.perf_counter()
     hist = sk.abundance_distribution((buf, off), tracking)
     t_ab = time.perf_counter() - t0

@@ -479,8 +479,10 @@ __global__ void k_big_buckets(const uint32_t* __restrict__ cursor, uint32_t b_lo
 // =====================================================================================================================
 template <int KIND>
 __host__ __device__ constexpr uint32_t slice_bytes_full() { return KIND == BYTE ? BKT_BINS : KIND == NIBBLE ? BKT_BINS / 2 : BKT_BINS / 8; }
-template <int KIND>
-constexpr size_t apply2_smem() { return (size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4 + slice_bytes_full<KIND>() + 64; }
+// SPLIT: CTAs per bucket.  Each takes 1/SPLIT of the bucket's bins (and reads all of its records, keeping its own): lightly loaded
+// buckets, whose cost is the set-up and the sweep of the shared-memory arrays rather than the records, then run 2-3 CTAs per SM.
+template <int KIND, int SPLIT>
+constexpr size_t apply2_smem() { return ((size_t)BKT_BINS * 2 + (size_t)BKT_BINS * 4 + slice_bytes_full<KIND>()) / SPLIT + 64; }
 
 template <int KIND>
 __device__ __forceinline__ bool slice_empty(const uint8_t* slice, uint32_t lb)
@@ -490,21 +492,23 @@ __device__ __forceinline__ bool slice_empty(const uint8_t* slice, uint32_t lb)
     return !((slice[lb >> 3] >> (lb & 7)) & 1u);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(1024, 1)
+template <int KIND, int SPLIT>
+__global__ void __launch_bounds__(1024 / SPLIT, SPLIT == 4 ? 3 : SPLIT)
 k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayout L, Store st, uint32_t bucket0, uint32_t* __restrict__ newbits,
          uint64_t* __restrict__ binlist, unsigned long long list_cap, Ctrl* ctrl, int want_cross, const __grid_constant__ SatBitsG sb,
          unsigned long long ovf_mask, uint32_t* __restrict__ newmask, int gate, const uint32_t* __restrict__ bucket_list)
 {
     extern __shared__ __align__(128) unsigned char ap_raw[];
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // BKT_BINS / 2 words, two 16-bit lanes each
-    uint32_t* minpos = cnt + BKT_BINS / 2;                                     // BKT_BINS words
-    uint8_t* slice = reinterpret_cast<uint8_t*>(minpos + BKT_BINS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(slice + slice_bytes_full<KIND>());
+    constexpr uint32_t SUB_BINS = BKT_BINS / SPLIT, NTHR = 1024 / SPLIT, SUB_BYTES = slice_bytes_full<KIND>() / SPLIT;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(ap_raw);                       // SUB_BINS / 2 words, two 16-bit lanes each
+    uint32_t* minpos = cnt + SUB_BINS / 2;                                     // SUB_BINS words
+    uint8_t* slice = reinterpret_cast<uint8_t*>(minpos + SUB_BINS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(slice + SUB_BYTES);
     if (ctrl->overflow & ovf_mask) return;      // a region of this table group ran out of room: the group is regrouped with exact offsets
     // bucket_list: the launch covers only the listed buckets (the heavily loaded ones of a regrouping run whose other buckets
     // go through k_apply_sparse)
-    const uint32_t b = bucket_list ? bucket_list[blockIdx.x] : bucket0 + blockIdx.x;
+    const uint32_t b = bucket_list ? bucket_list[blockIdx.x / SPLIT] : bucket0 + blockIdx.x / SPLIT;
+    const uint32_t sub = blockIdx.x % SPLIT;
     const uint32_t tid = threadIdx.x;
     const uint32_t n = st.cursor[b];
     if (n == 0) return;
@@ -512,15 +516,16 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
 #pragma unroll 1
     for (int i = 1; i < L.n_tables; i++)
         if (b >= L.first[i]) t = i;
-    const uint64_t bin0 = (uint64_t)(b - L.first[t]) << BKT_SHIFT;
+    const uint64_t bin0 = ((uint64_t)(b - L.first[t]) << BKT_SHIFT) + (uint64_t)sub * SUB_BINS;
     const uint64_t size = S.sizes[t];
+    if (bin0 >= size) return;   // a part of the table's last bucket that lies past its end
     int changed = 0;
     uint8_t* table = S.tables[t];
     // bytes of the table this bucket covers, rounded up to the 16-byte granule of bulk copies (tables are allocated in
     // whole granules; bytes past the last bin are written back as they were read)
     const uint64_t tbytes = KIND == BYTE ? size : KIND == NIBBLE ? size / 2 + 1 : size / 8 + 1;
     const uint64_t byte0 = KIND == BYTE ? bin0 : KIND == NIBBLE ? bin0 >> 1 : bin0 >> 3;
-    uint32_t sbytes = (uint32_t)(tbytes - byte0 < slice_bytes_full<KIND>() ? tbytes - byte0 : slice_bytes_full<KIND>());
+    uint32_t sbytes = (uint32_t)(tbytes - byte0 < SUB_BYTES ? tbytes - byte0 : SUB_BYTES);
     sbytes = (sbytes + 15u) & ~15u;
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -530,17 +535,17 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     }
     {
         uint4* f = reinterpret_cast<uint4*>(minpos);
-        for (uint32_t i = tid; i < BKT_BINS / 4; i += 1024) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (uint32_t i = tid; i < SUB_BINS / 4; i += NTHR) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     if (gate) mbar_wait(bar, 0);   // ungated: the slice is first needed by the sweep, its load hides behind the record loop
-    constexpr int GPT = BKT_BINS / 8 / 1024;
+    constexpr int GPT = SUB_BINS / 8 / NTHR;
     if (KIND != BIT) {
         // touch lanes start at 0, with bit 15 set for bins that hold a count already: the value atomicAdd returns then tells
         // every record, at no extra cost, whether its bin was empty before the chunk — only those records can be a new k-mer's
         // first toucher and pay the atomicMin below
 #pragma unroll
         for (int q = 0; q < GPT; q++) {
-            const uint32_t g = q * 1024 + tid;
+            const uint32_t g = q * NTHR + tid;
             uint32_t w[4] = {0, 0, 0, 0};
             if (gate && (uint64_t)g * (KIND == BYTE ? 8 : 4) < sbytes) {
                 if (KIND == BYTE) {
@@ -559,17 +564,23 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     __syncthreads();
     const unsigned long long* src = st.rec + st.base(b);
     constexpr int RIF = 16;   // records in flight per thread
-    for (uint32_t e0 = 0; e0 < n; e0 += RIF * 1024) {
+    constexpr uint32_t ITER_REC = RIF * NTHR, CLAMP_EVERY = 32768u / ITER_REC;
+    for (uint32_t e0 = 0; e0 < n; e0 += ITER_REC) {
         unsigned long long v[RIF];
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
-            uint32_t e = e0 + j * 1024 + tid;
-            v[j] = e < n ? __ldcs(src + e) : ~0ull;
+            uint32_t e = e0 + j * NTHR + tid;
+            // the parts of a bucket run side by side and read the same records: the first reader brings them into L2 for the others
+            v[j] = e < n ? (SPLIT == 1 ? __ldcs(src + e) : __ldg(src + e)) : ~0ull;
         }
 #pragma unroll
         for (int j = 0; j < RIF; j++) {
             if (v[j] == ~0ull) continue;
-            const uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
+            uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
+            if (SPLIT > 1) {
+                if (lb / SUB_BINS != sub) continue;
+                lb &= SUB_BINS - 1;
+            }
             if (KIND == BIT) {
                 // a Bloom bit that is set already changes nothing
                 if (!gate || slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
@@ -585,11 +596,11 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
         // More records than a lane can count (15 bits when bit 15 is the "was occupied" flag, else 16): clamp every lane after each
         // 16 Ki (32 Ki) records to a value the next round cannot push into the flag bit or the neighbouring lane — any value >=
         // the counter's cap saturates it just the same.
-        const bool clamp_now = gate ? n > 32767u : (n > 65535u && ((e0 / (RIF * 1024)) & 1u));
+        const bool clamp_now = gate ? n > 32767u : (n > 65535u && (e0 / ITER_REC) % CLAMP_EVERY == CLAMP_EVERY - 1);
         if (KIND != BIT && clamp_now) {
             const uint32_t lim = gate ? 0x3FFFu : 0x7FFFu, keep = gate ? 0x80008000u : 0u, msk = gate ? 0x7FFFu : 0xFFFFu;
             __syncthreads();
-            for (uint32_t i = tid; i < BKT_BINS / 2; i += 1024) {
+            for (uint32_t i = tid; i < SUB_BINS / 2; i += NTHR) {
                 const uint32_t w = cnt[i];
                 const uint32_t lo = w & msk, hi = (w >> 16) & msk;
                 cnt[i] = (w & keep) | (lo > lim ? lim : lo) | ((hi > lim ? lim : hi) << 16);
@@ -602,7 +613,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     unsigned n_new = 0, n_sat = 0, n_cross = 0;
 #pragma unroll
     for (int q = 0; q < GPT; q++) {
-        const uint32_t g = q * 1024 + tid;
+        const uint32_t g = q * NTHR + tid;
         const uint64_t b0 = bin0 + (uint64_t)g * 8;
         unsigned newm = 0;
         if (KIND == BIT) {

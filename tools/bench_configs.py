@@ -2,7 +2,7 @@
 """Secondary measurements (not the bench line): the other BASELINE configs at their table sizes on ONE GPU, through the C ABI
 with device-resident batches (ingest) and host buffers (queries, normalization).  One JSON object per configuration.
 
-    python tools/bench_configs.py [C1 C2 C3 C4 C5 NORM ...]      (default: all)
+    python tools/bench_configs.py [--no-queries] [C1 C2 C3 C4 C5 NORM ...]      (default: all)
 """
 import json
 import os
@@ -17,7 +17,11 @@ import bench  # noqa: E402
 from khmer_b200 import cabi  # noqa: E402
 
 
+NO_QUERIES = "--no-queries" in sys.argv
+
+
 def run(name, storage, hashkind, k, x, n_reads=2_000_000, reps=2, bigcount=False, queries=True):
+    queries = queries and not NO_QUERIES
     sizes = bench.primes_near_x(4, int(x))
     t0 = time.perf_counter()
     sk = cabi.Sketch(storage, hashkind, k, sizes)
@@ -100,7 +104,7 @@ CONFIGS = {
 }
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["C1", "C2", "C3", "C4", "C4S", "C5M", "C5", "NORM"]
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["C1", "C2", "C3", "C4", "C4S", "C5M", "C5", "NORM"]
     for n in names:
         try:
             CONFIGS[n]()
