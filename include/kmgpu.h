@@ -288,6 +288,20 @@ int kmgpu_sync(kmgpu_t* h);
 int kmgpu_timer_start(kmgpu_t* h);
 int kmgpu_timer_stop(kmgpu_t* h, double* ms);
 
+/* ---- HyperLogLog registers (unique-kmers.py; HLLCounter, src/oxli/hllcounter.cc:262-317) -------------------------------
+ * The counter's ingest: for every k-mer of the reads, its canonical Murmur hash (_hash_murmur, kmer_hash.cc:177-198); register
+ * index = the hash's low n_counters_log2 bits, value = leading zeros of the remaining bits + 1; register = max(register, value).
+ * The registers are HLLCounter::counters (one byte each, 2^n_counters_log2 of them): estimate_cardinality() and its bias
+ * tables stay with the caller.  consume: HLLCounter::consume_string over every read (KMGPU_CLEAN: Read::set_clean_seq first, as
+ * consume_seqfile does); without KMGPU_CLEAN a byte outside ACGT fails with KMGPU_ENONACGT.
+ * merge_registers: HLLCounter::merge (replace == 0: element-wise max) / set_counters (replace != 0). */
+typedef struct kmgpu_hll kmgpu_hll_t;
+int kmgpu_hll_create(int device, int ksize, int n_counters_log2, kmgpu_hll_t** out);
+int kmgpu_hll_destroy(kmgpu_hll_t* c);
+int kmgpu_hll_consume(kmgpu_hll_t* c, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags, uint64_t* n_kmers_out);
+int kmgpu_hll_get_registers(kmgpu_hll_t* c, uint8_t* out);
+int kmgpu_hll_merge_registers(kmgpu_hll_t* c, const uint8_t* in, int replace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,7 +37,8 @@ SYMBOLS = [
     "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
     "kmgpu_shard_create", "kmgpu_shard_destroy", "kmgpu_shard_local", "kmgpu_shard_slice", "kmgpu_shard_ipc_export",
     "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_apply",
-    "kmgpu_shard_count_new", "kmgpu_shard_stats",
+    "kmgpu_shard_count_new", "kmgpu_shard_stats", "kmgpu_hll_create", "kmgpu_hll_destroy", "kmgpu_hll_consume",
+    "kmgpu_hll_get_registers", "kmgpu_hll_merge_registers",
 ]
 
 
@@ -80,6 +81,11 @@ def lib():
         L.kmgpu_batch_destroy.argtypes = [C.c_void_p]
         L.kmgpu_batch_info.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.kmgpu_consume_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Band), C.POINTER(Mask), u64p]
+        L.kmgpu_hll_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.kmgpu_hll_destroy.argtypes = [C.c_void_p]
+        L.kmgpu_hll_consume.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]
+        L.kmgpu_hll_get_registers.argtypes = [C.c_void_p, C.c_void_p]
+        L.kmgpu_hll_merge_registers.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.kmgpu_batch_read_medians.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kmgpu_add_hashes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.kmgpu_get_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -200,6 +206,42 @@ class Batch:
     def close(self):
         if self.h:
             lib().kmgpu_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HLL:
+    """HyperLogLog registers on the device (kmgpu_hll_*): the ingest of the reference's HLLCounter."""
+
+    def __init__(self, ksize, p, device=0):
+        self.p, self.ksize = p, ksize
+        self.h = C.c_void_p()
+        check(lib().kmgpu_hll_create(device, ksize, p, C.byref(self.h)))
+
+    def consume_reads(self, reads, clean=True):
+        buf, off = as_reads(reads)
+        n = C.c_uint64()
+        check(lib().kmgpu_hll_consume(self.h, _ptr(buf), _ptr(off), len(off) - 1, CLEAN if clean else 0, C.byref(n)))
+        return n.value
+
+    def registers(self):
+        out = np.zeros(1 << self.p, dtype=np.uint8)
+        check(lib().kmgpu_hll_get_registers(self.h, _ptr(out)))
+        return out
+
+    def merge_registers(self, regs, replace=False):
+        regs = np.ascontiguousarray(regs, dtype=np.uint8)
+        assert len(regs) == 1 << self.p
+        check(lib().kmgpu_hll_merge_registers(self.h, _ptr(regs), int(replace)))
+
+    def close(self):
+        if self.h:
+            lib().kmgpu_hll_destroy(self.h)
             self.h = None
 
     def __del__(self):

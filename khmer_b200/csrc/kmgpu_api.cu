@@ -363,15 +363,28 @@ static void launch_counts(int src, const SketchDev& S, HashCfg H, const Input& i
                           uint32_t nb, uint16_t* counts, uint64_t* hashes, const uint32_t* only_bits, cudaStream_t st)
 {
     unsigned g = n_tiles(in.n_pos);
-#define LC(KIND)                                                                                                          \
+#define LC(KIND, T0, T1)                                                                                                  \
     do {                                                                                                                  \
-        if (src == 1) k_counts<KIND, TWOBIT, 1><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits);   \
-        else if (H.kind == TWOBIT) k_counts<KIND, TWOBIT, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits); \
-        else k_counts<KIND, MURMUR, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits);            \
+        if (src == 1) k_counts<KIND, TWOBIT, 1><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits, T0, T1);   \
+        else if (H.kind == TWOBIT) k_counts<KIND, TWOBIT, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits, T0, T1); \
+        else k_counts<KIND, MURMUR, 0><<<g, THREADS, 0, st>>>(S, H, in, bk, bv, nb, counts, hashes, only_bits, T0, T1);            \
     } while (0)
-    if (S.kind == BYTE) LC(BYTE);
-    else if (S.kind == NIBBLE) LC(NIBBLE);
-    else LC(BIT);
+    // One table per launch when every table fits L2 by itself and the batch is large enough to re-use it (2-bit hashes are cheap
+    // to recompute; a 400 MB sketch read through 100 MB at a time turns HBM-random loads into L2 hits).  KMGPU_COUNT_PASSES=0: off.
+    static const bool passes_on = env_u64("KMGPU_COUNT_PASSES", 1) != 0;
+    static const uint64_t count_pass_max = env_u64("KMGPU_COUNT_PASS_MAX_MB", 110) * 1000000ull;
+    static const uint64_t count_pass_min_pos = env_u64("KMGPU_COUNT_PASS_MIN_POS", 1u << 22);   // tests: 1
+    bool passes = passes_on && counts && !only_bits && S.n_tables > 1 && in.n_pos >= count_pass_min_pos && (src == 1 || H.kind == TWOBIT);
+    for (int i = 0; passes && i < S.n_tables; i++) {
+        const uint64_t bytes = S.kind == BYTE ? S.sizes[i] : S.kind == NIBBLE ? S.sizes[i] / 2 : S.sizes[i] / 8;
+        if (bytes > count_pass_max) passes = false;
+    }
+    for (int t0 = 0; t0 < S.n_tables; t0 += passes ? 1 : S.n_tables) {
+        const int t1 = passes ? t0 + 1 : S.n_tables;
+        if (S.kind == BYTE) LC(BYTE, t0, t1);
+        else if (S.kind == NIBBLE) LC(NIBBLE, t0, t1);
+        else LC(BIT, t0, t1);
+    }
 #undef LC
 }
 
@@ -3332,3 +3345,108 @@ extern "C" int kmgpu_shard_count_new(kmgpu_shard_t* s, uint64_t* n_new_out)
     if (n_new_out) *n_new_out = h->h_ctrl->n_unique;
     return KMGPU_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// HyperLogLog registers (unique-kmers.py's counter)
+// ------------------------------------------------------------------------------------------------------
+struct kmgpu_hll {
+    kmgpu_sketch* stage = nullptr;   // a one-bin sketch: device, stream and the staging buffers of the read feed
+    int p = 0, k = 0;
+    DevBuf<uint32_t> regs;
+    DevBuf<uint8_t> bytes;
+};
+
+extern "C" int kmgpu_hll_destroy(kmgpu_hll_t* c)
+{
+    if (!c) return KMGPU_OK;
+    if (c->stage) {
+        cudaSetDevice(c->stage->device);
+        c->regs.release();
+        c->bytes.release();
+        kmgpu_destroy(c->stage);
+    }
+    delete c;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_hll_create(int device, int ksize, int n_counters_log2, kmgpu_hll_t** out)
+{
+    if (!out) return fail(KMGPU_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_counters_log2 < 4 || n_counters_log2 > 26) return fail(KMGPU_EINVAL, "log2(counters) %d out of range [4, 26]", n_counters_log2);
+    kmgpu_hll* c = new kmgpu_hll();
+    c->p = n_counters_log2;
+    c->k = ksize;
+    const uint64_t one = 2;
+    int rc = kmgpu_create(KMGPU_BIT, KMGPU_MURMUR, ksize, 1, &one, device, &c->stage);
+    if (rc != KMGPU_OK) {
+        delete c;
+        return rc;
+    }
+    const size_t n = (size_t)1 << c->p;
+    if (c->regs.ensure(n) != KMGPU_OK || c->bytes.ensure(n) != KMGPU_OK || cudaMemset(c->regs.p, 0, n * 4) != cudaSuccess) {
+        kmgpu_hll_destroy(c);
+        return fail(KMGPU_ENOMEM, "HLL registers");
+    }
+    *out = c;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_hll_consume(kmgpu_hll_t* c, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags, uint64_t* n_kmers_out)
+{
+    if (!c) return fail(KMGPU_EINVAL, "null handle");
+    if (n_kmers_out) *n_kmers_out = 0;
+    if (n_reads == 0) return KMGPU_OK;
+    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    kmgpu_sketch* h = c->stage;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    const HashCfg H{h->hash, h->k};
+    std::vector<ChunkPlan> plan;
+    plan_chunks(offsets, n_reads, h->k, chunk_bases(), plan);
+    uint64_t n_kmers = 0;
+    for (const ChunkPlan& cp : plan) {
+        ChunkDev cd;
+        CKR(stage_chunk(h, seqs, cp, flags, &cd, needs_acgt_check(h, flags)));
+        if (cd.n_pos == 0) continue;
+        k_hll<MURMUR, 0><<<n_tiles(cd.n_pos), THREADS, 0, h->stream>>>(H, make_input(cd), c->p, c->regs.p);
+        h->all_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));   // the staging buffers are reused by the next chunk
+        for (size_t j = 0; j + 1 < cp.offs.size(); j++) {
+            const uint32_t len = cp.offs[j + 1] - cp.offs[j];
+            if (len >= (uint32_t)h->k) n_kmers += len - h->k + 1;
+        }
+    }
+    if (n_kmers_out) *n_kmers_out = n_kmers;
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_hll_get_registers(kmgpu_hll_t* c, uint8_t* out)
+{
+    if (!c || !out) return fail(KMGPU_EINVAL, "null argument");
+    kmgpu_sketch* h = c->stage;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    const uint32_t n = 1u << c->p;
+    k_hll_bytes<<<(n + 255) / 256, 256, 0, h->stream>>>(c->regs.p, n, c->bytes.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->bytes.p, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+
+extern "C" int kmgpu_hll_merge_registers(kmgpu_hll_t* c, const uint8_t* in, int replace)
+{
+    if (!c || !in) return fail(KMGPU_EINVAL, "null argument");
+    kmgpu_sketch* h = c->stage;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    const uint32_t n = 1u << c->p;
+    CK(cudaMemcpyAsync(c->bytes.p, in, n, cudaMemcpyHostToDevice, h->stream));
+    k_hll_max_bytes<<<(n + 255) / 256, 256, 0, h->stream>>>(c->regs.p, n, c->bytes.p, replace);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return KMGPU_OK;
+}
+

@@ -1171,3 +1171,46 @@ k_ft_resolve(const FtEntry* __restrict__ ent, unsigned long long n, const LowerR
 }
 
 }  // namespace kmgpu
+
+namespace kmgpu {
+
+// =====================================================================================================================
+// 7. HyperLogLog registers (HLLCounter::add, src/oxli/hllcounter.cc:262-298; unique-kmers.py): for every k-mer, its
+//    canonical Murmur hash (_hash_murmur, kmer_hash.cc:177-198); register = low p bits, value = leading zeros of the
+//    remaining 64 - p bits + 1 (64 - p + 1 when they are all zero); registers[index] = max(registers[index], value).
+//    Registers are 32-bit words on the device (atomicMax), bytes at the ABI.  After the first few thousand k-mers almost
+//    no k-mer raises its register: the plain load in front of the atomic is what the kernel mostly does.
+// =====================================================================================================================
+template <int HK, int SRC>
+__global__ void __launch_bounds__(THREADS)
+k_hll(HashCfg H, Input in, int p, uint32_t* __restrict__ regs)
+{
+    __shared__ TileSmem sm;
+    const uint32_t t0 = blockIdx.x * TILE;
+    tile_begin<HK, SRC>(in, H.k, t0, sm);
+    const uint64_t mask = (1ull << p) - 1;
+#pragma unroll 1
+    for (uint32_t lp = threadIdx.x; lp < TILE; lp += THREADS) {
+        if (t0 + lp >= in.n_pos) break;
+        if (!tile_valid<HK, SRC>(sm, lp)) continue;
+        const uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
+        const uint64_t rest = h >> p;
+        const uint32_t v = (uint32_t)(rest ? __clzll((long long)rest) : 64) - (uint32_t)p + 1u;
+        uint32_t* r = regs + (h & mask);
+        if (*r < v) atomicMax(r, v);
+    }
+}
+
+__global__ void k_hll_bytes(const uint32_t* __restrict__ regs, uint32_t n, uint8_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)regs[i];
+}
+
+__global__ void k_hll_max_bytes(uint32_t* __restrict__ regs, uint32_t n, const uint8_t* __restrict__ in, int replace)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) regs[i] = replace ? (uint32_t)in[i] : max(regs[i], (uint32_t)in[i]);
+}
+
+}  // namespace kmgpu

@@ -504,8 +504,10 @@ k_cross_replay(SketchDev S, HashCfg H, Input in, const uint32_t* __restrict__ fl
 template <int KIND, int HK, int SRC>
 __global__ void __launch_bounds__(THREADS)
 k_counts(SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ big_keys, const uint16_t* __restrict__ big_vals,
-         uint32_t n_big, uint16_t* __restrict__ counts, uint64_t* __restrict__ hashes, const uint32_t* __restrict__ only_bits)
+         uint32_t n_big, uint16_t* __restrict__ counts, uint64_t* __restrict__ hashes, const uint32_t* __restrict__ only_bits, int t_lo, int t_hi)
 {
+    // tables [t_lo, t_hi): all of them in one launch, or one table per launch when every table fits L2 on its own (random loads
+    // from an L2-resident table run several times faster than from HBM; the later passes fold into counts[] with min)
     __shared__ TileSmem sm;
     const uint32_t t0 = blockIdx.x * TILE;
     tile_begin<HK, SRC>(in, H.k, t0, sm);
@@ -516,18 +518,18 @@ k_counts(SketchDev S, HashCfg H, Input in, const uint64_t* __restrict__ big_keys
         uint64_t h = tile_hash<HK, SRC>(in, sm, H.k, t0, lp);
         if (hashes) hashes[p] = h;
         if (!counts) continue;
-        uint32_t mn = counter_cap<KIND>();
-        for (int i0 = 0; i0 < S.n_tables; i0 += 4) {   // four tables at a time: all four loads in flight before the first is used
+        uint32_t mn = t_lo ? (uint32_t)counts[p] : counter_cap<KIND>();
+        for (int i0 = t_lo; i0 < t_hi; i0 += 4) {   // four tables at a time: all four loads in flight before the first is used
             uint32_t c[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int i = i0 + j < S.n_tables ? i0 + j : i0;
+                const int i = i0 + j < t_hi ? i0 + j : i0;
                 c[j] = read_counter<KIND>(S.tables[i], mod_magic(h, S.sizes[i], S.magic[i]));
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) mn = c[j] < mn ? c[j] : mn;
         }
-        if (KIND == BYTE && mn == 255u && n_big) {
+        if (KIND == BYTE && mn == 255u && n_big && t_hi == S.n_tables) {
             uint32_t lo = 0, hi = n_big;
             while (lo < hi) {
                 uint32_t mid = (lo + hi) >> 1;

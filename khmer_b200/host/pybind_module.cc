@@ -173,6 +173,17 @@ PYBIND11_MODULE(_oxli, m)
             for (size_t i = 0; i < n; i++) out.append(py::bytes(b.seqs + b.offsets[i], b.offsets[i + 1] - b.offsets[i]));
             return out;
         }, py::arg("max_bases") = (uint64_t)(64u << 20))
+        .def("read_batch_packed", [](PyParser& p, uint64_t max_bases) {
+            // the batch exactly as the device feed takes it: cleaned, 2-bit packed by the parser threads; returns (reads, bases)
+            ReadBatch b;
+            b.pack = true;
+            size_t n;
+            {
+                py::gil_scoped_release nogil;
+                n = p.parser->io().read_batch(max_bases, b);
+            }
+            return py::make_tuple(n, (uint64_t)b.n_bases);
+        }, py::arg("max_bases") = (uint64_t)(64u << 20))
         .def("__iter__", [](py::object self) { return self; })
         .def("__next__", [](PyParser& p) {
             try {

@@ -10,7 +10,9 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -276,6 +278,243 @@ private:
 }  // namespace
 
 namespace {
+
+unsigned parse_threads()
+{
+    static unsigned n = [] {
+        const char* e = getenv("KMGPU_PARSE_THREADS");
+        unsigned v = e && *e ? (unsigned)atoi(e) : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        return std::max(1u, std::min(v, 64u));
+    }();
+    return n;
+}
+
+// Decompressed bytes of a gzip / bzip2 file, produced ahead of the parser by a thread of its own: inflating costs several times
+// more than parsing, so it runs while the previous batch is parsed, packed and counted.  BGZF files (bgzip, the block-compressed
+// gzip of htslib: members of at most 64 KB whose header carries the member's compressed size) are inflated by all parser
+// threads at once; ordinary gzip has no block index and stays one sequential inflate (the reference reads it through seqan's
+// single zlib stream, src/oxli/read_parsers.cc:259-372).
+class Inflater {
+public:
+    static constexpr size_t BLOCK = 8u << 20;   // decompressed bytes per hand-over
+    static constexpr size_t AHEAD = 8;          // blocks produced ahead of the parser
+
+    Inflater(gzFile gz, void* bz, const std::string& path, bool bgzf) : gz_(gz), bz_(bz)
+    {
+        if (bgzf) {
+            fp_ = fopen(path.c_str(), "rb");
+            if (fp_) setvbuf(fp_, nullptr, _IOFBF, 4u << 20);
+        }
+        th_ = std::thread([this] { fp_ ? run_bgzf() : run_stream(); });
+    }
+    ~Inflater()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_room_.notify_all();
+        th_.join();
+        if (fp_) fclose(fp_);
+    }
+    // next block in stream order into `out`; false at the end of the stream, *err set if it ended in an error
+    bool next(std::vector<char>& out, bool* err)
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_data_.wait(g, [this] { return !ready_.empty() || done_; });
+        if (ready_.empty()) {
+            *err = error_;
+            return false;
+        }
+        out.swap(ready_.front());
+        ready_.pop_front();
+        g.unlock();
+        cv_room_.notify_one();
+        return true;
+    }
+    void recycle(std::vector<char>& v)
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (spare_.size() < AHEAD) spare_.emplace_back(std::move(v));
+    }
+    // is this file BGZF?  (first member: gzip, FEXTRA set, a 'B','C' subfield of two bytes)
+    static bool is_bgzf(const std::string& path)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        unsigned char h[4096];
+        const size_t n = fread(h, 1, sizeof h, f);
+        fclose(f);
+        uint32_t bsize = 0, xlen = 0;
+        return parse_header(h, n, &bsize, &xlen);
+    }
+
+private:
+    static bool parse_header(const unsigned char* h, size_t n, uint32_t* block_size, uint32_t* xlen_out)
+    {
+        if (n < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || (h[3] & ~4u)) return false;
+        const uint32_t xlen = h[10] | (h[11] << 8);
+        if (12 + (size_t)xlen > n) return false;
+        for (uint32_t o = 0; o + 4 <= xlen;) {
+            const unsigned char* sf = h + 12 + o;
+            const uint32_t slen = sf[2] | (sf[3] << 8);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && o + 6 <= xlen) {
+                *block_size = (uint32_t)(sf[4] | (sf[5] << 8)) + 1;
+                *xlen_out = xlen;
+                return *block_size >= 12 + xlen + 8;
+            }
+            o += 4 + slen;
+        }
+        return false;
+    }
+    std::vector<char> fresh()
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (!spare_.empty()) {
+            std::vector<char> v = std::move(spare_.back());
+            spare_.pop_back();
+            return v;
+        }
+        return std::vector<char>();
+    }
+    // false when the reader has gone away
+    bool push(std::vector<char>& v)
+    {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_room_.wait(g, [this] { return ready_.size() < AHEAD || stop_; });
+        if (stop_) return false;
+        ready_.emplace_back(std::move(v));
+        g.unlock();
+        cv_data_.notify_one();
+        return true;
+    }
+    void finish(bool error)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            done_ = true;
+            error_ = error;
+        }
+        cv_data_.notify_all();
+    }
+    void run_stream()
+    {
+        bool error = false;
+        while (true) {
+            std::vector<char> v = fresh();
+            v.resize(BLOCK);
+            int got;
+            if (bz_) {
+                got = bz2().read(bz_, v.data(), (int)BLOCK);
+                if (got < 0) { error = true; got = 0; }
+            } else {
+                got = gzread(gz_, v.data(), (unsigned)BLOCK);
+                if (got < 0) {
+                    error = true;
+                    got = 0;
+                } else if ((size_t)got < BLOCK) {
+                    int errnum = 0;
+                    gzerror(gz_, &errnum);
+                    if (errnum != Z_OK && errnum != Z_STREAM_END) error = true;   // truncated / corrupt stream
+                }
+            }
+            if (got == 0) break;
+            v.resize((size_t)got);
+            if (!push(v)) return;
+            if (error) break;
+        }
+        finish(error);
+    }
+    struct Member {
+        size_t c_off, c_len, out_off;
+        uint32_t isize, crc;
+    };
+    void run_bgzf()
+    {
+        const unsigned T = parse_threads();
+        Workers pool(T);
+        std::vector<z_stream> zs(T);
+        for (auto& z : zs) {
+            memset(&z, 0, sizeof z);
+            inflateInit2(&z, -15);
+        }
+        std::vector<unsigned char> comp;
+        std::vector<Member> mem;
+        bool error = false, eof = false;
+        while (!eof && !error) {
+            comp.clear();
+            mem.clear();
+            size_t total = 0;
+            while (total < BLOCK) {
+                unsigned char h[12];
+                const size_t n = fread(h, 1, 12, fp_);
+                if (n == 0) { eof = true; break; }
+                if (n < 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { error = true; break; }
+                const uint32_t xlen = h[10] | (h[11] << 8);
+                const size_t at = comp.size();
+                comp.resize(at + 12 + xlen);
+                memcpy(comp.data() + at, h, 12);
+                if (fread(comp.data() + at + 12, 1, xlen, fp_) != xlen) { error = true; break; }
+                uint32_t bsize = 0, xl = 0;
+                if (!parse_header(comp.data() + at, std::max<size_t>(18, 12 + xlen), &bsize, &xl)) { error = true; break; }
+                const size_t rest = bsize - 12 - xlen;
+                comp.resize(at + bsize);
+                if (fread(comp.data() + at + 12 + xlen, 1, rest, fp_) != rest) { error = true; break; }
+                const unsigned char* tr = comp.data() + at + bsize - 8;
+                Member m;
+                m.c_off = at + 12 + xlen;
+                m.c_len = rest - 8;
+                m.crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+                m.isize = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24);
+                m.out_off = total;
+                total += m.isize;
+                mem.push_back(m);
+            }
+            if (mem.empty() || total == 0) continue;
+            std::vector<char> v = fresh();
+            v.resize(total);
+            std::atomic<size_t> nextm(0);
+            std::atomic<bool> bad(false);
+            pool.run([&](unsigned t) {
+                z_stream& z = zs[t];
+                for (size_t i = nextm.fetch_add(1); i < mem.size(); i = nextm.fetch_add(1)) {
+                    const Member& m = mem[i];
+                    if (m.isize == 0) continue;
+                    inflateReset2(&z, -15);
+                    z.next_in = comp.data() + m.c_off;
+                    z.avail_in = (uInt)m.c_len;
+                    z.next_out = (Bytef*)v.data() + m.out_off;
+                    z.avail_out = m.isize;
+                    const int rc = inflate(&z, Z_FINISH);
+                    if (rc != Z_STREAM_END || z.avail_out != 0 ||
+                        crc32(crc32(0L, Z_NULL, 0), (const Bytef*)v.data() + m.out_off, m.isize) != m.crc)
+                        bad.store(true);
+                }
+            });
+            if (bad.load()) {
+                error = true;
+                break;
+            }
+            if (!push(v)) break;
+        }
+        for (auto& z : zs) inflateEnd(&z);
+        finish(error);
+    }
+
+    gzFile gz_;
+    void* bz_;
+    FILE* fp_ = nullptr;
+    std::thread th_;
+    std::mutex mu_;
+    std::condition_variable cv_data_, cv_room_;
+    std::deque<std::vector<char>> ready_;
+    std::vector<std::vector<char>> spare_;
+    bool done_ = false, error_ = false, stop_ = false;
+};
+
+}  // namespace
+
+namespace {
 struct Seg {            // a piece of sequence inside the mapping
     const char* p;
     uint32_t n;
@@ -297,6 +536,8 @@ struct FastxReader::Impl {
     std::string filename;
     gzFile gz = nullptr;
     void* bz = nullptr;
+    std::unique_ptr<Inflater> inflater;   // compressed input: blocks inflated ahead by its thread(s)
+    std::vector<char> spare;
     std::vector<char> buf;
     char* base = nullptr;      // parse window: buf.data() for compressed input, the mapping for plain files
     size_t pos = 0, end = 0;
@@ -316,31 +557,34 @@ struct FastxReader::Impl {
     bool fill()
     {
         if (eof) return false;
-        if (pos < end) {
-            memmove(buf.data(), buf.data() + pos, end - pos);
-        }
+        if (pos && pos < end) memmove(buf.data(), buf.data() + pos, end - pos);
         end -= pos;
         pos = 0;
+        if (inflater) {
+            bool err = false;
+            spare.clear();
+            const bool have = inflater->next(spare, &err);
+            if (err) read_error = true;
+            const size_t got = have ? spare.size() : 0;
+            if (buf.size() - end < got) buf.resize(std::max(buf.size() * 2, end + got));
+            base = buf.data();
+            if (got) memcpy(buf.data() + end, spare.data(), got);
+            if (have) inflater->recycle(spare);
+            if (got == 0) eof = true;
+            end += got;
+            return got > 0;
+        }
         if (buf.size() - end < (1u << 16)) buf.resize(buf.size() * 2);
         base = buf.data();
         int want = (int)std::min<size_t>(buf.size() - end, 1u << 30);
-        int got;
-        if (bz) {
-            got = bz2().read(bz, buf.data() + end, want);
-            if (got < 0) {
-                read_error = true;
-                got = 0;
-            }
-        } else {
-            got = gzread(gz, buf.data() + end, (unsigned)want);
-            if (got < 0) {
-                read_error = true;
-                got = 0;
-            } else if (got < want) {
-                int errnum = 0;
-                gzerror(gz, &errnum);
-                if (errnum != Z_OK && errnum != Z_STREAM_END) read_error = true;  // truncated / corrupt stream
-            }
+        int got = gzread(gz, buf.data() + end, (unsigned)want);
+        if (got < 0) {
+            read_error = true;
+            got = 0;
+        } else if (got < want) {
+            int errnum = 0;
+            gzerror(gz, &errnum);
+            if (errnum != Z_OK && errnum != Z_STREAM_END) read_error = true;  // truncated / corrupt stream
         }
         if (got == 0) eof = true;
         end += (size_t)got;
@@ -453,10 +697,12 @@ FastxReader::FastxReader(const std::string& filename) : _impl(new Impl())
         if (!bz2().lib) throw InvalidStream("File " + filename + " is bzip2-compressed and libbz2 is not available.");
         m.bz = bz2().open(filename.c_str(), "rb");
         if (!m.bz) throw InvalidStream(bad);
+        m.inflater.reset(new Inflater(nullptr, m.bz, filename, false));
     } else if (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
         m.gz = gzopen(filename.c_str(), "rb");
         if (!m.gz) throw InvalidStream(bad);
         gzbuffer(m.gz, 1u << 20);
+        m.inflater.reset(new Inflater(m.gz, nullptr, filename, Inflater::is_bgzf(filename)));
     } else {
         // plain file: map it; the serial routines parse straight out of the mapping (no refills), and
         // read_batch can hand slices of it to several threads
@@ -501,6 +747,7 @@ FastxReader::~FastxReader() { close(); }
 void FastxReader::close()
 {
     Impl& m = *_impl;
+    m.inflater.reset();   // joins the inflating thread before its stream goes away
     if (m.gz) gzclose(m.gz);
     if (m.bz) bz2().close(m.bz);
     m.gz = nullptr;
@@ -550,16 +797,6 @@ Read FastxReader::get_next_read()
 }
 
 namespace {
-
-unsigned parse_threads()
-{
-    static unsigned n = [] {
-        const char* e = getenv("KMGPU_PARSE_THREADS");
-        unsigned v = e && *e ? (unsigned)atoi(e) : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-        return std::max(1u, std::min(v, 64u));
-    }();
-    return n;
-}
 
 // first record start at or after p in [p, e): a line beginning with `kind`; for FASTQ the line two below must begin
 // with '+' (a quality line may begin with '@', but then the line two below it is a sequence line)
@@ -645,8 +882,8 @@ void parse_slice(Slice& s, char kind)
 
 }  // namespace
 
-// plain (memory-mapped) files: cut the next window of the mapping into slices at record boundaries and parse them
-// concurrently.  Any irregularity (empty sequence, quality length mismatch, multi-line FASTQ, stray bytes) makes the
+// plain (memory-mapped) files and the inflated window of compressed ones: cut the next window into slices at record
+// boundaries and parse them concurrently.  Any irregularity (empty sequence, quality length mismatch, multi-line FASTQ, stray bytes) makes the
 // whole window fall back to the serial parser, which then reports it exactly as the reference would.
 size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
 {
@@ -664,10 +901,13 @@ size_t FastxReader::read_batch(uint64_t max_bases, ReadBatch& out)
         const char* e = getenv("KMGPU_PARSE_MIN_BYTES");
         return e && *e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(4u << 20);
     }();
-    if (m.map && parse_threads() > 1 && m.end - m.pos > par_min) {
+    // window: enough bytes for ~max_bases bases (FASTQ spends about half its bytes on qualities)
+    const uint64_t want = m.kind == '@' ? max_bases * 2 + max_bases / 4 : max_bases + max_bases / 8;
+    if (m.inflater && parse_threads() > 1)   // compressed input: gather the window (and the margin the cut below looks into) first
+        while (!m.eof && m.end - m.pos < want + (2u << 20))
+            if (!m.fill()) break;
+    if ((m.map || m.inflater) && parse_threads() > 1 && m.end - m.pos > par_min) {
         const unsigned T = parse_threads();
-        // window: enough bytes for ~max_bases bases (FASTQ spends about half its bytes on qualities)
-        uint64_t want = m.kind == '@' ? max_bases * 2 + max_bases / 4 : max_bases + max_bases / 8;
         const char* b = m.base;
         const char* w0 = b + m.pos;
         const char* fe = b + m.end;

@@ -20,6 +20,7 @@
 #include "oxli/oxli.hh"
 #include "oxli/hashtable.hh"
 #include "oxli/hashgraph.hh"
+#include "oxli/hllcounter.hh"
 #include "oxli/kmer_hash.hh"
 #include "oxli/read_parsers.hh"
 #include "oxli/storage.hh"
@@ -308,6 +309,60 @@ int ref_save_tagset(void* h, const char* fn)
     if (!hg) { g_err = "not a Hashgraph"; return -1; }
     hg->save_tagset(fn);
     return 0;
+    REF_CATCH(-1)
+}
+
+
+// HLLCounter (khmer/_oxli/hllcounter.pyx; scripts/unique-kmers.py): n_counters = 2^p registers
+void* ref_hll_new(int n_counters, int ksize)
+{
+    REF_TRY
+    return new HLLCounter(n_counters, (WordLength)ksize);
+    REF_CATCH(nullptr)
+}
+
+void ref_hll_free(void* c) { delete (HLLCounter*)c; }
+
+int64_t ref_hll_consume_string(void* c, const char* s)
+{
+    REF_TRY
+    return (int64_t)((HLLCounter*)c)->consume_string(std::string(s));
+    REF_CATCH(-1)
+}
+
+int ref_hll_consume_seqfile(void* c, const char* fn, uint64_t* reads, uint64_t* n_consumed_out)
+{
+    REF_TRY
+    unsigned int total_reads = 0;
+    unsigned long long n_consumed = 0;
+    ((HLLCounter*)c)->consume_seqfile<FastxReader>(std::string(fn), false, total_reads, n_consumed);
+    *reads = total_reads;
+    *n_consumed_out = n_consumed;
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_hll_counters(void* c, uint8_t* out)
+{
+    REF_TRY
+    std::vector<uint8_t> v = ((HLLCounter*)c)->get_counters();
+    memcpy(out, v.data(), v.size());
+    return (int)v.size();
+    REF_CATCH(-1)
+}
+
+int ref_hll_set_counters(void* c, const uint8_t* in, int n)
+{
+    REF_TRY
+    ((HLLCounter*)c)->set_counters(std::vector<uint8_t>(in, in + n));
+    return 0;
+    REF_CATCH(-1)
+}
+
+int64_t ref_hll_estimate(void* c)
+{
+    REF_TRY
+    return (int64_t)((HLLCounter*)c)->estimate_cardinality();
     REF_CATCH(-1)
 }
 

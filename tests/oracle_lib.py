@@ -503,3 +503,67 @@ def read_fastx(path):
         else:
             i += 1
     return seqs
+
+
+# ---- HyperLogLog registers (HLLCounter, src/oxli/hllcounter.cc) --------------------------------------------
+def hll_consume(reads, k, p, counters=None, clean=True):
+    """plain-C restatement: (registers, k-mers consumed)"""
+    L = oracle_lib()
+    L.ko_hll_consume.restype = C.c_int64
+    L.ko_hll_consume.argtypes = [C.c_char_p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    seqs, off = pack_reads(reads)
+    regs = np.zeros(1 << p, dtype=np.uint8) if counters is None else np.ascontiguousarray(counters, dtype=np.uint8).copy()
+    n = L.ko_hll_consume(seqs, off.ctypes.data_as(u64p), len(off) - 1, k, p, int(clean), regs.ctypes.data)
+    return regs, n
+
+
+class RefHLL:
+    """the reference's HLLCounter (oracle/_ref)"""
+
+    def __init__(self, p, k):
+        self.L = ref_lib()
+        if not hasattr(self.L, "ref_hll_new"):
+            raise RefError("oracle/_ref was built before the HLL wrappers were added")
+        self.L.ref_hll_new.restype = C.c_void_p
+        self.L.ref_hll_new.argtypes = [C.c_int, C.c_int]
+        self.L.ref_hll_free.argtypes = [C.c_void_p]
+        self.L.ref_hll_consume_string.restype = C.c_int64
+        self.L.ref_hll_consume_string.argtypes = [C.c_void_p, C.c_char_p]
+        self.L.ref_hll_consume_seqfile.argtypes = [C.c_void_p, C.c_char_p, u64p, u64p]
+        self.L.ref_hll_counters.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.ref_hll_set_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.L.ref_hll_estimate.restype = C.c_int64
+        self.L.ref_hll_estimate.argtypes = [C.c_void_p]
+        self.p = p
+        self.h = self.L.ref_hll_new(1 << p, k)
+        if not self.h:
+            raise RefError(self.L.ref_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_hll_free(self.h)
+            self.h = None
+
+    def consume_string(self, s):
+        n = self.L.ref_hll_consume_string(self.h, _b(s))
+        if n < 0:
+            raise RefError(self.L.ref_last_error().decode())
+        return n
+
+    def consume_seqfile(self, path):
+        r, k = C.c_uint64(), C.c_uint64()
+        if self.L.ref_hll_consume_seqfile(self.h, _b(path), C.byref(r), C.byref(k)) < 0:
+            raise RefError(self.L.ref_last_error().decode())
+        return r.value, k.value
+
+    def counters(self):
+        out = np.zeros(1 << self.p, dtype=np.uint8)
+        assert self.L.ref_hll_counters(self.h, out.ctypes.data) == len(out)
+        return out
+
+    def set_counters(self, regs):
+        regs = np.ascontiguousarray(regs, dtype=np.uint8)
+        assert self.L.ref_hll_set_counters(self.h, regs.ctypes.data, len(regs)) == 0
+
+    def estimate(self):
+        return self.L.ref_hll_estimate(self.h)

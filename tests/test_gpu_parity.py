@@ -77,7 +77,7 @@ def _same_state(g, o, n_tables):
 @pytest.mark.parametrize("cls", list(ol.CLASSES))
 @pytest.mark.parametrize("chunk", [None, 4096, "cas-8192", "passes", "delta-blocks", "delta-cold", "delta-cold-stamps", "buckets",
                                    "buckets-overflow", "buckets-whole", "group", "group-whole", "group-regroup", "group-two",
-                                   "group-two-regroup", "group-turns", "group-t16k"])
+                                   "group-two-regroup", "group-turns", "group-t16k", "count-passes"])
 def test_gpu_vs_oracle_random(cls, chunk, monkeypatch):
     """Fresh seeded inputs, incremental calls (state carried across calls), tiny device chunks so that reads
     straddle chunks (the chunk size is read once per process: exercised through a subprocess for != None)."""

@@ -218,3 +218,37 @@ def test_batch_read_medians_equals_host_call(cls):
             assert (int(med[i]), np.float32(avg[i]).tobytes(), np.float32(sd[i]).tobytes()) == (m, np.float32(a).tobytes(), np.float32(s).tobytes())
     assert g.batch_read_medians(b, stats=False)[0].tolist() == med.tolist()
     b.close()
+
+
+@pytest.mark.parametrize("k,p", [(20, 14), (32, 10), (41, 16), (5, 4), (75, 12)])
+def test_hll_registers_equal_reference(k, p):
+    """kmgpu_hll_consume: the registers of the reference's HLLCounter (oracle restatement pinned to it in test_oracle.py; the
+    compiled reference itself where it travelled), over several calls, with dirty reads cleaned, merged with another counter"""
+    from khmer_b200 import cabi
+    reads_a = synth_reads(21, 3000, 150, 40000, err=0.01, with_n=True) + ["ACGT", "", "N" * 200, "acgtn" * 40]
+    reads_b = synth_reads(22, 2000, 90, 40000, err=0.0)
+    g = cabi.HLL(k, p)
+    n = g.consume_reads(reads_a, clean=True)
+    want, n_want = ol.hll_consume(reads_a, k, p, clean=True)
+    assert n == n_want and np.array_equal(g.registers(), want)
+    n2 = g.consume_reads(reads_b, clean=True)
+    want2, n_want2 = ol.hll_consume(reads_b, k, p, counters=want, clean=True)
+    assert n2 == n_want2 and np.array_equal(g.registers(), want2)
+    if ol.have_ref():
+        try:
+            ref = ol.RefHLL(p, k)
+        except ol.RefError:
+            ref = None
+        if ref is not None:
+            for r in reads_a + reads_b:
+                ref.consume_string(ol.clean(r))
+            assert np.array_equal(g.registers(), ref.counters())
+    other = cabi.HLL(k, p)
+    other.consume_reads(reads_b, clean=True)
+    other.merge_registers(want)                       # HLLCounter::merge
+    assert np.array_equal(other.registers(), want2)
+    other.merge_registers(want, replace=True)         # set_counters
+    assert np.array_equal(other.registers(), want)
+    if k > 32:
+        with pytest.raises(cabi.KmgpuError):
+            g.consume_reads(["ACGTNACGT" * 20], clean=False)   # Murmur hashes the letters themselves: non-ACGT needs cleaning

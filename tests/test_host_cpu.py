@@ -166,3 +166,77 @@ def test_parallel_batch_parser_falls_back_on_irregular_input(tmp_path):
     r = subprocess.run([sys.executable, "-c", code, str(bad)], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == "ValueError 2000 Sequence is empty"      # the good reads first, then the reference's error
+
+
+def _write_bgzf(path, data, block=30000):
+    """block-compressed gzip as bgzip writes it: members of <= 64 KB with a 'BC' extra subfield holding the member size, then
+    the empty end-of-file member"""
+    import struct
+    import zlib
+    with open(path, "wb") as fh:
+        for o in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if o is None else data[o:o + block]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = c.compress(chunk) + c.flush()
+            bsize = 12 + 6 + len(body) + 8
+            fh.write(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1))
+            fh.write(body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+
+def test_compressed_input_inflated_ahead_and_parsed_in_parallel(tmp_path):
+    """gzip / bzip2 input is inflated by a thread of its own and the inflated window parsed like a plain file; BGZF members are
+    inflated concurrently.  Records must equal the plain file's, whatever the batch size; a truncated stream must raise after
+    the reads before the damage."""
+    import bz2
+    import gzip
+    import subprocess
+    import sys
+    import numpy as np
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(30000):
+        n = int(rng.integers(30, 200))
+        s = "".join("ACGTN"[j] for j in rng.integers(0, 5, n))
+        q = "".join(chr(int(c)) for c in rng.integers(33, 74, n))
+        recs.append("@read%d\n%s\n+\n%s\n" % (i, s, q))
+    data = "".join(recs).encode()
+    plain = tmp_path / "r.fq"
+    plain.write_bytes(data)
+    (tmp_path / "r.fq.gz").write_bytes(gzip.compress(data, 4))
+    (tmp_path / "r2.fq.gz").write_bytes(gzip.compress(data[:len(data) // 2], 4) + gzip.compress(data[len(data) // 2:], 4))   # two members
+    (tmp_path / "r.fq.bz2").write_bytes(bz2.compress(data))
+    _write_bgzf(tmp_path / "r.bgzf.fq.gz", data)
+    assert gzip.decompress((tmp_path / "r.bgzf.fq.gz").read_bytes()) == data    # the hand-built file is valid gzip
+    want = [r.sequence for r in kh.ReadParser(str(plain))]
+    code = ("import sys; sys.path.insert(0, %r); import khmer_b200 as kh, hashlib\n"
+            "out = []\n"
+            "try:\n"
+            "    p = kh.ReadParser(sys.argv[1])\n"
+            "    while True:\n"
+            "        b = p.read_batch(int(sys.argv[2]))\n"
+            "        if not b: break\n"
+            "        out += b\n"
+            "    print(len(out), hashlib.md5(b'\\n'.join(out)).hexdigest())\n"
+            "except (OSError, ValueError) as e:\n"
+            "    print('error', len(out), type(e).__name__)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digest = hashlib.md5("\n".join(want).encode()).hexdigest()
+    for name in ("r.fq.gz", "r2.fq.gz", "r.fq.bz2", "r.bgzf.fq.gz"):
+        for threads, batch in (("1", "100000000"), ("4", "100000000"), ("5", "300000"), ("3", "20000")):
+            env = dict(os.environ, KMGPU_PARSE_THREADS=threads, KMGPU_PARSE_MIN_BYTES="1000")
+            r = subprocess.run([sys.executable, "-c", code, str(tmp_path / name), batch], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            assert r.stdout.split() == [str(len(want)), digest], (name, threads, batch, r.stdout)
+        assert [r.sequence for r in kh.ReadParser(str(tmp_path / name))] == want     # one read at a time
+    # damage: a gzip stream cut short, a BGZF member with a flipped byte
+    gz = (tmp_path / "r.fq.gz").read_bytes()
+    (tmp_path / "cut.fq.gz").write_bytes(gz[:len(gz) * 2 // 3])
+    bg = bytearray((tmp_path / "r.bgzf.fq.gz").read_bytes())
+    bg[len(bg) // 2] ^= 0x5A
+    (tmp_path / "bad.bgzf.fq.gz").write_bytes(bytes(bg))
+    for name in ("cut.fq.gz", "bad.bgzf.fq.gz"):
+        env = dict(os.environ, KMGPU_PARSE_THREADS="4", KMGPU_PARSE_MIN_BYTES="1000")
+        r = subprocess.run([sys.executable, "-c", code, str(tmp_path / name), "200000"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        tag, n, exc = r.stdout.split()
+        # (the damaged member lies in the first inflated block of the BGZF file: nothing of it is handed out)
+        assert tag == "error" and int(n) < len(want) and (int(n) > 0 or name.startswith("bad")) and exc in ("OSError", "ValueError"), r.stdout

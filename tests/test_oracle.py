@@ -244,3 +244,27 @@ def test_diginorm_reproduces_reference_script_md5s(datadir):
         keep, _ = o.normalize_reads(cleaned, cutoff)
         out = "".join(">%s\n%s\n" % (n, s) for (n, s), k in zip(recs, keep) if k)
         assert hashlib.md5(out.encode()).hexdigest() == want
+
+
+def test_hll_registers_restatement_equals_reference(datadir):
+    """ko_hll_consume (the restatement of HLLCounter::add / consume_string) against the compiled reference's HLLCounter:
+    identical registers on random-20-a.fa (consume_seqfile cleans the reads) and on strings fed one by one"""
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref not built")
+    reads = ol.read_fastx(os.path.join(datadir, "random-20-a.fa"))
+    for k, p in ((20, 14), (32, 10), (41, 16), (5, 4)):
+        ref = ol.RefHLL(p, k)
+        nr, nk = ref.consume_seqfile(os.path.join(datadir, "random-20-a.fa"))
+        regs, n = ol.hll_consume(reads, k, p, clean=True)
+        assert (nr, nk) == (len(reads), n)
+        assert np.array_equal(regs, ref.counters())
+        ref2 = ol.RefHLL(p, k)
+        tot = sum(ref2.consume_string(ol.clean(r)) for r in reads[:50])
+        regs2, n2 = ol.hll_consume(reads[:50], k, p, clean=True)
+        assert tot == n2 and np.array_equal(regs2, ref2.counters())
+    # the estimate stays with the reference: registers computed elsewhere are handed over with set_counters
+    ref3 = ol.RefHLL(14, 20)
+    ref3.set_counters(ol.hll_consume(reads, 20, 14)[0])
+    ref4 = ol.RefHLL(14, 20)
+    ref4.consume_seqfile(os.path.join(datadir, "random-20-a.fa"))
+    assert ref3.estimate() == ref4.estimate() > 0

@@ -97,6 +97,8 @@ CONFIGS = {
     "C2": lambda: run("C2 Nodegraph k=32 x=1e9 bits", cabi.BIT, cabi.TWOBIT, 32, 1e9),
     "C3": lambda: run("C3 Countgraph k=20 x=2e9 bytes (8 GB)", cabi.BYTE, cabi.TWOBIT, 20, 2e9, bigcount=True),
     "C4": lambda: run("C4 SmallCountgraph k=31 x=8e9 nibbles (16 GB)", cabi.NIBBLE, cabi.TWOBIT, 31, 8e9),
+    "C3L": lambda: run("C3 Countgraph k=20 x=2e9 bytes (8 GB), 5 M reads per batch (one chunk)", cabi.BYTE, cabi.TWOBIT, 20, 2e9, n_reads=5_000_000, bigcount=True, queries=False),
+    "C4L": lambda: run("C4 SmallCountgraph k=31 x=8e9 nibbles (16 GB), 5 M reads per batch (one chunk)", cabi.NIBBLE, cabi.TWOBIT, 31, 8e9, n_reads=5_000_000, queries=False),
     "C4S": lambda: run("C4-shape SmallCountgraph k=31 x=4e8 nibbles", cabi.NIBBLE, cabi.TWOBIT, 31, 4e8),
     "C5M": lambda: run("C5 hash path, Counttable k=40 (Murmur) x=1e8", cabi.BYTE, cabi.MURMUR, 40, 1e8, bigcount=False),
     "C5": lambda: run("C5 single-GPU slice, Counttable k=40 (Murmur) 4 x 3.2e10 bytes (128 GB)", cabi.BYTE, cabi.MURMUR, 40, 3.2e10, queries=False),

@@ -41,6 +41,10 @@ def main(rep, out):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
+    for i, h in enumerate(hdr):      # some columns carry a section prefix ("FBSP.TriageCompute.dram__throughput…")
+        for k in KEEP:
+            if h.endswith("." + k) and k not in idx:
+                idx[k] = i
     res = []
     for r in rows[2:]:
         if len(r) < len(hdr):
