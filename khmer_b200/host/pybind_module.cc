@@ -182,7 +182,9 @@ PYBIND11_MODULE(_oxli, m)
                 py::gil_scoped_release nogil;
                 n = p.parser->io().read_batch(max_bases, b);
             }
-            return py::make_tuple(n, (uint64_t)b.n_bases);
+            if (!n) return py::make_tuple(n, (uint64_t)0, py::bytes(), py::bytes());
+            return py::make_tuple(n, (uint64_t)b.n_bases, py::bytes((const char*)b.words(), b.n_words() * 8),
+                                  py::bytes((const char*)b.offsets.data(), b.offsets.size() * 8));
         }, py::arg("max_bases") = (uint64_t)(64u << 20))
         .def("__iter__", [](py::object self) { return self; })
         .def("__next__", [](PyParser& p) {

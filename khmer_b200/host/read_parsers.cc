@@ -9,6 +9,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <condition_variable>
@@ -179,6 +182,34 @@ struct PackLut {
 };
 const PackLut g_pack_lut;
 
+#if defined(__x86_64__)
+// 32 sequence bytes -> 64 bits, first base in the two most significant bits; bytes outside ACGTacgt give 0 ('A', as the cleaning
+// does).  (c >> 1) & 3 separates the four letters in either case (A 0, C 1, T 2, G 3); a byte shuffle turns that into khmer's code.
+__attribute__((target("avx2"))) inline uint64_t pack32_avx2(const char* p)
+{
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+    const __m256i t = _mm256_and_si256(_mm256_srli_epi16(x, 1), _mm256_set1_epi8(3));
+    const __m256i lut = _mm256_setr_epi8(0, 2, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 1, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i up = _mm256_and_si256(x, _mm256_set1_epi8((char)0xDF));
+    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(up, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(up, _mm256_set1_epi8('C'))),
+                                       _mm256_or_si256(_mm256_cmpeq_epi8(up, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(up, _mm256_set1_epi8('T'))));
+    const __m256i code = _mm256_and_si256(_mm256_shuffle_epi8(lut, t), ok);
+    const __m256i nib = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0104));          // pairs of bases: first * 4 + second
+    const __m256i byt = _mm256_madd_epi16(nib, _mm256_set1_epi32(0x00010010));         // pairs of those: first * 16 + second
+    // one byte (four bases) per 32-bit lane; gather them, first lane last, so that each half reads as a big-endian group
+    const __m256i sel = _mm256_setr_epi8(12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 12, 8, 4, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                         -1);
+    const __m256i g = _mm256_shuffle_epi8(byt, sel);
+    const uint32_t hi = (uint32_t)_mm256_extract_epi32(g, 0), lo = (uint32_t)_mm256_extract_epi32(g, 4);
+    return ((uint64_t)hi << 32) | lo;
+}
+inline bool have_avx2()
+{
+    static const bool v = __builtin_cpu_supports("avx2") && !(getenv("KMGPU_NO_SIMD") && *getenv("KMGPU_NO_SIMD") == '1');
+    return v;
+}
+#endif
+
 // Appends bases to a 2-bit stream at base position `at`.  Several packers may work on disjoint base ranges of one stream:
 // words that a range shares with its neighbours (the first and the last one it touches) are OR-ed in atomically — they
 // are zeroed, or hold an earlier range's bits, before the packers start — all others are plain stores.
@@ -193,7 +224,7 @@ struct Packer {
         else words[w] = acc;
         acc = 0;
     }
-    inline void add(const char* p, size_t n)
+    inline void add_scalar(const char* p, size_t n)
     {
         const uint8_t* lut = g_pack_lut.v;
         for (size_t i = 0; i < n; i++) {
@@ -202,6 +233,32 @@ struct Packer {
             at++;
             if ((at & 31) == 0) flush_word((at >> 5) - 1, (at >> 5) - 1 == first_word);
         }
+    }
+#if defined(__x86_64__)
+    __attribute__((target("avx2"))) void add_avx2(const char* p, size_t n)
+    {
+        size_t i = 0;
+        for (; i + 32 <= n; i += 32) {   // 32 bases complete the current word, whatever the offset within it
+            const uint64_t v = pack32_avx2(p + i);
+            const unsigned off = (unsigned)(at & 31);
+            acc |= v >> (2 * off);
+            const size_t w = at >> 5;
+            flush_word(w, w == first_word);
+            acc = off ? v << (64 - 2 * off) : 0;
+            at += 32;
+        }
+        add_scalar(p + i, n - i);
+    }
+#endif
+    inline void add(const char* p, size_t n)
+    {
+#if defined(__x86_64__)
+        if (n >= 32 && have_avx2()) {
+            add_avx2(p, n);
+            return;
+        }
+#endif
+        add_scalar(p, n);
     }
     inline void finish()
     {

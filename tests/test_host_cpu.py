@@ -240,3 +240,53 @@ def test_compressed_input_inflated_ahead_and_parsed_in_parallel(tmp_path):
         tag, n, exc = r.stdout.split()
         # (the damaged member lies in the first inflated block of the BGZF file: nothing of it is handed out)
         assert tag == "error" and int(n) < len(want) and (int(n) > 0 or name.startswith("bad")) and exc in ("OSError", "ValueError"), r.stdout
+
+
+def test_packed_batches_equal_cleaned_twobit(tmp_path):
+    """read_batch in pack mode (what the device feed uploads): 2 bits per base, first base in the top bits of each 64-bit word,
+    A0 T1 C2 G3, every other byte cleaned to A — with and without the SIMD packer, for several thread counts and batch sizes"""
+    import subprocess
+    import sys
+    import numpy as np
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNnRY.-*", dtype=np.uint8)
+    seqs = []
+    fa = tmp_path / "mix.fa"
+    with open(fa, "wb") as fh:
+        for i in range(6000):
+            n = int(rng.integers(1, 400))
+            s = alphabet[rng.integers(0, len(alphabet) if i % 3 == 0 else 4, n)].tobytes()
+            seqs.append(s)
+            fh.write(b">r%d\n" % i)
+            for o in range(0, n, 97):
+                fh.write(s[o:o + 97] + b"\n")
+    code_of = np.zeros(256, dtype=np.uint64)
+    for ch, v in ((b"T", 1), (b"t", 1), (b"C", 2), (b"c", 2), (b"G", 3), (b"g", 3)):
+        code_of[ch[0]] = v
+    allb = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    codes = code_of[allb]
+    pad = (-len(codes)) % 32
+    codes = np.concatenate([codes, np.zeros(pad, dtype=np.uint64)]).reshape(-1, 32)
+    want_words = (codes << (np.uint64(62) - np.uint64(2) * np.arange(32, dtype=np.uint64))).sum(axis=1, dtype=np.uint64)
+    want_off = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+    code = ("import sys; sys.path.insert(0, %r); import khmer_b200 as kh, numpy as np, hashlib\n"
+            "p = kh.ReadParser(sys.argv[1]); words = []; offs = [np.zeros(1, dtype=np.uint64)]; bases = 0\n"
+            "while True:\n"
+            "    n, nb, w, o = p.read_batch_packed(int(sys.argv[2]))\n"
+            "    if not n: break\n"
+            "    w = np.frombuffer(w, dtype=np.uint64); o = np.frombuffer(o, dtype=np.uint64)\n"
+            "    # batches are independent streams: unpack to codes and re-concatenate\n"
+            "    c = ((w[:, None] >> (np.uint64(62) - np.uint64(2) * np.arange(32, dtype=np.uint64))) & np.uint64(3)).reshape(-1)[:nb]\n"
+            "    words.append(c.astype(np.uint8)); offs.append(o[1:] + np.uint64(bases)); bases += nb\n"
+            "allc = np.concatenate(words)\n"
+            "print(bases, hashlib.md5(allc.tobytes()).hexdigest(), hashlib.md5(np.concatenate(offs).tobytes()).hexdigest())\n"
+            ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want_codes = code_of[allb].astype(np.uint8)
+    want = "%d %s %s" % (len(allb), hashlib.md5(want_codes.tobytes()).hexdigest(), hashlib.md5(want_off.tobytes()).hexdigest())
+    assert int(want_words[0]) >> 62 == int(code_of[allb[0]])
+    for simd in ("0", "1"):
+        for threads, batch in (("1", "100000000"), ("4", "100000000"), ("5", "70000"), ("3", "9000")):
+            env = dict(os.environ, KMGPU_PARSE_THREADS=threads, KMGPU_PARSE_MIN_BYTES="1000", KMGPU_NO_SIMD=simd)
+            r = subprocess.run([sys.executable, "-c", code, str(fa), batch], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            assert r.stdout.strip() == want, (simd, threads, batch)
