@@ -571,7 +571,7 @@ def run_ours(args):
     value = hbm["kmers"] / (hbm["ms"] * 1e-3)
     e2e_value = e2e["kmers"] / (e2e["ms"] * 1e-3)
     peak, peak_src = measured_peak()
-    # the ingest kernel group (hash once, then scatter + fold per table block); algorithmic bytes of the timed
+    # the ingest kernel group (hash, group by bucket, apply in shared memory); algorithmic bytes of the timed
     # launches = k-mers ingested x N x 64 B, divided by the summed group durations (CUDA events on the library's stream)
     kmers_per_launch = hbm["local_kmers"] / max(1, hbm["kern_launches"])
     avg_launch_ms = hbm["kern_ms"] / max(1, hbm["kern_launches"])
@@ -579,7 +579,9 @@ def run_ours(args):
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_kmer"] * kmers_per_launch if traffic else None,
-                "kernel": "ingest kernel group per chunk: k_part (fused hash + grouping) + k_apply2<BYTE> + k_popc (grouped path)",
+                "kernel": ("ingest kernel group per chunk: k_part (fused hash + grouping) + k_apply2<BYTE> + k_popc (grouped path, KMGPU_PREFER_BINS=0)"
+                           if os.environ.get("KMGPU_PREFER_BINS") == "0" else
+                           "ingest kernel group per chunk: k_hashbins + k_bucketize + k_apply<BYTE> + k_popc (bins path, the default for this shape)"),
                 "kernel_ms_per_launch": avg_launch_ms, "kernel_launches": int(hbm["kern_launches"]),
                 "kmers_per_launch": kmers_per_launch, "algorithmic_bytes_per_launch": kmers_per_launch * ALGO_BYTES_PER_KMER,
                 "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
@@ -667,6 +669,11 @@ def run_sharded(args):
         t0 = time.perf_counter()
         n = sh.route((buf, off), clean=True)
         barrier()
+        ta = time.perf_counter()
+        sh.offsets()
+        barrier()
+        sh.push()
+        barrier()
         t1 = time.perf_counter()
         sh.apply()
         barrier()
@@ -674,16 +681,17 @@ def run_sharded(args):
         sh.count_new()
         barrier()
         t3 = time.perf_counter()
-        t[0] += t1 - t0
+        t[0] += ta - t0
         t[1] += t2 - t1
         t[2] += t3 - t2
+        t[3] += t1 - ta
         return n
 
-    t = [0.0, 0.0, 0.0]
+    t = [0.0, 0.0, 0.0, 0.0]
     for s in range(args.warmup):
         step(s, t)
     barrier()
-    t = [0.0, 0.0, 0.0]
+    t = [0.0, 0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     kmers = 0
     for s in range(args.steps):
@@ -710,8 +718,9 @@ def run_sharded(args):
                                    "synthetic 150bp 30x reads, %d reads per GPU and round" % (x, world, sum(sizes) / world / 1e9, R),
                        "table_bytes_per_gpu": sum(sizes) // world, "receive_store_bytes_per_gpu": store_bytes,
                        "timing": "wall clock between barriers (each phase ends in a device synchronisation), max over ranks"},
-            "phases_ms_per_step": {"route": 1e3 * float(mx[2]) / args.steps, "apply": 1e3 * float(mx[3]) / args.steps,
-                                   "count_new": 1e3 * float(mx[4]) / args.steps},
+            "phases_ms_per_step": {"route (hash + group locally)": 1e3 * float(mx[2]) / args.steps,
+                                   "exchange (offsets + push over NVLink)": 1e3 * float(mx[5]) / args.steps,
+                                   "apply": 1e3 * float(mx[3]) / args.steps, "count_new": 1e3 * float(mx[4]) / args.steps},
             # every counter update is an 8-byte record written into its owner's HBM; (world - 1) / world of them cross NVLink
             "nvlink_bytes_per_kmer": N_TABLES * 8.0 * (world - 1) / world,
             "n_occupied": occ, "n_unique_kmers": uniq, "gpu_launches": int(sh.local.profile_get()[2]),

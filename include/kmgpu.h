@@ -246,19 +246,26 @@ int kmgpu_first_touch_log(kmgpu_t* h, int on);
 int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64_t* n_local_out, uint64_t* hist);
 
 /* ---- multi-GPU, address-sharded sketches ---------------------------------
- * For tables too large to replicate: bins [r*S_i, (r+1)*S_i) of table i live on rank r (S_i = slice length).  Every rank
- * hashes its own reads and writes each counter update — grouped by the owner's super-bucket (2^27 bins), 64-bit bins —
- * straight into the owner's record store in HBM over NVLink peer memory: the k-mer all-to-all, fused into the hashing pass.
- * Every owner then groups what it received by 32 Ki-bin bucket and applies it in shared memory like a local chunk.
- * Positions are global across the ranks of a round (rank * max_positions + position in the rank's reads, i.e. the stream
- * order is rank 0's reads, then rank 1's, ...), so the first toucher of a bin is decided across ranks and n_unique_kmers is
- * exact: it equals one sketch fed the rounds in that order.  Collective protocol per round (the caller provides the barriers):
- *     kmgpu_shard_route  ->  barrier  ->  kmgpu_shard_apply  ->  barrier  ->  kmgpu_shard_count_new  ->  barrier
+ * For tables too large to replicate: rank r holds the bins [r*S_i, (r+1)*S_i) of table i (S_i: a whole number of super-buckets
+ * of 2^(15+s) bins, see kmgpu_shard_slice) as an ordinary local sketch.  A round of the k-mer exchange:
+ *     kmgpu_shard_route    every rank hashes its own reads, groups the counter updates by super-bucket of the FULL tables
+ *                          (64-bit bins) in its own HBM and posts the per-super-bucket record counts to the owners
+ *     kmgpu_shard_offsets  every owner lays out its receive arena exactly (per super-bucket, the senders' runs side by side)
+ *     kmgpu_shard_push     every sender writes its runs — contiguous, hundreds of KB each — straight into the owners' arenas over
+ *                          NVLink peer memory (plain stores from a copy kernel; no NCCL, no staging on the receiving side)
+ *     kmgpu_shard_apply    every owner groups what it received by 32 Ki-bin bucket and applies it in shared memory like a chunk
+ *     kmgpu_shard_count_new
+ * with a barrier (provided by the caller) after each step; every rank takes part in every round, with zero reads if it has
+ * none left.  Positions are global across the ranks of a round (rank * max_positions + position in the rank's reads, i.e. the
+ * stream order is rank 0's reads, then rank 1's, ...), so the first toucher of a bin is decided across ranks and n_unique_kmers
+ * is exact: it equals one sketch fed the rounds in that order.  Heavily repeated k-mers cannot overflow anything (regions are
+ * exact); a round is refused (KMGPU_ENOMEM from kmgpu_shard_apply on that rank, nothing applied there) only if one owner is sent
+ * more than 1.5 x its average share of a full round.
  * Table bytes and n_occupied are exact (concatenated slices / summed counters equal the single sketch); n_unique_kmers is the
  * sum of the ranks' shares (kmgpu_shard_stats); bigcount is not maintained in this mode.  The saved table is the
  * concatenation of the ranks' slices in rank order (kmgpu_shard_slice + the local sketch's kmgpu_download_table). */
 typedef struct kmgpu_shard kmgpu_shard_t;
-#define KMGPU_SHARD_IPC_HANDLES 4 /* record store, cursors, overflow word, new-position bitmap */
+#define KMGPU_SHARD_IPC_HANDLES 5 /* receive arena, demand table, receive offsets, refusal word, new-position bitmap */
 #define KMGPU_MAX_WORLD 16
 int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables, const uint64_t* full_sizes, int device,
                        int rank, int world, uint64_t max_positions_per_route, kmgpu_shard_t** out);
@@ -274,6 +281,8 @@ int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all_handles);
 int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n);
 int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                       uint64_t* n_kmers_out);
+int kmgpu_shard_offsets(kmgpu_shard_t* s);
+int kmgpu_shard_push(kmgpu_shard_t* s);
 int kmgpu_shard_apply(kmgpu_shard_t* s);
 int kmgpu_shard_count_new(kmgpu_shard_t* s, uint64_t* n_new_out);
 

@@ -36,7 +36,7 @@ SYMBOLS = [
     "kmgpu_reduce_replicas", "kmgpu_attach_replicas", "kmgpu_profile_reset", "kmgpu_profile_get", "kmgpu_sync", "kmgpu_reset",
     "kmgpu_timer_start", "kmgpu_timer_stop", "kmgpu_slice_range", "kmgpu_alloc_pinned", "kmgpu_free_pinned",
     "kmgpu_shard_create", "kmgpu_shard_destroy", "kmgpu_shard_local", "kmgpu_shard_slice", "kmgpu_shard_ipc_export",
-    "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_apply",
+    "kmgpu_shard_ipc_attach", "kmgpu_shard_attach_local", "kmgpu_shard_route", "kmgpu_shard_offsets", "kmgpu_shard_push", "kmgpu_shard_apply",
     "kmgpu_shard_count_new", "kmgpu_shard_stats", "kmgpu_hll_create", "kmgpu_hll_destroy", "kmgpu_hll_consume",
     "kmgpu_hll_get_registers", "kmgpu_hll_merge_registers",
 ]
@@ -142,6 +142,8 @@ def lib():
         L.kmgpu_shard_attach_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.kmgpu_shard_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]
         L.kmgpu_shard_apply.argtypes = [C.c_void_p]
+        L.kmgpu_shard_offsets.argtypes = [C.c_void_p]
+        L.kmgpu_shard_push.argtypes = [C.c_void_p]
         L.kmgpu_shard_count_new.argtypes = [C.c_void_p, u64p]
         L.kmgpu_shard_stats.argtypes = [C.c_void_p, u64p, u64p, u64p]
         _lib = L
@@ -512,7 +514,7 @@ class Sketch:
         return ms.value
 
 
-SHARD_IPC_HANDLES = 4
+SHARD_IPC_HANDLES = 5
 
 
 class Shard:
@@ -563,6 +565,12 @@ class Shard:
         n = C.c_uint64()
         check(lib().kmgpu_shard_route(self.h, _ptr(buf), _ptr(off), len(off) - 1, CLEAN if clean else 0, C.byref(n)))
         return n.value
+
+    def offsets(self):
+        check(lib().kmgpu_shard_offsets(self.h))
+
+    def push(self):
+        check(lib().kmgpu_shard_push(self.h))
 
     def apply(self):
         check(lib().kmgpu_shard_apply(self.h))

@@ -2973,12 +2973,16 @@ extern "C" int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64
 // ------------------------------------------------------------------------------------------------------
 // multi-GPU: address-sharded sketches (k-mer all-to-all over NVLink peer memory, see include/kmgpu.h)
 //
-// Rank r holds bins [r * slice_i, (r + 1) * slice_i) of table i as an ordinary local sketch.  A round: every rank hashes
-// its own reads and k_part MODE 3 writes each counter update, already grouped by the owner's super-bucket, straight into
-// the owner's record store over peer memory (route); after a barrier every owner groups what it received by bucket and
-// applies it in shared memory like any chunk (apply: k_part MODE 2 + k_apply2 / k_apply_sparse); positions are global
-// (rank * max_positions + position), so "first toucher of a bin" is decided across ranks, and after another barrier every
-// rank counts the positions of ITS reads that some owner marked new (count_new) — n_unique_kmers is exact.
+// Rank r holds a whole number of super-buckets of every table as an ordinary local sketch.  A round:
+//   route   every rank hashes its own reads and groups the counter updates by super-bucket of the FULL tables (k_part MODE 1,
+//           local; regions that overflow are regrouped exactly like any chunk), then posts its per-super-bucket counts to the
+//           owners (k_shard_post, a few KB over NVLink)
+//   offsets every owner lays out its receive arena exactly: per super-bucket, the senders' runs side by side (k_shard_scan)
+//   push    every sender writes its runs into the owners' arenas (k_shard_push: contiguous 8-byte stores into peer memory)
+//   apply   every owner groups what it received by bucket and applies it in shared memory (k_part MODE 2 + k_apply2 / _sparse)
+//   count   positions are global (rank * max_positions + position), so "first toucher of a bin" is decided across ranks;
+//           every rank ORs the owners' new-position bitmaps for ITS positions — n_unique_kmers is exact
+// with a barrier after each step.
 // ------------------------------------------------------------------------------------------------------
 struct kmgpu_shard {
     kmgpu_sketch* local = nullptr;
@@ -2986,21 +2990,37 @@ struct kmgpu_shard {
     uint64_t full_sizes[MAX_TABLES];
     uint64_t slice[MAX_TABLES];
     SketchDev full;   // full-table sizes and magics: what the k-mers are hashed against
-    GroupPlan G;      // layout of one rank's slices (the same on every rank) and region sizes for max_positions per rank and round
+    GroupPlan GF;     // layout of the full tables (route): super-buckets only
+    GroupPlan G;      // layout of one rank's slices (the same on every rank): apply
+    ShardGeom geom;
     uint64_t max_positions = 0;
-    unsigned long long* rec1 = nullptr;    // received records, by super-bucket
-    uint32_t* cur1 = nullptr;
-    unsigned long long* flags = nullptr;   // bit 0: a region of this rank was cut short by a sender
+    uint64_t arena = 0;                    // records the receive arena holds
+    uint32_t n_sb_local = 0;               // super-buckets per rank, all tables
+    // receive side (peers write / read these)
+    unsigned long long* rec1 = nullptr;    // arena
+    uint32_t* demand = nullptr;            // [local super-bucket * world + sender]
+    unsigned long long* recv_off = nullptr;
+    unsigned long long* flags = nullptr;   // bit 0: this round does not fit the arena
     uint32_t* newbits = nullptr;           // one bit per global position of a round: marked new by this owner
     struct PeerQ {
         unsigned long long* rec1;
-        uint32_t* cur1;
+        uint32_t* demand;
+        unsigned long long* recv_off;
         unsigned long long* flags;
         uint32_t* newbits;
     } peers[MAX_WORLD];
+    // owner side
+    DevBuf<unsigned long long> sb_off;
+    DevBuf<uint32_t> sb_cnt;
+    uint32_t max_cnt = 0;
+    uint64_t received = 0;
+    bool refused = false;
+    // sender side
+    DevBuf<unsigned long long> rec_s, off_s;
+    DevBuf<uint32_t> cur_s;
+    bool exact_s = false;
     bool attached = false, ipc = false;
     uint64_t n_unique = 0;   // k-mers of this rank's reads that were new
-    uint64_t routed_overflow = 0;
 };
 
 extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s);
@@ -3016,6 +3036,8 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
     max_positions = ((max_positions + 127) / 128) * 128;   // every rank's range of the new-position bitmaps starts on 16 bytes
     if (max_positions > chunk_bases() || (uint64_t)world * max_positions >= (1ull << 32))
         return fail(KMGPU_EINVAL, "max_positions %llu too large (positions of a round are 32-bit across all ranks)", (unsigned long long)max_positions);
+    for (int i = 0; i < n_tables; i++)
+        if (full_sizes[i] == 0 || full_sizes[i] >= (1ull << 55)) return fail(KMGPU_EINVAL, "table size %llu out of range", (unsigned long long)full_sizes[i]);
     kmgpu_shard* s = new kmgpu_shard();
     s->rank = rank;
     s->world = world;
@@ -3023,21 +3045,40 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
     s->max_positions = max_positions;
     memset(&s->full, 0, sizeof s->full);
     memset(s->peers, 0, sizeof s->peers);
-    uint64_t local_sizes[MAX_TABLES], nominal[MAX_TABLES];
-    for (int i = 0; i < n_tables; i++) {
-        if (full_sizes[i] == 0 || full_sizes[i] >= (1ull << 55)) {
+    memset(&s->geom, 0, sizeof s->geom);
+    {
+        // layout of the FULL tables: super-buckets of 2^(15 + shift) bins, at most PART_MAXP of them per table (one grouping pass)
+        kmgpu_sketch full_shape;
+        full_shape.nt = n_tables;
+        full_shape.kind = storage;
+        for (int i = 0; i < n_tables; i++) full_shape.sizes[i] = full_sizes[i];
+        if (!plan_group(&full_shape, (uint32_t)max_positions, true, &s->GF, true) || !s->GF.L.two_level) {
             delete s;
-            return fail(KMGPU_EINVAL, "table size %llu out of range", (unsigned long long)full_sizes[i]);
+            return fail(KMGPU_EUNSUPPORTED, "tables of this size cannot be grouped");
         }
+    }
+    const int shift = s->GF.L.sb_shift;
+    uint64_t local_sizes[MAX_TABLES], nominal[MAX_TABLES];
+    s->geom.n_tables = n_tables;
+    s->geom.world = world;
+    s->geom.rank = rank;
+    for (int i = 0; i < n_tables; i++) {
         s->full_sizes[i] = full_sizes[i];
-        uint64_t per = (full_sizes[i] + world - 1) / world;
-        s->slice[i] = ((per + 127) / 128) * 128;  // slices start on a byte of every storage kind
+        const uint32_t nsb = s->GF.L.first_sb[i + 1] - s->GF.L.first_sb[i];
+        const uint32_t per = (nsb + world - 1) / world;
+        s->geom.first_sb[i] = s->GF.L.first_sb[i];
+        s->geom.sb_per_rank[i] = per;
+        s->geom.local_first[i] = s->n_sb_local;
+        s->n_sb_local += per;
+        s->slice[i] = (uint64_t)per << (BKT_SHIFT + shift);   // a whole number of super-buckets: the owner of a record is a division
         uint64_t lo = std::min<uint64_t>(full_sizes[i], s->slice[i] * rank), hi = std::min<uint64_t>(full_sizes[i], s->slice[i] * (rank + 1));
-        local_sizes[i] = std::max<uint64_t>(hi - lo, 1);  // a rank past the end of a tiny table keeps a dummy bin
+        local_sizes[i] = std::max<uint64_t>(hi - lo, 1);  // a rank past the end of a table keeps a dummy bin
         nominal[i] = s->slice[i];
         s->full.sizes[i] = full_sizes[i];
         s->full.magic[i] = ~0ull / full_sizes[i];
     }
+    s->geom.first_sb[n_tables] = s->GF.L.first_sb[n_tables];
+    s->geom.local_first[n_tables] = s->n_sb_local;
     s->full.n_tables = n_tables;
     s->full.kind = storage;
     int rc = kmgpu_create(storage, hash, ksize, n_tables, local_sizes, device, &s->local);
@@ -3046,29 +3087,28 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
         return rc;
     }
     {
-        // one layout for every rank: buckets and super-buckets of the NOMINAL slice; regions sized for what all ranks together
-        // send an owner in a round when each hashes max_positions positions (= max_positions per owner on average)
+        // one layout for every rank: buckets and super-buckets of the NOMINAL slice, with the full tables' super-bucket size
         kmgpu_sketch nominal_shape;
         nominal_shape.nt = n_tables;
         nominal_shape.kind = storage;
         for (int i = 0; i < n_tables; i++) nominal_shape.sizes[i] = nominal[i];
-        const bool ok = plan_group(&nominal_shape, (uint32_t)max_positions, true, &s->G, true, (uint32_t)(PART_MAXP / world),
-                                   (uint64_t)world * max_positions);
-        if (!ok || !s->G.L.two_level) {
+        const bool ok = plan_group(&nominal_shape, (uint32_t)max_positions, true, &s->G, true, PART_MAXP, (uint64_t)world * max_positions, shift);
+        if (!ok || !s->G.L.two_level || s->G.n_sb != s->n_sb_local) {
             kmgpu_shard_destroy(s);
             return fail(KMGPU_EUNSUPPORTED, "slices of this size cannot be grouped");
         }
-        for (int i = 0; i < n_tables; i++)
-            if ((uint64_t)(s->G.L.first_sb[i + 1] - s->G.L.first_sb[i]) * world > (uint64_t)PART_MAXP) {
-                kmgpu_shard_destroy(s);
-                return fail(KMGPU_EUNSUPPORTED, "table %d: %u super-buckets per rank x %d ranks exceed what one routing pass sorts into (%d)", i,
-                            s->G.L.first_sb[i + 1] - s->G.L.first_sb[i], world, PART_MAXP);
-            }
     }
+    // the arena: what all ranks together send an owner in a round is N x max_positions records on average; half as much again
+    // for owners that hold more than their share of the k-mers (a round that still does not fit is refused, see kmgpu_shard_offsets)
+    s->arena = (uint64_t)n_tables * max_positions * 3 / 2 + 4096;
+    if (uint64_t f = env_u64("KMGPU_SHARD_ARENA", 0)) s->arena = f;   // tests
     const size_t nb_words = (size_t)world * max_positions / 32;
-    cudaError_t e = cudaMalloc(&s->rec1, (size_t)s->G.n_sb * s->G.L.cap1 * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&s->cur1, (size_t)s->G.n_sb * 4);
-    if (e == cudaSuccess) e = cudaMemset(s->cur1, 0, (size_t)s->G.n_sb * 4);
+    const size_t n_dem = (size_t)s->n_sb_local * world;
+    cudaError_t e = cudaMalloc(&s->rec1, s->arena * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->demand, n_dem * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->demand, 0, n_dem * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&s->recv_off, (n_dem + 1) * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->recv_off, 0, (n_dem + 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->flags, 8);
     if (e == cudaSuccess) e = cudaMemset(s->flags, 0, 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->newbits, nb_words * 4);
@@ -3090,14 +3130,21 @@ extern "C" int kmgpu_shard_destroy(kmgpu_shard_t* s)
         for (int q = 0; q < s->world; q++) {
             if (q == s->rank) continue;
             if (s->peers[q].rec1) cudaIpcCloseMemHandle(s->peers[q].rec1);
-            if (s->peers[q].cur1) cudaIpcCloseMemHandle(s->peers[q].cur1);
+            if (s->peers[q].demand) cudaIpcCloseMemHandle(s->peers[q].demand);
+            if (s->peers[q].recv_off) cudaIpcCloseMemHandle(s->peers[q].recv_off);
             if (s->peers[q].flags) cudaIpcCloseMemHandle(s->peers[q].flags);
             if (s->peers[q].newbits) cudaIpcCloseMemHandle(s->peers[q].newbits);
         }
     if (s->rec1) cudaFree(s->rec1);
-    if (s->cur1) cudaFree(s->cur1);
+    if (s->demand) cudaFree(s->demand);
+    if (s->recv_off) cudaFree(s->recv_off);
     if (s->flags) cudaFree(s->flags);
     if (s->newbits) cudaFree(s->newbits);
+    s->sb_off.release();
+    s->sb_cnt.release();
+    s->rec_s.release();
+    s->off_s.release();
+    s->cur_s.release();
     if (s->local) kmgpu_destroy(s->local);
     delete s;
     return KMGPU_OK;
@@ -3118,7 +3165,7 @@ extern "C" int kmgpu_shard_stats(kmgpu_shard_t* s, uint64_t* n_occupied_local, u
     if (!s) return fail(KMGPU_EINVAL, "null shard");
     if (n_occupied_local) *n_occupied_local = s->local->n_occupied;
     if (n_unique_share) *n_unique_share = s->n_unique;
-    if (store_bytes) *store_bytes = (uint64_t)s->G.n_sb * s->G.L.cap1 * 8;
+    if (store_bytes) *store_bytes = s->arena * 8;
     return KMGPU_OK;
 }
 
@@ -3126,7 +3173,7 @@ extern "C" int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles)
 {
     if (!s || !handles) return fail(KMGPU_EINVAL, "null argument");
     CKR(set_device(s->local->device));
-    void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->cur1, s->flags, s->newbits};
+    void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->demand, s->recv_off, s->flags, s->newbits};
     for (int i = 0; i < KMGPU_SHARD_IPC_HANDLES; i++) {
         cudaIpcMemHandle_t mh;
         CK(cudaIpcGetMemHandle(&mh, ptrs[i]));
@@ -3135,22 +3182,28 @@ extern "C" int kmgpu_shard_ipc_export(kmgpu_shard_t* s, uint8_t* handles)
     return KMGPU_OK;
 }
 
+static void shard_set_peer(kmgpu_shard* s, int q, void* const* ptrs)
+{
+    s->peers[q].rec1 = (unsigned long long*)ptrs[0];
+    s->peers[q].demand = (uint32_t*)ptrs[1];
+    s->peers[q].recv_off = (unsigned long long*)ptrs[2];
+    s->peers[q].flags = (unsigned long long*)ptrs[3];
+    s->peers[q].newbits = (uint32_t*)ptrs[4];
+}
+
 extern "C" int kmgpu_shard_ipc_attach(kmgpu_shard_t* s, const uint8_t* all)
 {
     if (!s || !all) return fail(KMGPU_EINVAL, "null argument");
     CKR(set_device(s->local->device));
     for (int q = 0; q < s->world; q++) {
-        void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->cur1, s->flags, s->newbits};
+        void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {s->rec1, s->demand, s->recv_off, s->flags, s->newbits};
         if (q != s->rank)
             for (int i = 0; i < KMGPU_SHARD_IPC_HANDLES; i++) {
                 cudaIpcMemHandle_t mh;
                 memcpy(&mh, all + ((size_t)q * KMGPU_SHARD_IPC_HANDLES + i) * KMGPU_IPC_HANDLE_BYTES, KMGPU_IPC_HANDLE_BYTES);
                 CK(cudaIpcOpenMemHandle(&ptrs[i], mh, cudaIpcMemLazyEnablePeerAccess));
             }
-        s->peers[q].rec1 = (unsigned long long*)ptrs[0];
-        s->peers[q].cur1 = (uint32_t*)ptrs[1];
-        s->peers[q].flags = (unsigned long long*)ptrs[2];
-        s->peers[q].newbits = (uint32_t*)ptrs[3];
+        shard_set_peer(s, q, ptrs);
     }
     s->attached = true;
     s->ipc = true;
@@ -3172,10 +3225,8 @@ extern "C" int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n)
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
                 cudaGetLastError();
             }
-            all[a]->peers[b].rec1 = all[b]->rec1;
-            all[a]->peers[b].cur1 = all[b]->cur1;
-            all[a]->peers[b].flags = all[b]->flags;
-            all[a]->peers[b].newbits = all[b]->newbits;
+            void* ptrs[KMGPU_SHARD_IPC_HANDLES] = {all[b]->rec1, all[b]->demand, all[b]->recv_off, all[b]->flags, all[b]->newbits};
+            shard_set_peer(all[a], b, ptrs);
         }
         all[a]->attached = true;
         all[a]->ipc = false;
@@ -3183,73 +3234,168 @@ extern "C" int kmgpu_shard_attach_local(kmgpu_shard_t** all, int n)
     return KMGPU_OK;
 }
 
+static void shard_peers(const kmgpu_shard* s, ShardPeers* P)
+{
+    memset(P, 0, sizeof *P);
+    for (int q = 0; q < s->world; q++) {
+        P->demand[q] = s->peers[q].demand;
+        P->recv_off[q] = s->peers[q].recv_off;
+        P->rec[q] = s->peers[q].rec1;
+        P->flags[q] = s->peers[q].flags;
+    }
+}
+
+// route: group my reads' counter updates by super-bucket of the full tables (locally), post the counts to the owners.
+// n_reads == 0: a rank without reads in this round still posts (zero) counts.
 extern "C" int kmgpu_shard_route(kmgpu_shard_t* s, const char* seqs, const uint64_t* offsets, uint64_t n_reads, uint32_t flags,
                                  uint64_t* n_kmers_out)
 {
     if (!s) return fail(KMGPU_EINVAL, "null shard");
     if (n_kmers_out) *n_kmers_out = 0;
     if (!s->attached) return fail(KMGPU_EINVAL, "peers are not attached");
-    if (n_reads == 0) return KMGPU_OK;
-    if (!seqs || !offsets) return fail(KMGPU_EINVAL, "null input");
+    if (n_reads && (!seqs || !offsets)) return fail(KMGPU_EINVAL, "null input");
     kmgpu_sketch* h = s->local;
-    const uint64_t first = offsets[0], last = offsets[n_reads];
+    const uint64_t first = n_reads ? offsets[0] : 0, last = n_reads ? offsets[n_reads] : 0;
     if (last - first > s->max_positions)
         return fail(KMGPU_EINVAL, "%llu bases in one route call; this shard was created for at most %llu", (unsigned long long)(last - first),
                     (unsigned long long)s->max_positions);
-    if (last == first) return KMGPU_OK;
     std::lock_guard<std::mutex> g(h->mu);
     CKR(set_device(h->device));
     cudaStream_t st = h->stream;
-    ChunkDev cd;
-    CKR(stage_range(h, seqs, offsets, n_reads, first, last, flags, &cd, needs_acgt_check(h, flags), 0, st));
-    Input in = make_input(cd);
+    const GroupLayout& LF = s->GF.L;
+    const uint32_t n_sb = s->GF.n_sb;
+    CKR(s->cur_s.ensure(n_sb));
+    CK(cudaMemsetAsync(s->cur_s.p, 0, (size_t)n_sb * 4, st));
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
-    CK(cudaEventRecord(h->ev0, st));
-    const HashCfg H{h->hash, h->k};
-    int srck = 0;
-    if (H.kind == MURMUR) {
-        CKR(h->d_hash64.ensure(in.n_pos));
-        k_hash64<MURMUR><<<n_tiles(in.n_pos), THREADS, 0, st>>>(H, in, h->d_hash64.p);
-        in.hashes = h->d_hash64.p;
-        srck = 1;
+    s->exact_s = false;
+    uint64_t n_kmers = 0;
+    if (last > first) {
+        ChunkDev cd;
+        CKR(stage_range(h, seqs, offsets, n_reads, first, last, flags, &cd, needs_acgt_check(h, flags), 0, st));
+        Input in = make_input(cd);
+        CK(cudaEventRecord(h->ev0, st));
+        const HashCfg H{h->hash, h->k};
+        int srck = 0;
+        if (H.kind == MURMUR) {
+            CKR(h->d_hash64.ensure(in.n_pos));
+            k_hash64<MURMUR><<<n_tiles(in.n_pos), THREADS, 0, st>>>(H, in, h->d_hash64.p);
+            in.hashes = h->d_hash64.p;
+            srck = 1;
+            h->all_launches += 1;
+        }
+        if (!try_ensure(s->rec_s, std::max<uint64_t>((uint64_t)n_sb * LF.cap1, 2))) return fail(KMGPU_ENOMEM, "no room for the sender's record store");
+        PartArgs A;
+        memset(&A, 0, sizeof A);
+        A.S = s->full;
+        A.H = H;
+        A.in = in;
+        A.pos_base = (uint32_t)((uint64_t)s->rank * s->max_positions);
+        A.have_valid = 1;
+        A.table0 = 0;
+        A.count_kmers = 1;
+        A.L = LF;
+        A.ctrl = h->d_ctrl;
+        A.dst = Store{s->rec_s.p, nullptr, s->cur_s.p, LF.cap1, 0};
+        A.ovf_bit = 1ull;
+        Pred P0;
+        memset(&P0, 0, sizeof P0);
+        uint32_t np = 0;
+        for (int t = 0; t < s->nt; t++) np = std::max(np, LF.first_sb[t + 1] - LF.first_sb[t]);
+        const dim3 grid((in.n_pos + 8191) / 8192, s->nt);
+        CKR(launch_part(1, srck, false, 8192, true, np, grid, st, A, s->full, P0));
         h->all_launches += 1;
+        CK(cudaGetLastError());
+        CKR(read_ctrl(h));
+        n_kmers = h->h_ctrl->n_kmers;
+        if (h->h_ctrl->overflow) {
+            // a super-bucket region ran out of room (heavily repeated k-mers): the cursors hold the exact demand, regroup into
+            // exact regions
+            CKR(s->off_s.ensure((size_t)n_sb + 1));
+            k_exact_offsets<<<1, 1024, 0, st>>>(s->cur_s.p, n_sb, s->off_s.p);
+            unsigned long long total = 0;
+            CK(cudaMemcpyAsync(&total, s->off_s.p + n_sb, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!try_ensure(s->rec_s, std::max<size_t>((size_t)total, 2))) return fail(KMGPU_ENOMEM, "no room for the sender's record store");
+            CK(cudaMemsetAsync(s->cur_s.p, 0, (size_t)n_sb * 4, st));
+            CK(cudaMemsetAsync(&h->d_ctrl->overflow, 0, sizeof(unsigned long long), st));
+            A.dst = Store{s->rec_s.p, s->off_s.p, s->cur_s.p, 0, 0};
+            A.count_kmers = 0;
+            A.ovf_bit = 1ull << 63;
+            CKR(launch_part(1, srck, false, 8192, true, np, grid, st, A, s->full, P0));
+            h->all_launches += 2;
+            h->n_regroups++;
+            s->exact_s = true;
+            CK(cudaGetLastError());
+            CKR(read_ctrl(h));
+            if (h->h_ctrl->overflow) return fail(KMGPU_ECUDA, "internal: regrouping run overflowed");
+        }
+        CK(cudaEventRecord(h->ev1, st));
     }
-    ShardRoute R;
-    memset(&R, 0, sizeof R);
-    R.world = s->world;
-    for (int q = 0; q < s->world; q++) {
-        R.rec[q] = s->peers[q].rec1;
-        R.cursor[q] = s->peers[q].cur1;
-        R.flags[q] = s->peers[q].flags;
+    ShardPeers PP;
+    shard_peers(s, &PP);
+    k_shard_post<<<(n_sb + 255) / 256, 256, 0, st>>>(s->geom, s->cur_s.p, n_sb, PP);
+    h->all_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    if (last > first) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ingest_ms += ms;
     }
-    for (int i = 0; i < s->nt; i++) {
-        R.slice[i] = s->slice[i];
-        R.slice_magic[i] = ~0ull / s->slice[i];
-    }
-    PartArgs A;
-    memset(&A, 0, sizeof A);
-    A.S = s->full;
-    A.H = H;
-    A.in = in;
-    A.pos_base = (uint32_t)((uint64_t)s->rank * s->max_positions);
-    A.have_valid = 1;
-    A.table0 = 0;
-    A.count_kmers = 1;
-    A.L = s->G.L;
-    A.ctrl = h->d_ctrl;
-    Pred P0;
-    memset(&P0, 0, sizeof P0);
-    const dim3 grid((in.n_pos + 8191) / 8192, s->nt);
-    if (srck) CKR((launch_part_inst<8192, 512, 3, 1, false, false, 12>(grid, st, A, s->full, P0, R)));
-    else CKR((launch_part_inst<8192, 512, 3, 0, false, false, 12>(grid, st, A, s->full, P0, R)));
+    if (n_kmers_out) *n_kmers_out = n_kmers;
+    return KMGPU_OK;
+}
+
+// offsets (owner): exact layout of what this round sends me; a round larger than the arena is refused (flag read by the senders)
+extern "C" int kmgpu_shard_offsets(kmgpu_shard_t* s)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    kmgpu_sketch* h = s->local;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    const uint32_t n_dem = s->n_sb_local * (uint32_t)s->world;
+    CKR(s->sb_off.ensure((size_t)s->n_sb_local + 1));
+    CKR(s->sb_cnt.ensure(std::max<uint32_t>(s->n_sb_local, 1)));
+    unsigned int* mx = reinterpret_cast<unsigned int*>(&h->d_ctrl->n_events);
+    CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
+    k_shard_scan<<<1, 1024, 0, st>>>(s->demand, n_dem, s->recv_off);
+    k_shard_sb<<<(s->n_sb_local + 256) / 256, 256, 0, st>>>(s->recv_off, s->n_sb_local, s->world, s->sb_off.p, s->sb_cnt.p, mx);
+    h->all_launches += 2;
+    CK(cudaGetLastError());
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, s->recv_off + n_dem, 8, cudaMemcpyDeviceToHost, st));
+    CKR(read_ctrl(h));
+    s->max_cnt = (uint32_t)h->h_ctrl->n_events;
+    s->received = total;
+    s->refused = total > s->arena;
+    const unsigned long long fl = s->refused ? 1ull : 0ull;
+    CK(cudaMemcpyAsync(s->flags, &fl, 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return KMGPU_OK;
+}
+
+// push (sender): my runs into the owners' arenas
+extern "C" int kmgpu_shard_push(kmgpu_shard_t* s)
+{
+    if (!s) return fail(KMGPU_EINVAL, "null shard");
+    kmgpu_sketch* h = s->local;
+    std::lock_guard<std::mutex> g(h->mu);
+    CKR(set_device(h->device));
+    cudaStream_t st = h->stream;
+    if (!s->rec_s.p) return KMGPU_OK;   // nothing was ever routed
+    ShardPeers PP;
+    shard_peers(s, &PP);
+    const Store src = s->exact_s ? Store{s->rec_s.p, s->off_s.p, s->cur_s.p, 0, 0} : Store{s->rec_s.p, nullptr, s->cur_s.p, s->GF.L.cap1, 0};
+    CK(cudaEventRecord(h->ev0, st));
+    k_shard_push<<<dim3(s->GF.n_sb, 8), 256, 0, st>>>(s->geom, src, PP);
     h->all_launches += 1;
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
-    CKR(read_ctrl(h));
+    CK(cudaStreamSynchronize(st));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->ingest_ms += ms;
-    if (n_kmers_out) *n_kmers_out = h->h_ctrl->n_kmers;
     return KMGPU_OK;
 }
 
@@ -3261,16 +3407,18 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
     CKR(set_device(h->device));
     if (h->kind == BYTE && h->use_bigcount) return fail(KMGPU_EUNSUPPORTED, "bigcount is not maintained by sharded sketches");
     cudaStream_t st = h->stream;
-    unsigned long long fl = 0;
-    CK(cudaMemcpyAsync(&fl, s->flags, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (fl) {
+    const size_t n_dem = (size_t)s->n_sb_local * s->world;
+    if (s->refused) {
+        s->refused = false;
         CK(cudaMemsetAsync(s->flags, 0, 8, st));
-        CK(cudaMemsetAsync(s->cur1, 0, (size_t)s->G.n_sb * 4, st));
-        return fail(KMGPU_ENOMEM, "a receive region of rank %d overflowed (heavily repeated k-mers): the round was not applied; create the shards with a "
-                                  "smaller max_positions_per_route", s->rank);
+        CK(cudaMemsetAsync(s->demand, 0, n_dem * 4, st));
+        CK(cudaStreamSynchronize(st));
+        return fail(KMGPU_ENOMEM, "rank %d was sent %llu records in one round, its arena holds %llu (this rank owns far more than its share of the "
+                                  "k-mers): the round was not applied; create the shards with a smaller max_positions_per_route",
+                    s->rank, (unsigned long long)s->received, (unsigned long long)s->arena);
     }
-    const GroupPlan& G = s->G;
+    GroupPlan G = s->G;
+    G.L.cap1 = std::max<uint32_t>(s->max_cnt, 2);   // the level-2 pass covers the fullest super-bucket
     const uint32_t n_pos_all = (uint32_t)((uint64_t)s->world * s->max_positions);
     CKR(h->d_cursors.ensure(G.n_buckets));
     if (!try_ensure(h->d_records, std::max<uint64_t>((uint64_t)G.n_buckets * G.L.cap, 2)))
@@ -3280,14 +3428,14 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
     CK(cudaMemsetAsync(h->d_ctrl, 0, sizeof(Ctrl), st));
     CK(cudaEventRecord(h->ev0, st));
     const GroupTurn tn{0, h->nt, 0, G.n_buckets, 0, G.n_sb};
-    const Store s1{s->rec1, nullptr, s->cur1, G.L.cap1, 0};
+    const Store s1{s->rec1, s->sb_off.p, s->sb_cnt.p, 0, 0};
     SatBitsG sb;
     memset(&sb, 0, sizeof sb);
     Pred P0;
     memset(&P0, 0, sizeof P0);
     const HashCfg H{h->hash, h->k};
     const std::vector<Part> none;
-    CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, 0u, n_pos_all, 1, 0, sb, &s1, s->newbits));
+    if (s->received) CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, 0u, n_pos_all, 1, 0, sb, &s1, s->newbits));
     CK(cudaEventRecord(h->ev1, st));
     CKR(read_ctrl(h));
     float ms = 0;
@@ -3300,14 +3448,14 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
         CKR(group_turn(h, G, tn, 0, 0, H, none, P0, false, h->dev, false, bits, n_pos_all, 1, 0, sb, &s1, s->newbits));
         CKR(read_ctrl(h));
         if (h->h_ctrl->overflow) return fail(KMGPU_ECUDA, "internal: regrouping run overflowed");
-        // bucket regions get more slack from the next round on (the receive regions were sized at creation and stay)
+        // bucket regions get more slack from the next round on
         const uint32_t cap_now = s->G.L.cap;
         s->G.L.cap = (uint32_t)std::min<uint64_t>(((uint64_t)cap_now * 3 / 2 + 1) & ~1ull, (uint64_t)n_pos_all + 2);
         s->G.wide = s->G.L.cap > 65535;
         s->G.sparse = s->G.sparse && s->G.L.cap <= SPARSE_MAX_RECORDS;
     }
     h->n_occupied += h->h_ctrl->n_z0;
-    CK(cudaMemsetAsync(s->cur1, 0, (size_t)s->G.n_sb * 4, st));
+    CK(cudaMemsetAsync(s->demand, 0, n_dem * 4, st));   // ranks without reads in a later round post nothing for tables they do not reach
     CK(cudaStreamSynchronize(st));
     h->satbits_valid = false;
     return KMGPU_OK;

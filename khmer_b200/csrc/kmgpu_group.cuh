@@ -1214,3 +1214,114 @@ __global__ void k_hll_max_bytes(uint32_t* __restrict__ regs, uint32_t n, const u
 }
 
 }  // namespace kmgpu
+
+namespace kmgpu {
+
+// =====================================================================================================================
+// 8. Address-sharded sketches: the k-mer exchange.  Every rank groups its own counter updates by
+//    super-bucket of the FULL tables (k_part MODE 1; a rank's slice is a whole number of super-buckets, so "owner" is a
+//    division of the super-bucket index), tells every owner how many records it holds for each of the owner's super-buckets
+//    (k_shard_post), the owner lays its receive arena out exactly (k_shard_scan, k_shard_sb: per super-bucket, per sender),
+//    and every sender then writes its runs — contiguous, hundreds of KB each — straight into the owner's HBM over NVLink
+//    peer memory (k_shard_push).  No per-record remote atomics, no staging on the receiving side, no NCCL.
+// =====================================================================================================================
+struct ShardGeom {
+    uint32_t first_sb[G_MAXT + 1];      // full-table layout: table i owns global super-buckets [first_sb[i], first_sb[i+1])
+    uint32_t sb_per_rank[G_MAXT];       // super-buckets of table i held by every rank (the last ranks may hold fewer or none)
+    uint32_t local_first[G_MAXT + 1];   // a rank's local numbering: table i starts at local_first[i] (= prefix sums of sb_per_rank)
+    int n_tables, world, rank;
+};
+
+struct ShardPeers {
+    uint32_t* demand[MAX_WORLD];                 // [local super-bucket * world + sender]
+    const unsigned long long* recv_off[MAX_WORLD];   // same indexing (+1): where that sender's run starts in the owner's arena
+    unsigned long long* rec[MAX_WORLD];          // the owner's arena
+    const unsigned long long* flags[MAX_WORLD];  // bit 0: the owner's arena cannot hold this round
+};
+
+__device__ __forceinline__ void shard_owner(const ShardGeom& G, uint32_t g, int* owner, uint32_t* local)
+{
+    int t = 0;
+#pragma unroll 1
+    for (int i = 1; i < G.n_tables; i++)
+        if (g >= G.first_sb[i]) t = i;
+    const uint32_t sb = g - G.first_sb[t];
+    const uint32_t q = sb / G.sb_per_rank[t];
+    *owner = (int)q;
+    *local = G.local_first[t] + (sb - q * G.sb_per_rank[t]);
+}
+
+// my record counts per global super-bucket -> the owners' demand tables
+__global__ void k_shard_post(const __grid_constant__ ShardGeom G, const uint32_t* __restrict__ count, uint32_t n_sb_total, const __grid_constant__ ShardPeers P)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_sb_total) return;
+    int q;
+    uint32_t j;
+    shard_owner(G, g, &q, &j);
+    P.demand[q][(size_t)j * G.world + G.rank] = count[g];
+}
+
+// exclusive scan (no padding between entries): off[i] for i in [0, n], single CTA
+__global__ void __launch_bounds__(1024) k_shard_scan(const uint32_t* __restrict__ cnt, uint32_t n, unsigned long long* __restrict__ off)
+{
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned long long v = i < n ? cnt[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads();
+        unsigned long long before = s_carry;
+        for (uint32_t w = 0; w < wid; w++) before += s_w[w];
+        if (i < n) off[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = s_carry;
+}
+
+// per local super-bucket: where its records start (all senders' runs are adjacent) and how many there are; the largest count
+__global__ void k_shard_sb(const unsigned long long* __restrict__ recv_off, uint32_t n_sb_local, int world, unsigned long long* __restrict__ sb_off,
+                           uint32_t* __restrict__ sb_cnt, unsigned int* max_cnt)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n_sb_local) return;
+    const unsigned long long a = recv_off[(size_t)j * world];
+    sb_off[j] = a;
+    if (j < n_sb_local) {
+        const uint32_t c = (uint32_t)(recv_off[(size_t)(j + 1) * world] - a);
+        sb_cnt[j] = c;
+        atomicMax(max_cnt, c);
+    }
+}
+
+// my runs go to their owners: grid (global super-buckets, PUSH_Y); plain coalesced 8-byte stores into peer memory
+__global__ void __launch_bounds__(256)
+k_shard_push(const __grid_constant__ ShardGeom G, Store src, const __grid_constant__ ShardPeers P)
+{
+    const uint32_t g = blockIdx.x;
+    uint32_t c = src.cursor[g];
+    if (c == 0) return;
+    const uint32_t room = src.room(g);
+    if (c > room) c = room;   // cannot happen after the exact regrouping run; the owner's count would then disagree and refuse
+    int q;
+    uint32_t j;
+    shard_owner(G, g, &q, &j);
+    if (*P.flags[q] & 1ull) return;
+    const unsigned long long* from = src.rec + src.base(g);
+    unsigned long long* to = P.rec[q] + P.recv_off[q][(size_t)j * G.world + G.rank];
+    for (uint32_t e = blockIdx.y * 256u + threadIdx.x; e < c; e += gridDim.y * 256u) to[e] = __ldcs(from + e);
+}
+
+}  // namespace kmgpu
+

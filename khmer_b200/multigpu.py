@@ -258,9 +258,10 @@ def split_by_bases(buf, off, max_bases):
 
 
 class ShardedGroup:
-    """An address-sharded sketch across ranks: every rank hashes its own reads and routes each counter update, grouped by the
-    owner's super-bucket, into the owner's HBM over NVLink peer memory (route); owners apply what they received (apply); every
-    rank counts which of its k-mers were new (count_new).  Only the barriers between the phases come from `comm`."""
+    """An address-sharded sketch across ranks: every rank hashes its own reads and groups the counter updates by the owners'
+    super-buckets (route), the owners lay out their receive arenas (offsets), the senders write their runs into the owners' HBM
+    over NVLink peer memory (push), owners apply what they received (apply); every rank counts which of its k-mers were new
+    (count_new).  Only the barriers between the phases come from `comm`."""
 
     def __init__(self, shard, comm=None, device=None):
         self.shard = shard
@@ -283,11 +284,18 @@ class ShardedGroup:
         runs = split_by_bases(buf, off, self.shard.max_positions)
         rounds = max(int.from_bytes(p, "little") for p in self.comm.all_gather_bytes(len(runs).to_bytes(8, "little")))
         kmers = 0
+        empty = (np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
         for i in range(rounds):
             if i < len(runs):
                 r0, r1 = runs[i]
                 kmers += self.shard.route((buf, off[r0:r1 + 1]), clean=clean)
-            self.barrier()          # every update of this round sits in its owner's store
+            else:
+                self.shard.route(empty, clean=clean)      # a rank without reads left still posts its (zero) counts
+            self.barrier()          # every owner knows what it will be sent
+            self.shard.offsets()
+            self.barrier()          # every sender can read where its runs go
+            self.shard.push()
+            self.barrier()          # every update of this round sits in its owner's arena
             self.shard.apply()
             self.barrier()          # every owner has marked the new positions of the round
             self.shard.count_new()

@@ -48,6 +48,12 @@ def test_sharded_equals_single_sketch(cls, k, world):
                 # the stream order of a round is rank 0's reads, then rank 1's, ...: what the single sketch is fed
                 lo, _ = shard_range(len(reads), r, world)
                 okmers += o.consume_reads(reads[lo + a: lo + b])
+            else:
+                shards[r].route((np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64)))
+        for r in range(world):
+            shards[r].offsets()
+        for r in range(world):
+            shards[r].push()
         for r in range(world):
             shards[r].apply()
         for r in range(world):
