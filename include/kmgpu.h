@@ -260,7 +260,7 @@ int kmgpu_first_touch_resolve(kmgpu_t* h, uint64_t* n_new_out, uint64_t* n_local
  * stream order is rank 0's reads, then rank 1's, ...), so the first toucher of a bin is decided across ranks and n_unique_kmers
  * is exact: it equals one sketch fed the rounds in that order.  Heavily repeated k-mers cannot overflow anything (regions are
  * exact); a round is refused (KMGPU_ENOMEM from kmgpu_shard_apply on that rank, nothing applied there) only if one owner is sent
- * more than 1.5 x its average share of a full round.
+ * more than 1.5 x what its share of the bins receives on average in a full round.
  * Table bytes and n_occupied are exact (concatenated slices / summed counters equal the single sketch); n_unique_kmers is the
  * sum of the ranks' shares (kmgpu_shard_stats); bigcount is not maintained in this mode.  The saved table is the
  * concatenation of the ranks' slices in rank order (kmgpu_shard_slice + the local sketch's kmgpu_download_table). */

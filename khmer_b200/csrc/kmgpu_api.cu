@@ -3098,9 +3098,17 @@ extern "C" int kmgpu_shard_create(int storage, int hash, int ksize, int n_tables
             return fail(KMGPU_EUNSUPPORTED, "slices of this size cannot be grouped");
         }
     }
-    // the arena: what all ranks together send an owner in a round is N x max_positions records on average; half as much again
-    // for owners that hold more than their share of the k-mers (a round that still does not fit is refused, see kmgpu_shard_offsets)
-    s->arena = (uint64_t)n_tables * max_positions * 3 / 2 + 4096;
+    // the arena: what all ranks together send an owner in a full round is (its share of the bins) x world x max_positions records
+    // on average; half as much again for owners whose bins are hit more often than others' (a round that still does not fit is
+    // refused, see kmgpu_shard_offsets)
+    {
+        double share = 0;   // the part of every table this rank owns, summed over the tables (N / world when the slices are even)
+        for (int i = 0; i < n_tables; i++) {
+            const uint64_t lo = std::min<uint64_t>(full_sizes[i], s->slice[i] * rank), hi = std::min<uint64_t>(full_sizes[i], s->slice[i] * (rank + 1));
+            share += (double)(hi - lo) / (double)full_sizes[i];
+        }
+        s->arena = (uint64_t)(1.5 * share * (double)world * (double)max_positions) + 4096;
+    }
     if (uint64_t f = env_u64("KMGPU_SHARD_ARENA", 0)) s->arena = f;   // tests
     const size_t nb_words = (size_t)world * max_positions / 32;
     const size_t n_dem = (size_t)s->n_sb_local * world;

@@ -54,16 +54,7 @@ struct Store {
     __device__ __forceinline__ uint32_t room(uint32_t p) const { return off ? (uint32_t)(off[p - p0 + 1] - off[p - p0]) : cap; }
 };
 
-// address-sharded sketches: where rank r's super-bucket regions live (peer memory over NVLink), see k_part MODE 3
-constexpr int MAX_WORLD = 16;
-struct ShardRoute {
-    unsigned long long* rec[MAX_WORLD];      // super-bucket store of every rank
-    uint32_t* cursor[MAX_WORLD];             // its cursors
-    unsigned long long* flags[MAX_WORLD];    // its overflow word
-    uint64_t slice[G_MAXT];                  // bins of table i held by every rank (the last rank may use fewer)
-    uint64_t slice_magic[G_MAXT];
-    int world;
-};
+constexpr int MAX_WORLD = 16;   // ranks of an address-sharded sketch
 
 // ---- bulk asynchronous copies + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,9 +104,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   MODE 0  stream -> buckets            partition = bin >> 15            record = position << 15 | bin & 0x7FFF
 //   MODE 1  stream -> super-buckets      partition = bin >> 27            record = position << 27 | bin & 0x7FFFFFF
 //   MODE 2  super-bucket -> its buckets  partition = (rec >> 15) & 0xFFF  record = position << 15 | bin & 0x7FFF
-//   MODE 3  stream -> the super-buckets of the rank that owns the bin (address-sharded sketches): partition = owner *
-//           super-buckets per rank + (bin within the owner's slice >> 27); the runs are written straight into the owner's
-//           store over NVLink peer memory, one remote atomicAdd per (CTA, partition) reserves them — the k-mer all-to-all
+//   (address-sharded sketches group with MODE 1 over the FULL tables and send whole super-bucket runs to their owners,
+//   section 8; writing every CTA's short runs straight into peer memory — one remote atomicAdd per (CTA, partition) — was
+//   measured 3x slower over NVLink than the exchange of whole runs)
 //
 //   SRC 0: the k-mers are hashed here from the 2-bit stream (TwoBit);  SRC 1: 64-bit hashes precomputed by k_hash64
 //   (Murmur: hashing 2 x k letters per table would dominate) or supplied by the caller (kmgpu_add_hashes).
@@ -206,12 +197,12 @@ __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t
 // BPT: consecutive partitions per thread in the scan; the launch picks the smallest instantiation with BPT * NTHR >= the
 // number of partitions, so that every thread has a share (and no registers are held for partitions that do not exist)
 template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP, int BPT>
-__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || MODE == 3 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
-k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P, const __grid_constant__ ShardRoute R)
+__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
+k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P)
 {
-    constexpr bool WIDE = MODE == 1 || MODE == 3 || WIDEP;
+    constexpr bool WIDE = MODE == 1 || WIDEP;
     constexpr int PER = T / NTHR;
-    constexpr bool SBMODE = MODE == 1 || MODE == 3;            // partitions are super-buckets
+    constexpr bool SBMODE = MODE == 1;                         // partitions are super-buckets
     const int SB_SHIFT = A.L.sb_shift, SB_BIN_SHIFT = BKT_SHIFT + SB_SHIFT;
     const int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;          // payload bits of the records written
     extern __shared__ __align__(16) unsigned char pt_raw[];
@@ -253,7 +244,6 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         } else {
             np = A.L.first_sb[t + 1] - A.L.first_sb[t];
             cur0 = A.L.first_sb[t];
-            if (MODE == 3) np *= (uint32_t)R.world;
         }
         if (p0 >= A.in.n_pos) return;
     }
@@ -289,17 +279,7 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
                     uint64_t bin = mod_magic(h, size, magic);
                     n_k++;
                     if (SBMODE) {
-                        uint32_t pid;
-                        if (MODE == 3) {
-                            // owner = bin / slice (same reciprocal trick as mod_magic), then the bin within the owner's slice
-                            uint64_t q = __umul64hi(bin, R.slice_magic[t]);
-                            uint64_t rem = bin - q * R.slice[t];
-                            if (rem >= R.slice[t]) { rem -= R.slice[t]; q++; }
-                            bin = rem;
-                            pid = (uint32_t)q * (A.L.first_sb[t + 1] - A.L.first_sb[t]) + (uint32_t)(bin >> SB_BIN_SHIFT);
-                        } else {
-                            pid = (uint32_t)(bin >> SB_BIN_SHIFT);
-                        }
+                        const uint32_t pid = (uint32_t)(bin >> SB_BIN_SHIFT);
                         key[j] = (uint32_t)bin & ((1u << SB_BIN_SHIFT) - 1);
                         if (j & 1) pid1[j >> 1] = (pid1[j >> 1] & 0xFFFFu) | (pid << 16); else pid1[j >> 1] = (pid1[j >> 1] & 0xFFFF0000u) | pid;
                     } else {
@@ -354,13 +334,7 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     for (int q = 0; q < BPT; q++) {
         const uint32_t b = tid * BPT + q;
         if (b < np) hist[b] = at;   // run start (the count has been read by its only reader, this thread)
-        if (MODE == 3) {
-            const uint32_t nsb = A.L.first_sb[t + 1] - A.L.first_sb[t];
-            const uint32_t owner = b / nsb;
-            gbase[q] = c[q] ? atomicAdd(R.cursor[owner] + cur0 + (b - owner * nsb), c[q]) : 0u;   // remote (NVLink) for other ranks
-        } else {
-            gbase[q] = c[q] ? atomicAdd(&A.dst.cursor[cur0 + b], c[q]) : 0u;   // in flight while the records are placed
-        }
+        gbase[q] = c[q] ? atomicAdd(&A.dst.cursor[cur0 + b], c[q]) : 0u;   // in flight while the records are placed
         at += c[q];
     }
     __syncthreads();
@@ -405,15 +379,8 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
         unsigned long long rec;
         if (MODE == 2) rec = ((unsigned long long)m.x << BKT_SHIFT) | (m.y & (BKT_BINS - 1));
         else rec = ((unsigned long long)(A.pos_base + p0 + (m.y & 0x3FFFu)) << PB) | m.x;
-        if (MODE == 3) {
-            const uint32_t nsb = A.L.first_sb[t + 1] - A.L.first_sb[t];
-            const uint32_t owner = pid / nsb;
-            if (idx < A.L.cap1) R.rec[owner][(unsigned long long)(cur0 + (pid - owner * nsb)) * A.L.cap1 + idx] = rec;
-            else atomicOr(R.flags[owner], 1ull);   // the owner refuses to apply a round with a region cut short
-        } else {
-            if (idx < A.dst.room(cur0 + pid)) A.dst.rec[A.dst.base(cur0 + pid) + idx] = rec;
-            else over = true;
-        }
+        if (idx < A.dst.room(cur0 + pid)) A.dst.rec[A.dst.base(cur0 + pid) + idx] = rec;
+        else over = true;
     }
     if (over) atomicOr(&A.ctrl->overflow, A.ovf_bit);
 }
