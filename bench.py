@@ -358,6 +358,20 @@ def file_leg(args, local_rank, repeats=3):
             pass
 
 
+def file_leg_subprocess(args, local_rank):
+    """The file leg in a process of its own, as a user's script would run it (load-into-counting.py is one process per file):
+    `python bench.py --file-leg` prints file_leg()'s dictionary."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--file-leg", "--reads", str(args.reads)],
+                       env=dict(os.environ, KMGPU_DEVICE=str(local_rank)), capture_output=True, text=True, timeout=1200)
+    for ln in reversed(r.stdout.strip().split("\n")):
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            d["process"] = "separate process (python bench.py --file-leg)"
+            return d
+    sys.stderr.write("[bench] file leg failed: %s\n" % r.stderr[-2000:])
+    return {"value": None, "error": r.stderr[-500:]}
+
+
 def secondary_legs(cabi, sk, host, dev, local_rank, n_query=400_000):
     """The read-side queries on the table the timed legs left behind (not the headline metric): per-read medians
     (Hashtable::get_median_count, hashtable.cc:299-328) and the abundance histogram (hashtable.cc:451-493), wall clock around the
@@ -482,6 +496,24 @@ def run_ours(args):
         host.append((buf, off, keep))
         dev.append(cabi.Batch((buf, off), K, clean=True, device=local_rank))
 
+    # the same batches as the host read feed hands them over (kmgpu_consume_packed): cleaned, 2 bits per base, pinned
+    packed = []
+    code_of = np.zeros(256, dtype=np.uint64)
+    for ch, v in ((b"T", 1), (b"C", 2), (b"G", 3)):
+        code_of[ch[0]] = v
+    shifts = np.uint64(62) - np.uint64(2) * np.arange(32, dtype=np.uint64)
+    for buf, off, _ in host:
+        n_words = (len(buf) + 31) // 32 + 2
+        tw = torch.zeros(n_words, dtype=torch.int64, pin_memory=True)
+        w = tw.numpy().view(np.uint64)
+        step = 32 << 20
+        for o in range(0, len(buf), step):
+            c = code_of[buf[o:o + step]]
+            if len(c) % 32:
+                c = np.concatenate([c, np.zeros(32 - len(c) % 32, dtype=np.uint64)])
+            w[o // 32: o // 32 + len(c) // 32] = (c.reshape(-1, 32) << shifts).sum(axis=1, dtype=np.uint64)
+        packed.append((w, off, tw))
+
     from khmer_b200.multigpu import ReplicaGroup
     group = ReplicaGroup(sk, dist if world > 1 else None, device=torch.device("cuda", local_rank))
     group.attach()
@@ -500,6 +532,9 @@ def run_ours(args):
         for s in range(first, first + n):
             if leg == "hbm":
                 kmers += sk.consume_batch(dev[s % P])
+            elif leg == "e2e_packed":
+                w, off, _ = packed[s % P]
+                kmers += sk.consume_packed(w, off)
             else:
                 buf, off, _ = host[s % P]
                 kmers += sk.consume_reads((buf, off), clean=True)
@@ -508,7 +543,7 @@ def run_ours(args):
 
     results = {}
     clocks = None
-    for leg in ("hbm", "e2e"):
+    for leg in ("hbm", "e2e", "e2e_packed"):
         sk.reset()
         run_steps(args.warmup, leg, 0)
         # start the timed region on a job boundary so every timed step sees the same table states
@@ -557,7 +592,7 @@ def run_ours(args):
     e2e_file = None
     secondary = None
     if world == 1 and not args.no_file:
-        e2e_file = file_leg(args, local_rank)
+        e2e_file = file_leg_subprocess(args, local_rank)
         secondary = secondary_legs(cabi, sk, host, dev, local_rank)
 
     checks = {}
@@ -616,6 +651,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": 64 * ((bases + (32 << 20) - 1) // (32 << 20)), "ms_per_step": e2e["ms"] / args.steps},
             "gpu_launches": int(hbm["launches"]), "clocks": clocks,
         }
+        pk = results["e2e_packed"]
+        line["e2e_packed"] = {"value": pk["kmers"] / (pk["ms"] * 1e-3), "unit": "k-mers/s", "h2d_bytes_per_step": bases // 4 + 8 * (R + 1),
+                              "api": "kmgpu_consume_packed: host buffers as the read feed's parser threads leave them (cleaned, 2 bits per base)"}
         if value_nobig is not None:
             line["value_bigcount_off"] = value_nobig
         if e2e_file is not None:
@@ -765,8 +803,11 @@ def main():
     ap.add_argument("--no-check", action="store_true", help="skip parity_check / merge_check")
     ap.add_argument("--no-file", action="store_true", help="skip the e2e_file and secondary legs")
     ap.add_argument("--check-reads", type=int, default=250_000, help="reads of the parity_check batch")
+    ap.add_argument("--file-leg", action="store_true", help="internal: run the e2e_file leg alone and print its dictionary")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.file_leg:
+        emit(file_leg(args, int(os.environ.get("KMGPU_DEVICE", "0"))))
+    elif args.impl == "reference":
         run_reference(args)
     elif args.mode == "sharded":
         run_sharded(args)

@@ -128,3 +128,49 @@ def test_sharded_one_process_per_gpu(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
                         "127.0.0.1", "--master-port", "29621", str(script)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SHARDED-IPC-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+REFUSE = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+from khmer_b200 import cabi
+import oracle_lib as ol
+from common import synth_reads
+sizes = ol.primes_near_x(4, 3000000)
+shards = [cabi.Shard(cabi.BYTE, cabi.TWOBIT, 20, sizes, r, 2, max_positions=200000) for r in range(2)]
+cabi.attach_local_shards(shards)
+big = synth_reads(1, 1000, 150, 40000)
+small = synth_reads(2, 3, 150, 40000)
+def round_(reads_by_rank):
+    errs = 0
+    for r in range(2):
+        shards[r].route(cabi.as_reads(reads_by_rank[r]))
+    for r in range(2):
+        shards[r].offsets()
+    for r in range(2):
+        shards[r].push()
+    for r in range(2):
+        try:
+            shards[r].apply()
+        except cabi.KmgpuError as e:
+            assert "arena" in str(e)
+            errs += 1
+    for r in range(2):
+        shards[r].count_new()
+    return errs
+assert round_([big, big]) == 2            # 2 x 131 k k-mers x 4 tables against arenas of 20000 records: both owners refuse
+assert sum(s.stats()[0] for s in shards) == 0
+assert round_([small, small]) == 0        # the next round is taken as if nothing had happened
+o = ol.Oracle("Countgraph", 20, sizes)
+o.consume_reads(small); o.consume_reads(small)
+assert sum(s.stats()[0] for s in shards) == o.n_occupied() and sum(s.stats()[1] for s in shards) == o.n_unique_kmers()
+print("REFUSE-OK")
+'''
+
+
+def test_sharded_round_larger_than_the_arena_is_refused(tmp_path):
+    script = tmp_path / "refuse.py"
+    script.write_text(REFUSE % {"root": ROOT})
+    r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, KMGPU_SHARD_ARENA="20000"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REFUSE-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
