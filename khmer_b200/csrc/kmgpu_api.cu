@@ -3462,7 +3462,7 @@ extern "C" int kmgpu_shard_apply(kmgpu_shard_t* s)
         s->G.wide = s->G.L.cap > 65535;
         s->G.sparse = s->G.sparse && s->G.L.cap <= SPARSE_MAX_RECORDS;
     }
-    h->n_occupied += h->h_ctrl->n_z0;
+    h->n_occupied += h->h_ctrl->n_new_t[0];   // the apply kernels of the grouped path count newly occupied bins per table
     CK(cudaMemsetAsync(s->demand, 0, n_dem * 4, st));   // ranks without reads in a later round post nothing for tables they do not reach
     CK(cudaStreamSynchronize(st));
     h->satbits_valid = false;

@@ -680,11 +680,7 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     }
     __syncthreads();
     if (tid == 0) {
-        if (s_tot[0]) {
-            atomicAdd(&ctrl->n_zbits, (unsigned long long)s_tot[0]);
-            atomicAdd(&ctrl->n_new_t[t], (unsigned long long)s_tot[0]);
-            if (t == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)s_tot[0]);
-        }
+        if (s_tot[0]) atomicAdd(&ctrl->n_new_t[t], (unsigned long long)s_tot[0]);   // the host sums these (any table / table 0)
         if (s_tot[1]) atomicAdd(&ctrl->n_sat, (unsigned long long)s_tot[1]);
         if (s_tot[2]) atomicAdd(&ctrl->n_cross, (unsigned long long)s_tot[2]);
     }
@@ -745,67 +741,112 @@ k_apply_sparse(const __grid_constant__ SketchDev S, const __grid_constant__ Grou
     }
     __syncthreads();
     unsigned n_new = 0, n_sat = 0, n_cross = 0;
-    for (uint32_t s = tid; s < slots; s += 128) {
-        if (!hk[s]) continue;
-        const uint64_t bin = bin0 + (hk[s] - 1);
-        const uint32_t m = hc[s];
-        uint32_t before;
-        if (KIND == BIT) {
-            uint32_t* word = reinterpret_cast<uint32_t*>(table) + (bin >> 5);
-            const uint32_t bit = 1u << (bin & 31);
-            before = (atomicOr(word, bit) & bit) ? 1u : 0u;
-        } else {
-            constexpr uint32_t CAP = KIND == BYTE ? 255u : 15u;
-            uint32_t* word;
-            uint32_t sh;
-            if (KIND == BYTE) {
-                word = reinterpret_cast<uint32_t*>(table + (bin & ~3ull));
-                sh = (uint32_t)(bin & 3) * 8;
+    // every distinct bin: read its word, compare-and-swap the new value in.  Four slots per thread and round, all loads issued
+    // before the first is used and all first swaps before the first is checked: the two DRAM round trips of an update overlap
+    // with those of the thread's other slots instead of queueing behind them.
+    constexpr int U = 4;
+    constexpr uint32_t CAP = KIND == BYTE ? 255u : KIND == NIBBLE ? 15u : 1u;
+    for (uint32_t s0 = 0; s0 < slots; s0 += 128 * U) {
+        uint32_t* word[U];
+        uint32_t sh[U], cur[U], m[U], before[U], pos[U];
+        uint64_t bin[U];
+        bool act[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const uint32_t sl = s0 + j * 128 + tid;
+            act[j] = sl < slots && hk[sl] != 0;
+            word[j] = nullptr;
+            sh[j] = cur[j] = m[j] = before[j] = pos[j] = 0;
+            bin[j] = 0;
+            if (!act[j]) continue;
+            bin[j] = bin0 + (hk[sl] - 1);
+            m[j] = hc[sl];
+            pos[j] = hp[sl];
+            if (KIND == BIT) {
+                word[j] = reinterpret_cast<uint32_t*>(table) + (bin[j] >> 5);
+                sh[j] = (uint32_t)(bin[j] & 31);
+            } else if (KIND == BYTE) {
+                word[j] = reinterpret_cast<uint32_t*>(table + (bin[j] & ~3ull));
+                sh[j] = (uint32_t)(bin[j] & 3) * 8;
             } else {
-                const uint64_t byte = bin >> 1;
-                word = reinterpret_cast<uint32_t*>(table + (byte & ~3ull));
-                sh = (uint32_t)(byte & 3) * 8 + ((bin & 1) ? 0 : 4);
+                const uint64_t byte = bin[j] >> 1;
+                word[j] = reinterpret_cast<uint32_t*>(table + (byte & ~3ull));
+                sh[j] = (uint32_t)(byte & 3) * 8 + ((bin[j] & 1) ? 0 : 4);
             }
-            uint32_t cur = __ldcg(word);
-            while (true) {
-                before = (cur >> sh) & CAP;
-                const uint32_t tt = before + m, nv = tt > CAP ? CAP : tt;
-                if (nv == before) break;
-                const uint32_t seen = atomicCAS(word, cur, (cur & ~(CAP << sh)) | (nv << sh));
-                if (seen == cur) break;
-                cur = seen;
+            if (KIND != BIT) cur[j] = __ldcg(word[j]);
+        }
+        if (KIND == BIT) {
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (act[j]) before[j] = (atomicOr(word[j], 1u << sh[j]) >> sh[j]) & 1u;
+        } else {
+            uint32_t seen[U];
+            bool pend[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                pend[j] = false;
+                seen[j] = 0;
+                if (!act[j]) continue;
+                before[j] = (cur[j] >> sh[j]) & CAP;
+                const uint32_t tt = before[j] + m[j], nv = tt > CAP ? CAP : tt;
+                if (nv == before[j]) continue;
+                seen[j] = atomicCAS(word[j], cur[j], (cur[j] & ~(CAP << sh[j])) | (nv << sh[j]));
+                pend[j] = true;
             }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                if (!pend[j] || seen[j] == cur[j]) continue;
+                uint32_t c = seen[j];   // somebody else changed the word in between (a neighbouring bin): the usual loop
+                while (true) {
+                    before[j] = (c >> sh[j]) & CAP;
+                    const uint32_t tt = before[j] + m[j], nv = tt > CAP ? CAP : tt;
+                    if (nv == before[j]) break;
+                    const uint32_t sn = atomicCAS(word[j], c, (c & ~(CAP << sh[j])) | (nv << sh[j]));
+                    if (sn == c) break;
+                    c = sn;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            if (!act[j]) continue;
             if (KIND == BYTE) {
-                const uint32_t tt = before + m;
+                const uint32_t tt = before[j] + m[j];
                 n_sat += tt > 255u;
-                if (tt >= 255u && before < 255u) {
+                if (tt >= 255u && before[j] < 255u) {
                     n_cross++;
                     if (want_cross) {
                         unsigned long long at = atomicAdd(&ctrl->n_events, 1ull);
-                        if (at < list_cap) binlist[at] = BL_CROSS | ((unsigned long long)before << 48) | ht_key(bin, t);
+                        if (at < list_cap) binlist[at] = BL_CROSS | ((unsigned long long)before[j] << 48) | ht_key(bin[j], t);
                     }
                 }
-                if (want_cross && tt >= 255u) atomicOr(reinterpret_cast<uint32_t*>(sb.t[t]) + (bin >> 5), 1u << (bin & 31));
+                if (want_cross && tt >= 255u) atomicOr(reinterpret_cast<uint32_t*>(sb.t[t]) + (bin[j] >> 5), 1u << (bin[j] & 31));
+            }
+            if (before[j] == 0) {
+                n_new++;
+                atomicOr(&newbits[pos[j] >> 5], 1u << (pos[j] & 31));
+                if (newmask) atomicOr(&newmask[pos[j]], 1u << t);
             }
         }
-        if (before == 0) {
-            n_new++;
-            const uint32_t p = hp[s];
-            atomicOr(&newbits[p >> 5], 1u << (p & 31));
-            if (newmask) atomicOr(&newmask[p], 1u << t);
-        }
     }
+    // one update of the chunk's counters per CTA (millions of CTAs adding to the same few words would queue at their L2 slice);
+    // the host derives "bins newly occupied in any table / in table 0" from the per-table counts
+    __shared__ unsigned s_tot[3];
+    if (tid < 3) s_tot[tid] = 0;
+    __syncthreads();
     n_new = __reduce_add_sync(0xffffffffu, n_new);
     n_sat = __reduce_add_sync(0xffffffffu, n_sat);
     n_cross = __reduce_add_sync(0xffffffffu, n_cross);
     if ((tid & 31) == 0) {
-        if (n_new) {
-            atomicAdd(&ctrl->n_zbits, (unsigned long long)n_new);
-            atomicAdd(&ctrl->n_new_t[t], (unsigned long long)n_new);
-            if (t == 0) atomicAdd(&ctrl->n_z0, (unsigned long long)n_new);
-        }
-        if (n_sat) atomicAdd(&ctrl->n_sat, (unsigned long long)n_sat);
-        if (n_cross) atomicAdd(&ctrl->n_cross, (unsigned long long)n_cross);
+        if (n_new) atomicAdd(&s_tot[0], n_new);
+        if (n_sat) atomicAdd(&s_tot[1], n_sat);
+        if (n_cross) atomicAdd(&s_tot[2], n_cross);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_tot[0]) atomicAdd(&ctrl->n_new_t[t], (unsigned long long)s_tot[0]);
+        if (s_tot[1]) atomicAdd(&ctrl->n_sat, (unsigned long long)s_tot[1]);
+        if (s_tot[2]) atomicAdd(&ctrl->n_cross, (unsigned long long)s_tot[2]);
     }
 }
 
