@@ -533,31 +533,37 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
     constexpr int RIF = 16;   // records in flight per thread
     constexpr uint32_t ITER_REC = RIF * NTHR, CLAMP_EVERY = 32768u / ITER_REC;
     for (uint32_t e0 = 0; e0 < n; e0 += ITER_REC) {
-        unsigned long long v[RIF];
+        // four records per thread in flight at a time (a lightly loaded bucket ends after the first group: no predicated-off
+        // copies of the loop body for records that do not exist)
 #pragma unroll
-        for (int j = 0; j < RIF; j++) {
-            uint32_t e = e0 + j * NTHR + tid;
-            // the parts of a bucket run side by side and read the same records: the first reader brings them into L2 for the others
-            v[j] = e < n ? (SPLIT == 1 ? __ldcs(src + e) : __ldg(src + e)) : ~0ull;
-        }
+        for (int jj = 0; jj < RIF; jj += 4) {
+            if (e0 + (uint32_t)jj * NTHR >= n) break;
+            unsigned long long v[4];
 #pragma unroll
-        for (int j = 0; j < RIF; j++) {
-            if (v[j] == ~0ull) continue;
-            uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
-            if (SPLIT > 1) {
-                if (lb / SUB_BINS != sub) continue;
-                lb &= SUB_BINS - 1;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t e = e0 + (uint32_t)(jj + j) * NTHR + tid;
+                // the parts of a bucket run side by side and read the same records: the first reader brings them into L2 for the others
+                v[j] = e < n ? (SPLIT == 1 ? __ldcs(src + e) : __ldg(src + e)) : ~0ull;
             }
-            if (KIND == BIT) {
-                // a Bloom bit that is set already changes nothing
-                if (!gate || slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
-            } else if (gate) {
-                const uint32_t was = atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
-                if (!((lb & 1) ? was >> 31 : (was >> 15) & 1u)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
-            } else {
-                // ungated: both updates leave at once, nothing waits for a result (the sweep ignores positions of bins that were occupied)
-                atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
-                atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (v[j] == ~0ull) continue;
+                uint32_t lb = (uint32_t)v[j] & (BKT_BINS - 1);
+                if (SPLIT > 1) {
+                    if (lb / SUB_BINS != sub) continue;
+                    lb &= SUB_BINS - 1;
+                }
+                if (KIND == BIT) {
+                    // a Bloom bit that is set already changes nothing
+                    if (!gate || slice_empty<KIND>(slice, lb)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+                } else if (gate) {
+                    const uint32_t was = atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+                    if (!((lb & 1) ? was >> 31 : (was >> 15) & 1u)) atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+                } else {
+                    // ungated: both updates leave at once, nothing waits for a result (the sweep ignores positions of bins that were occupied)
+                    atomicAdd(&cnt[lb >> 1], (lb & 1) ? 0x10000u : 1u);
+                    atomicMin(&minpos[lb], (uint32_t)(v[j] >> BKT_SHIFT));
+                }
             }
         }
         // More records than a lane can count (15 bits when bit 15 is the "was occupied" flag, else 16): clamp every lane after each
@@ -611,16 +617,32 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
             const uint64_t old64 = *reinterpret_cast<const uint64_t*>(slice + (size_t)g * 8);
             uint64_t new64 = old64;
             unsigned fullm = 0;
+            // only the lanes that were touched (in a lightly loaded bucket one or two of the eight): a loop over the set bits
+            // of a mask instead of eight predicated copies of the update
+            unsigned nz = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                if (!m) continue;
+            for (int j = 0; j < 8; j++) nz |= (unsigned)(((cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) != 0) << j;
+            auto bump = [&](int j, uint32_t m) {
                 uint32_t s = (uint32_t)(old64 >> (8 * j)) & 255u, tt = s + m, nv = tt > 255u ? 255u : tt;
                 new64 = (new64 & ~(255ull << (8 * j))) | ((uint64_t)nv << (8 * j));
                 newm |= (unsigned)(s == 0) << j;
                 n_sat += tt > 255u;
                 crossm |= (unsigned)(tt >= 255u && s < 255u) << j;
                 fullm |= (unsigned)(nv == 255u) << j;
+            };
+            if (__popc(nz) > 3) {   // a well-filled group: the unrolled form (constant shifts)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                    if (m) bump(j, m);
+                }
+            } else {
+                while (nz) {
+                    const int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t wj = j < 2 ? c4.x : j < 4 ? c4.y : j < 6 ? c4.z : c4.w;   // (selects: no dynamically indexed array)
+                    bump(j, (wj >> ((j & 1) * 16)) & 0xFFFFu);
+                }
             }
             *reinterpret_cast<uint64_t*>(slice + (size_t)g * 8) = new64;
             if (want_cross && fullm) {
@@ -641,14 +663,28 @@ k_apply2(const __grid_constant__ SketchDev S, const __grid_constant__ GroupLayou
         } else {
             const uint32_t old32 = *reinterpret_cast<const uint32_t*>(slice + (size_t)g * 4);
             uint32_t new32 = old32;
+            unsigned nz = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                if (!m) continue;
+            for (int j = 0; j < 8; j++) nz |= (unsigned)(((cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) != 0) << j;
+            auto bump = [&](int j, uint32_t m) {
                 const uint32_t sh = (j >> 1) * 8 + ((j & 1) ? 0 : 4);   // even bin -> high nibble
                 uint32_t s = (old32 >> sh) & 15u, tt = s + m, nv = tt > 15u ? 15u : tt;
                 new32 = (new32 & ~(15u << sh)) | (nv << sh);
                 newm |= (unsigned)(s == 0) << j;
+            };
+            if (__popc(nz) > 3) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t m = (cw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                    if (m) bump(j, m);
+                }
+            } else {
+                while (nz) {
+                    const int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t wj = j < 2 ? c4.x : j < 4 ? c4.y : j < 6 ? c4.z : c4.w;
+                    bump(j, (wj >> ((j & 1) * 16)) & 0xFFFFu);
+                }
             }
             *reinterpret_cast<uint32_t*>(slice + (size_t)g * 4) = new32;
         }
