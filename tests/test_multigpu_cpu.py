@@ -131,3 +131,76 @@ def test_replica_group_socket_rendezvous_world2(tmp_path):
     assert open(out).read() == "ok"
     ops = [ln.split()[1] for ln in open(log).read().split("\n") if ln]
     assert ops[:2] == ["rs", "rs"] and ops[2:4] == ["ag", "ag"] and ops[4:] == ["detach", "detach"]
+
+
+class StubShard:
+    """Records what ShardedGroup asks of a shard (the protocol of a round: route | offsets | push | apply | count_new)."""
+
+    def __init__(self, rank, log, max_positions):
+        self.rank, self.log, self.max_positions = rank, log, max_positions
+        self.routed = []
+
+    def _w(self, what):
+        with open(self.log, "a") as fh:
+            fh.write("%d %s\n" % (self.rank, what))
+
+    def ipc_export(self):
+        return np.full(64 * 5, self.rank + 1, dtype=np.uint8)
+
+    def ipc_attach(self, handles):
+        self.handles = np.array(handles)
+
+    def route(self, reads, clean=True):
+        buf, off = reads
+        self.routed.append(len(off) - 1)
+        self._w("route")
+        return int(off[-1] - off[0])
+
+    def offsets(self):
+        self._w("offsets")
+
+    def push(self):
+        self._w("push")
+
+    def apply(self):
+        self._w("apply")
+
+    def count_new(self):
+        self._w("count_new")
+
+    def stats(self):
+        return 10 + self.rank, 100 + self.rank, 0
+
+
+def _sharded_worker(rank, world, port, log, out):
+    from khmer_b200.multigpu import ShardedGroup, SocketComm
+    comm = SocketComm(rank=rank, world=world, addr="127.0.0.1", port=port)
+    sh = StubShard(rank, log, max_positions=1000)
+    g = ShardedGroup(sh, comm)
+    g.attach()
+    assert sh.handles.shape == (world * 64 * 5,)
+    # rank 0 has three rounds of reads, rank 1 a single one: it must still take part in rounds 2 and 3 with empty input
+    n_reads = 30 if rank == 0 else 8
+    reads = ["ACGT" * 25] * n_reads
+    got = g.consume_reads(reads)
+    assert got == 100 * n_reads
+    assert sh.routed == ([10, 10, 10] if rank == 0 else [8, 0, 0])
+    assert g.stats() == (21, 201)
+    comm.close()
+    if rank == 0:
+        open(out, "w").write("ok")
+
+
+def test_sharded_group_protocol_world2(tmp_path):
+    """every phase of a round is finished on all ranks before the next one starts anywhere (barriers), and a rank that has run
+    out of reads keeps posting empty routes"""
+    log, out = str(tmp_path / "log"), str(tmp_path / "out")
+    port = 32500 + (os.getpid() % 500)
+    mp.spawn(_sharded_worker, args=(2, port, log, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+    ops = [ln.split()[1] for ln in open(log).read().split("\n") if ln]
+    want = []
+    for _ in range(3):
+        for phase in ("route", "offsets", "push", "apply", "count_new"):
+            want += [phase, phase]
+    assert ops == want
