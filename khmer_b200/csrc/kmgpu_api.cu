@@ -2353,6 +2353,17 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     uint64_t W = W_fixed ? std::max<uint64_t>(2, W_fixed) : 32768;
     uint64_t n_windows = 0;
     const uint64_t unsure0 = h->n_norm_unsure, rounds0 = h->n_norm_rounds;
+    // KMGPU_DEBUG: wall clock per phase (every phase ends in a synchronisation)
+    const bool dbg = env_u64("KMGPU_DEBUG", 0) != 0;
+    double t_phase[5] = {0, 0, 0, 0, 0};   // stage + first test, overlay test, in-between resolution, ingest of the kept reads, host loops
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = dbg ? now() : 0;
+    auto lap = [&](int i) {
+        if (!dbg) return;
+        const double t = now();
+        t_phase[i] += t - t_mark;
+        t_mark = t;
+    };
     const uint64_t max_bases = chunk_bases() / 2;
     Pred P0;
     memset(&P0, 0, sizeof P0);
@@ -2400,6 +2411,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
             al1.resize(nr);
             CK(cudaMemcpyAsync(al1.data(), h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            lap(0);
             // candidates: bundles with a read below the cutoff (a read without k-mers never makes its bundle a candidate)
             std::vector<uint8_t> cand(nr, 0);
             uint64_t cand_bases = 0, n_cand = 0;
@@ -2442,6 +2454,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                 al2.resize(nr);
                 CK(cudaMemcpyAsync(al2.data(), h->d_stat_b.p, nr, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                lap(1);
                 std::vector<uint8_t> sure(nr, 0), unsure(nr, 0);
                 uint64_t n_unsure = 0, up_total = 0;
                 for (uint32_t r = 0; r < nr;) {
@@ -2582,6 +2595,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                     }
                     for (uint32_t r = 0; r < nr; r++) keep[r] = state[r] == 1;
                 }
+                lap(2);
                 // 4. the kept reads are consumed in stream order (one ordinary ingest with a read mask)
                 uint64_t nk_reads = 0;
                 for (uint32_t r = 0; r < nr; r++) nk_reads += keep[r];
@@ -2594,17 +2608,21 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                     kmers_total += res.n_kmers;
                     kept_total += nk_reads;
                 }
+                lap(3);
             }
         }
         memcpy(keep_out + r0, keep.data(), nr);
+        lap(4);
         r0 = r1;
     }
     if (n_kept_out) *n_kept_out = kept_total;
     if (n_kmers_out) *n_kmers_out = kmers_total;
-    if (env_u64("KMGPU_DEBUG", 0))
-        fprintf(stderr, "[kmgpu] normalize_batch: %llu reads in %llu windows (last %llu reads), %llu in-between reads, %llu resolve rounds\n",
+    if (dbg)
+        fprintf(stderr, "[kmgpu] normalize_batch: %llu reads in %llu windows (last %llu reads), %llu in-between reads, %llu resolve rounds; "
+                        "seconds: first test %.3f, overlay test %.3f, in-between %.3f, ingest %.3f, other %.3f\n",
                 (unsigned long long)n_reads, (unsigned long long)n_windows, (unsigned long long)W,
-                (unsigned long long)(h->n_norm_unsure - unsure0), (unsigned long long)(h->n_norm_rounds - rounds0));
+                (unsigned long long)(h->n_norm_unsure - unsure0), (unsigned long long)(h->n_norm_rounds - rounds0), t_phase[0], t_phase[1], t_phase[2],
+                t_phase[3], t_phase[4]);
     return KMGPU_OK;
 }
 
