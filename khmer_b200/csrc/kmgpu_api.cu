@@ -2355,7 +2355,8 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     const uint64_t unsure0 = h->n_norm_unsure, rounds0 = h->n_norm_rounds;
     // KMGPU_DEBUG: wall clock per phase (every phase ends in a synchronisation)
     const bool dbg = env_u64("KMGPU_DEBUG", 0) != 0;
-    double t_phase[5] = {0, 0, 0, 0, 0};   // stage + first test, overlay test, in-between resolution, ingest of the kept reads, host loops
+    double t_phase[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // stage + first test, overlay test, in-between resolution, ingest of the kept reads,
+                                                          // host loops; 5..8: parts of the in-between resolution
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = dbg ? now() : 0;
     auto lap = [&](int i) {
@@ -2506,6 +2507,14 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                     const uint32_t n_up = (uint32_t)upos.size(), n_ub = (uint32_t)meta_start.size(), n_ur = (uint32_t)meta_read.size();
                     std::vector<uint8_t> state(nr, 0);
                     for (uint32_t r = 0; r < nr; r++) state[r] = sure[r] ? 1 : unsure[r] ? 2 : 0;
+                    double t_sub = dbg ? now() : 0;
+                    auto sub = [&](int i) {
+                        if (!dbg) return;
+                        const double t = now();
+                        t_phase[i] += t - t_sub;
+                        t_sub = t;
+                    };
+                    sub(5);   // host: the lists of the in-between bundles
                     if (n_up) {
                         const uint64_t slots2 = pow2_at_least(2 * (uint64_t)n_up * N);
                         if (slots2 > (1ull << 32)) return fail(KMGPU_EUNSUPPORTED, "normalize_batch: window too large");
@@ -2521,13 +2530,16 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                         pack.insert(pack.end(), meta_ur.begin(), meta_ur.end());
                         const size_t o_rd = pack.size();
                         pack.insert(pack.end(), meta_read.begin(), meta_read.end());
-                        CKR(h->d_upos.ensure(pack.size()));
-                        CKR(h->d_nslot.ensure((size_t)n_up * N));
-                        CKR(h->d_uc0.ensure((size_t)n_up * N));
-                        CKR(h->d_evkeys.ensure(slots2));
-                        CKR(h->d_ncnt.ensure(slots2));
-                        CKR(h->d_nfill.ensure(slots2));
-                        CKR(h->d_nstate.ensure(nr));
+                        // large calls: room for a typical window's in-between reads from the start (growing these buffers window
+                        // by window costs a cudaFree + cudaMalloc each time, milliseconds apiece on some hosts)
+                        const size_t fl = n_reads >= 100000 ? ((size_t)1 << 21) : 0;
+                        CKR(h->d_upos.ensure(std::max(pack.size(), fl + fl / 8)));
+                        CKR(h->d_nslot.ensure(std::max((size_t)n_up, fl) * N));
+                        CKR(h->d_uc0.ensure(std::max((size_t)n_up, fl) * N));
+                        CKR(h->d_evkeys.ensure(std::max<uint64_t>(slots2, pow2_at_least(2 * (uint64_t)fl * N))));
+                        CKR(h->d_ncnt.ensure(std::max<uint64_t>(slots2, pow2_at_least(2 * (uint64_t)fl * N))));
+                        CKR(h->d_nfill.ensure(std::max<uint64_t>(slots2, pow2_at_least(2 * (uint64_t)fl * N))));
+                        CKR(h->d_nstate.ensure(std::max<size_t>(nr, fl ? (size_t)1 << 17 : 0)));
                         CK(cudaMemcpyAsync(h->d_upos.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, st));
                         CK(cudaMemcpyAsync(h->d_nstate.p, state.data(), nr, cudaMemcpyHostToDevice, st));
                         CK(cudaMemsetAsync(h->d_evkeys.p, 0xFF, slots2 * 8, st));
@@ -2552,9 +2564,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                         h->all_launches += 3;
                         CK(cudaGetLastError());
                         CKR(read_ctrl(h));   // synchronises: the host vectors above may go
+                        sub(6);   // uploads, gather, counting pass of the hits
                         const uint64_t n_hits = h->h_ctrl->n_events;
                         if (n_hits >= (1ull << 32)) return fail(KMGPU_EUNSUPPORTED, "normalize_batch: window too large");
-                        CKR(h->d_nhits.ensure(std::max<uint64_t>(n_hits, 1)));
+                        CKR(h->d_nhits.ensure(std::max<uint64_t>(std::max<uint64_t>(n_hits, 1), 8 * (uint64_t)fl)));
                         if (H.kind == TWOBIT) k_norm_hits<TWOBIT, 0, 1><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_nfill.p, h->d_nhits.p);
                         else k_norm_hits<MURMUR, 0, 1><<<gt, THREADS, 0, st>>>(h->dev, H, inc, keys2, slots2 - 1, h->d_nfill.p, h->d_nhits.p);
                         h->all_launches += 1;
@@ -2573,6 +2586,8 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                         R.cutoff = cutoff;
                         R.cap = cap_c;
                         unsigned int* n_left = reinterpret_cast<unsigned int*>(&h->d_ctrl->n_events);
+                        if (dbg) CK(cudaStreamSynchronize(st));
+                        sub(7);   // fill pass of the hits
                         for (uint64_t round = 0;; round++) {
                             // two rounds per look at the counter (a round is a few microseconds, the look a round trip)
                             CK(cudaMemsetAsync(&h->d_ctrl->n_events, 0, sizeof(unsigned long long), st));
@@ -2588,6 +2603,7 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
                         }
                         CK(cudaMemcpyAsync(state.data(), h->d_nstate.p, nr, cudaMemcpyDeviceToHost, st));
                         CK(cudaStreamSynchronize(st));
+                        sub(8);   // rounds
                     } else {
                         // in-between bundles without a single k-mer cannot be "below": never kept (they were no candidates at all)
                         for (uint32_t r = 0; r < nr; r++)
@@ -2619,10 +2635,10 @@ extern "C" int kmgpu_normalize_batch(kmgpu_t* h, const char* seqs, const uint64_
     if (n_kmers_out) *n_kmers_out = kmers_total;
     if (dbg)
         fprintf(stderr, "[kmgpu] normalize_batch: %llu reads in %llu windows (last %llu reads), %llu in-between reads, %llu resolve rounds; "
-                        "seconds: first test %.3f, overlay test %.3f, in-between %.3f, ingest %.3f, other %.3f\n",
+                        "seconds: first test %.3f, overlay test %.3f, in-between %.3f (lists %.3f, gather + count %.3f, fill %.3f, rounds %.3f), ingest %.3f, other %.3f\n",
                 (unsigned long long)n_reads, (unsigned long long)n_windows, (unsigned long long)W,
                 (unsigned long long)(h->n_norm_unsure - unsure0), (unsigned long long)(h->n_norm_rounds - rounds0), t_phase[0], t_phase[1], t_phase[2],
-                t_phase[3], t_phase[4]);
+                t_phase[5], t_phase[6], t_phase[7], t_phase[8], t_phase[3], t_phase[4]);
     return KMGPU_OK;
 }
 

@@ -10,7 +10,7 @@ KMGPU_DEBUG=1 timeout 600 python tools/bench_configs.py NORM > $OUT/norm$i.json 
 cut -c1-400 $OUT/norm$i.json | tee -a $OUT/progress.txt
 grep normalize_batch $OUT/norm$i.err | tail -2 | tee -a $OUT/progress.txt
 done
-KMGPU_SPARSE=0 KMGPU_DEBUG=1 timeout 600 python tools/bench_configs.py NORM > $OUT/norm3.json 2> $OUT/norm3.err
-echo "-- KMGPU_SPARSE=0" | tee -a $OUT/progress.txt
-cut -c1-400 $OUT/norm3.json | tee -a $OUT/progress.txt
-grep normalize_batch $OUT/norm3.err | tail -1 | tee -a $OUT/progress.txt
+
+
+
+
