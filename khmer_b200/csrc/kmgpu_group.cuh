@@ -135,9 +135,11 @@ struct PartTile {
 };
 
 // WIDE: run bases kept in 32 bits (super-buckets; regions with exact offsets, which may hold more than 65535 records)
-__host__ __device__ constexpr size_t part_smem(int T, bool wide)
+// pcap: partitions the instantiation can sort into (BPT per thread): the histogram and the run bases take that many words each
+__host__ __device__ constexpr int part_cap(int bpt, int nthr) { return bpt * nthr < PART_MAXP ? bpt * nthr : PART_MAXP; }
+__host__ __device__ constexpr size_t part_smem(int T, bool wide, int pcap)
 {
-    return (size_t)T * 8 + (size_t)PART_MAXP * 4 * (wide ? 2 : 1) + (size_t)(T / 32 + TILE_PAD_WORDS) * 8 + (size_t)(T / 32) * 4 + 16;
+    return (size_t)T * 8 + (size_t)pcap * 4 * (wide ? 2 : 1) + (size_t)(T / 32 + TILE_PAD_WORDS) * 8 + (size_t)(T / 32) * 4 + 16;
 }
 
 // stage the tile's stream words and the bitmap of valid k-mer starts (cf. tile_begin, for tiles of T positions)
@@ -197,7 +199,7 @@ __device__ __forceinline__ void part_tile_begin(const Input& in, int k, uint32_t
 // BPT: consecutive partitions per thread in the scan; the launch picks the smallest instantiation with BPT * NTHR >= the
 // number of partitions, so that every thread has a share (and no registers are held for partitions that do not exist)
 template <int T, int NTHR, int MODE, int SRC, bool PRED, bool WIDEP, int BPT>
-__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || WIDEP) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(NTHR, (2 * part_smem(T, MODE == 1 || WIDEP, part_cap(BPT, NTHR)) <= 220 * 1024 && NTHR <= 512) ? 2 : 1)
 k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, const __grid_constant__ Pred P)
 {
     constexpr bool WIDE = MODE == 1 || WIDEP;
@@ -207,9 +209,10 @@ k_part(const __grid_constant__ PartArgs A, const __grid_constant__ SketchDev M, 
     const int PB = SBMODE ? SB_BIN_SHIFT : BKT_SHIFT;          // payload bits of the records written
     extern __shared__ __align__(16) unsigned char pt_raw[];
     uint2* stage = reinterpret_cast<uint2*>(pt_raw);                          // T slots, grouped by partition
-    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // PART_MAXP: count, then run start | cursor base << 16
-    uint32_t* gb32 = hist + PART_MAXP;                                        // WIDE only: 32-bit cursor bases
-    PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(hist + PART_MAXP * (WIDE ? 2 : 1));
+    constexpr int PCAP = part_cap(BPT, NTHR);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + T);                  // PCAP: count, then run start | cursor base << 16
+    uint32_t* gb32 = hist + PCAP;                                             // WIDE only: 32-bit cursor bases
+    PartTile<T>& tile = *reinterpret_cast<PartTile<T>*>(hist + PCAP * (WIDE ? 2 : 1));
     __shared__ uint32_t s_warp[32];
     const uint32_t tid = threadIdx.x;
     const uint32_t p0 = (MODE == 2 ? blockIdx.x % A.tiles_per_src : blockIdx.x) * (uint32_t)T;
