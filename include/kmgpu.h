@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KMGPU_ABI_VERSION 1
+#define KMGPU_ABI_VERSION 2 /* 2: batch normalization / trimming / new-flags, first-touch log, HLL registers, five-step sharded rounds */
 
 /* storage kinds — include/oxli/storage.hh: ByteStorage :480, NibbleStorage :241, BitStorage :92 */
 enum { KMGPU_BYTE = 0, KMGPU_NIBBLE = 1, KMGPU_BIT = 2 };
