@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(L, name), name
     L.kmgpu_abi_version.restype = ctypes.c_int
-    assert L.kmgpu_abi_version() == 1
+    assert L.kmgpu_abi_version() == 2
 
 
 def test_no_device_fails_loudly():
