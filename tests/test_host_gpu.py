@@ -375,6 +375,54 @@ def test_normalize_batch_reference_md5(datadir):
     assert kmers == sum(len(s) - 20 for (_, s), k in zip(recs, keep) if k)
 
 
+@pytest.mark.parametrize("cutoff,variable,z,want", [(2, False, 20, "9495801b282ff6b08961b685d12a954c"),
+                                                    (4, False, 20, "65596253b87ed8d5aeb14dc8cf5a7406"),
+                                                    (4, True, 15, "393805ac92e8bed31a374de9ee89ead8")])
+def test_trim_low_abund_reference_md5(datadir, cutoff, variable, z, want):
+    """scripts/trim-low-abund.py -k 21 -M 1e7 -C cutoff [-V -Z z] on simple-genome-reads.fa (tests/test_script_output.py:118-182):
+    the script's two passes (scripts/trim-low-abund.py:196-271, khmer/trimming.py:36-66) over this backend's get_median_count,
+    median_at_least, trim_on_abundance and consume write the records with the reference's md5 (the oracle reproduces all six
+    pinned md5s in tests/test_oracle.py)."""
+    kh = _kh()
+    recs, name = [], None
+    for ln in open(os.path.join(datadir, "simple-genome-reads.fa")).read().split("\n"):
+        if ln.startswith(">"):
+            name = ln[1:]
+        elif ln:
+            recs.append((name, ln))
+    g = kh.Countgraph(21, 1e7 / 4, 4)
+    k = 21
+
+    def trim_record(name, seq, cleaned):
+        if variable and not g.median_at_least(cleaned, z):
+            return (name, seq)
+        _, t = g.trim_on_abundance(cleaned, cutoff)
+        if t < k:
+            return None
+        return (name, seq if t == len(seq) else seq[:t])
+
+    out, saved = [], []
+    for name, seq in recs:
+        cleaned = seq.upper().replace("N", "A")
+        if g.get_median_count(cleaned)[0] >= z:
+            r = trim_record(name, seq, cleaned)
+            if r:
+                out.append(r)
+        else:
+            g.consume(cleaned)
+            saved.append((name, seq))
+    for name, seq in saved:
+        cleaned = seq.upper().replace("N", "A")
+        if not variable or g.median_at_least(cleaned, z):
+            r = trim_record(name, seq, cleaned)
+            if r:
+                out.append(r)
+        else:
+            out.append((name, seq))
+    text = "".join(">%s\n%s\n" % r for r in out)
+    assert hashlib.md5(text.encode()).hexdigest() == want
+
+
 def test_ascii_feed_still_matches(golden, datadir):
     """the host feed packs reads to 2 bits on the parser threads by default; KMGPU_FEED_PACKED=0 ships ASCII and packs on the device"""
     import subprocess, sys

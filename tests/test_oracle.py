@@ -268,3 +268,67 @@ def test_hll_registers_restatement_equals_reference(datadir):
     ref4 = ol.RefHLL(14, 20)
     ref4.consume_seqfile(os.path.join(datadir, "random-20-a.fa"))
     assert ref3.estimate() == ref4.estimate() > 0
+
+
+def _trim_low_abund(o, recs, k, cutoff, trim_at_coverage=20, variable=False):
+    """scripts/trim-low-abund.py:196-271 (Trimmer.pass1 / pass2) with khmer/trimming.py:36-66 (trim_record) and
+    Hashtable::trim_on_abundance (src/oxli/hashtable.cc:504-530), unpaired reads: records written, in the script's order"""
+    def trim_at(seq):
+        c = o.kmer_counts(seq)
+        if len(c) <= 1 or c[0] < cutoff:
+            return 0
+        for i in range(1, len(c)):
+            if c[i] < cutoff:
+                return k + i - 1
+        return len(seq)
+
+    def trim_record(name, seq, cleaned):
+        if variable and not o.median_at_least(cleaned, trim_at_coverage):
+            return (name, seq)
+        t = trim_at(cleaned)
+        if t < k:
+            return None
+        return (name, seq if t == len(seq) else seq[:t])
+
+    out, saved = [], []
+    for name, seq in recs:
+        cleaned = seq.upper().replace("N", "A")
+        if o.median(cleaned)[0] >= trim_at_coverage:
+            r = trim_record(name, seq, cleaned)
+            if r:
+                out.append(r)
+        else:
+            o.consume(cleaned)
+            saved.append((name, seq))
+    for name, seq in saved:
+        cleaned = seq.upper().replace("N", "A")
+        if not variable or o.median_at_least(cleaned, trim_at_coverage):
+            r = trim_record(name, seq, cleaned)
+            if r:
+                out.append(r)
+        else:
+            out.append((name, seq))
+    return out
+
+
+TRIM_MD5 = {(2, False, 20): "9495801b282ff6b08961b685d12a954c", (3, False, 20): "da36ec64e7d001470c04dc19af5b8635",
+            (4, False, 20): "65596253b87ed8d5aeb14dc8cf5a7406", (4, True, 20): "324871db807839f8bddd43548abcbeda",
+            (4, True, 25): "6ec4f9874262f3eaf98cab4910c428f5", (4, True, 15): "393805ac92e8bed31a374de9ee89ead8"}
+
+
+def test_trim_low_abund_script_md5s(datadir):
+    """the output md5s the reference pins for trim-low-abund.py -k 21 -M 1e7 on simple-genome-reads.fa
+    (tests/test_script_output.py:118-182: -C 2 / 3 / 4, -V, -V -Z 25, -V -Z 15), reproduced by the oracle's counts, medians and
+    consume under a restatement of the script's two passes"""
+    import hashlib
+    recs, name = [], None
+    for ln in open(os.path.join(datadir, "simple-genome-reads.fa")).read().split("\n"):
+        if ln.startswith(">"):
+            name = ln[1:]
+        elif ln:
+            recs.append((name, ln))
+    for (cutoff, variable, z), want in TRIM_MD5.items():
+        o = ol.Oracle("Countgraph", 21, ol.primes_near_x(4, int(1e7 / 4)))
+        out = _trim_low_abund(o, recs, 21, cutoff, z, variable)
+        text = "".join(">%s\n%s\n" % r for r in out)
+        assert hashlib.md5(text.encode()).hexdigest() == want, (cutoff, variable, z)
