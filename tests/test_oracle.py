@@ -270,7 +270,7 @@ def test_hll_registers_restatement_equals_reference(datadir):
     assert ref3.estimate() == ref4.estimate() > 0
 
 
-def _trim_low_abund(o, recs, k, cutoff, trim_at_coverage=20, variable=False):
+def _trim_low_abund(o, recs, k, cutoff, trim_at_coverage=20, variable=False, diginorm=None):
     """scripts/trim-low-abund.py:196-271 (Trimmer.pass1 / pass2) with khmer/trimming.py:36-66 (trim_record) and
     Hashtable::trim_on_abundance (src/oxli/hashtable.cc:504-530), unpaired reads: records written, in the script's order"""
     def trim_at(seq):
@@ -293,7 +293,10 @@ def _trim_low_abund(o, recs, k, cutoff, trim_at_coverage=20, variable=False):
     out, saved = [], []
     for name, seq in recs:
         cleaned = seq.upper().replace("N", "A")
-        if o.median(cleaned)[0] >= trim_at_coverage:
+        med = o.median(cleaned)[0]
+        if diginorm is not None and med >= diginorm:      # --diginorm: pass 1 drops reads at or above that coverage
+            continue
+        if med >= trim_at_coverage:
             r = trim_record(name, seq, cleaned)
             if r:
                 out.append(r)
@@ -318,7 +321,7 @@ TRIM_MD5 = {(2, False, 20): "9495801b282ff6b08961b685d12a954c", (3, False, 20): 
 
 def test_trim_low_abund_script_md5s(datadir):
     """the output md5s the reference pins for trim-low-abund.py -k 21 -M 1e7 on simple-genome-reads.fa
-    (tests/test_script_output.py:118-182: -C 2 / 3 / 4, -V, -V -Z 25, -V -Z 15), reproduced by the oracle's counts, medians and
+    (tests/test_script_output.py:73-182: -C 2 / 3 / 4, -V, -V -Z 25, -V -Z 15 and the --diginorm forms), reproduced by the oracle's counts, medians and
     consume under a restatement of the script's two passes"""
     import hashlib
     recs, name = [], None
@@ -332,3 +335,10 @@ def test_trim_low_abund_script_md5s(datadir):
         out = _trim_low_abund(o, recs, 21, cutoff, z, variable)
         text = "".join(">%s\n%s\n" % r for r in out)
         assert hashlib.md5(text.encode()).hexdigest() == want, (cutoff, variable, z)
+    # --diginorm (tests/test_script_output.py:73-112): -C 0 with coverage 20 / 15 equals normalize-by-median's output; -C 2, 15
+    for cutoff, dn, want in ((0, 20, "942e9024c25a8d85033d755d86aba4a3"), (0, 15, "0d1b4b9d4c76cb8cdeee5a98f6e70163"),
+                             (2, 15, "fa09d094a9e623639a34f772b04d766c")):
+        o = ol.Oracle("Countgraph", 21, ol.primes_near_x(4, int(1e7 / 4)))
+        out = _trim_low_abund(o, recs, 21, cutoff, 20, False, diginorm=dn)
+        text = "".join(">%s\n%s\n" % r for r in out)
+        assert hashlib.md5(text.encode()).hexdigest() == want, (cutoff, dn)
