@@ -342,3 +342,19 @@ def test_trim_low_abund_script_md5s(datadir):
         out = _trim_low_abund(o, recs, 21, cutoff, 20, False, diginorm=dn)
         text = "".join(">%s\n%s\n" % r for r in out)
         assert hashlib.md5(text.encode()).hexdigest() == want, (cutoff, dn)
+
+
+def test_count_median_script_rows(datadir):
+    """tests/test_scripts.py:465-481: count-median.py on test-abund-read-2.fa after load-into-counting -x 1e7 -N 2 -k 8 (bigcount):
+    rows 'seq,1001,1001.0,0.0,18' and '895:1:37:17593:9954/1,1,103.803741455,303.702941895,114' — median, and the float mean /
+    stddev rounded to nine places as the script prints them"""
+    reads = ol.read_fastx(os.path.join(datadir, "test-abund-read-2.fa"))
+    o = ol.Oracle("Countgraph", 8, ol.primes_near_x(2, int(1e7)))
+    o.set_use_bigcount(True)
+    o.consume_reads(reads, clean=True)
+    rows = set()
+    for r in (reads[0], reads[1]):
+        seq = r.upper().replace("N", "A")
+        med, avg, sd = o.median(seq)
+        rows.add("%d,%s,%s,%d" % (med, round(float(avg), 9), round(float(sd), 9), len(seq)))
+    assert rows == {"1001,1001.0,0.0,18", "1,103.803741455,303.702941895,114"}
