@@ -358,3 +358,29 @@ def test_count_median_script_rows(datadir):
         med, avg, sd = o.median(seq)
         rows.add("%d,%s,%s,%d" % (med, round(float(avg), 9), round(float(sd), 9), len(seq)))
     assert rows == {"1001,1001.0,0.0,18", "1,103.803741455,303.702941895,114"}
+
+
+def test_filter_abund_script_expectations(datadir):
+    """tests/test_filter_abund.py:42-66, :171-186: filter-abund(-single).py -k 17 (cutoff 2) on test-abund-read-2.fa: 98 unique k-mers;
+    every read kept is cut down to GGTTGACGGGGCTCAGGG (Hashtable::trim_on_abundance, src/oxli/hashtable.cc:504-530)"""
+    reads = ol.read_fastx(os.path.join(datadir, "test-abund-read-2.fa"))
+    k = 17
+    o = ol.Oracle("Countgraph", k, ol.primes_near_x(2, int(1e7)))
+    o.set_use_bigcount(True)
+    o.consume_reads(reads, clean=True)
+    assert o.n_unique_kmers() == 98
+    seqs = set()
+    for r in reads:
+        seq = r.upper().replace("N", "A")
+        c = o.kmer_counts(seq)
+        if len(c) <= 1 or c[0] < 2:
+            t = 0
+        else:
+            t = len(seq)
+            for i in range(1, len(c)):
+                if c[i] < 2:
+                    t = k + i - 1
+                    break
+        if t >= k:
+            seqs.add(r[:t])
+    assert seqs == {"GGTTGACGGGGCTCAGGG"}
