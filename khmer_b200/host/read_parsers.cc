@@ -523,6 +523,7 @@ private:
                 m.c_len = rest - 8;
                 m.crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
                 m.isize = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24);
+                if (m.isize > (1u << 20)) { error = true; break; }   // a BGZF member holds at most 64 KB: a damaged trailer
                 m.out_off = total;
                 total += m.isize;
                 mem.push_back(m);
