@@ -204,3 +204,34 @@ def test_sharded_group_protocol_world2(tmp_path):
         for phase in ("route", "offsets", "push", "apply", "count_new"):
             want += [phase, phase]
     assert ops == want
+
+
+def _sharded_worker_gloo(rank, world, port, log, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from khmer_b200.multigpu import ShardedGroup
+    sh = StubShard(rank, log, max_positions=500)
+    g = ShardedGroup(sh, dist)
+    g.attach()
+    n_reads = 4 if rank == 0 else 11                     # 1 round against 3: rank 0 posts two empty routes
+    assert g.consume_reads(["ACGT" * 25] * n_reads) == 100 * n_reads
+    assert sh.routed == ([4, 0, 0] if rank == 0 else [5, 5, 1])
+    assert g.stats() == (21, 201)
+    if rank == 0:
+        open(out, "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_sharded_group_protocol_gloo_world2(tmp_path):
+    """the same protocol over a torch.distributed (gloo) group"""
+    log, out = str(tmp_path / "log"), str(tmp_path / "out")
+    port = 29000 + (os.getpid() % 400)
+    mp.spawn(_sharded_worker_gloo, args=(2, port, log, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+    ops = [ln.split()[1] for ln in open(log).read().split("\n") if ln]
+    want = []
+    for _ in range(3):
+        for phase in ("route", "offsets", "push", "apply", "count_new"):
+            want += [phase, phase]
+    assert ops == want
